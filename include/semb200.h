@@ -1,0 +1,233 @@
+/*
+ * semb200.h -- C ABI of libsemb200.so: hand-written sm_100a kernels for the conv-stack
+ * hot path of BAMresearch/automatic-sem-image-segmentation (Release 1.2.0).
+ *
+ * The reference has no FFI of its own: every FLOP of its hot path is a Keras layer call
+ * that lands in torch.nn.functional on the torch backend.  The
+ * entry points below are therefore cut at exactly those library-call sites; each one
+ * names the reference call site(s) (file:line under Releases/Version 1.2.0/) whose
+ * arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, no torch types.  All tensor pointers are DEVICE
+ *     pointers owned by the caller; the library never allocates or frees tensor memory.
+ *   - activations are NHWC with a channel pitch (elements) and a channel offset, so a
+ *     tensor can be a channel slice of a wider buffer (skip-concat without a copy).
+ *   - `dtype` selects the activation storage type: SEMB_F32 (parity mode) or SEMB_BF16
+ *     (throughput mode).  Weights, statistics, gradients of weights are always fp32.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous.
+ *   - every function returns SEMB_OK (0) or a negative SEMB_E* code; the message is
+ *     available from semb_last_error() (thread-local).
+ */
+#ifndef SEMB200_H
+#define SEMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEMB_VERSION 100
+
+enum { SEMB_OK = 0, SEMB_ESHAPE = -1, SEMB_EALIGN = -2, SEMB_EARCH = -3, SEMB_EWORKSPACE = -4, SEMB_ECUDA = -5 };
+enum { SEMB_F32 = 0, SEMB_BF16 = 1 };
+enum { SEMB_PAD_ZERO = 0, SEMB_PAD_REFLECT = 1 };
+enum { SEMB_ACT_NONE = 0, SEMB_ACT_RELU = 1, SEMB_ACT_LEAKY = 2, SEMB_ACT_SIGMOID = 3, SEMB_ACT_TANH = 4 };
+/* how an operand of semb_affine_act_* is transformed before the add */
+enum { SEMB_AFF_NONE = 0,      /* identity (plain residual operand)                                */
+       SEMB_AFF_PLAIN = 1,     /* x*scale+shift, scale/shift are constants (inference BN)          */
+       SEMB_AFF_BATCH = 2 };   /* x*scale+shift where scale/shift come from batch statistics of x  */
+
+/* A view of an NHWC activation tensor (possibly a channel slice of a wider buffer). */
+typedef struct {
+    void*   ptr;     /* base of the underlying buffer (element type = dtype)            */
+    int32_t C;       /* channels of this view (PHYSICAL, i.e. padded: C % 8 == 0)        */
+    int32_t pitch;   /* elements between consecutive pixels of the underlying buffer    */
+    int32_t coff;    /* first channel of the view inside the buffer (coff % 8 == 0)     */
+} semb_tensor;
+/* Channel padding: every tensor the kernels see has its channel count padded to a multiple of 8
+ * (16 bytes of bf16).  The host keeps the map logical -> physical channel (multi_res_block's
+ * concat of 8|17|26 channels is stored as 8|24|32); padded lanes hold exact zeros, the matching
+ * weight rows/columns and BN parameters are zero, so they stay zero through forward, backward
+ * and Adam.  All C / Cin / Cout below are physical. */
+
+/* Geometry of one Conv2D (forward direction).  Keras call sites:
+ * UNet_Segmentation.py:421 (conv2d_bn), CycleGAN.py:327,333,340,372,393,429,448. */
+typedef struct {
+    int32_t N, H, W;          /* input  batch / height / width                          */
+    int32_t OH, OW;           /* output height / width                                  */
+    int32_t Cin, Cout;
+    int32_t R, S;             /* kernel height / width                                  */
+    int32_t stride;           /* 1 or 2                                                 */
+    int32_t pad_t, pad_l;     /* leading padding; trailing is implied by OH/OW          */
+    int32_t pad_mode;         /* SEMB_PAD_ZERO | SEMB_PAD_REFLECT                       */
+    int32_t dtype;            /* activation storage                                     */
+} semb_conv_geom;
+
+int         semb_version(void);
+const char* semb_last_error(void);
+/* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
+int64_t     semb_launch_count(void);
+/* 1 when the current device is compute capability 10.x */
+int         semb_device_ok(void);
+
+/* ---- convolutions ------------------------------------------------------------------------- */
+
+/* y[n,oy,ox,co] (+)= bias[co] + sum_{r,s,ci} x[n, oy*stride-pad_t+r, ox*stride-pad_l+s, ci] * w[r,s,ci,co]
+ * w: fp32 HWIO (Keras Conv2D kernel layout).  bias may be NULL.
+ * stats (may be NULL): fp32, sum at stats[n*stats_nstride + c], sum of squares at
+ * stats[n*stats_nstride + stats_cstride + c]; nstride = 0 gives BatchNorm (per-channel)
+ * moments, nstride = 2*cstride gives GroupNormalization(groups=-1) (per-sample) moments.
+ * Replaces F.conv2d under keras.layers.Conv2D + the keras.ops.moments pass of the following
+ * BatchNormalization / GroupNormalization (UNet_Segmentation.py:421-422, CycleGAN.py:327-329). */
+int semb_conv2d_fwd(const semb_conv_geom* g, const semb_tensor* x, const float* w, const float* bias,
+                    const semb_tensor* y, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                    int32_t accumulate, void* stream);
+
+/* dx[n,iy,ix,ci] (+)= bias[ci] + sum_{r,s,co : iy = oy*stride-pad_t+r} dy[n,oy,ox,co] * w[r,s,ci,co]
+ * Zero padding only (reflect-padded convs are differentiated on the padded domain and folded
+ * with semb_pad_crop).  This is (a) the data gradient of semb_conv2d_fwd (autograd of F.conv2d) and
+ * (b) the FORWARD of keras.layers.Conv2DTranspose whose Keras kernel (kh,kw,Cout,Cin) is read as
+ * HWIO with I=Cout_T, O=Cin_T (UNet_Segmentation.py:542-551, CycleGAN.py:353): g describes the
+ * equivalent strided conv that maps the transposed-conv OUTPUT back to its INPUT.  bias/stats as above
+ * (indexed by ci). */
+int semb_conv2d_dgrad(const semb_conv_geom* g, const semb_tensor* dy, const float* w, const float* bias,
+                      const semb_tensor* dx, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                      int32_t accumulate, void* stream);
+
+/* dw[r,s,ci,co] += sum_{n,oy,ox} x[n, oy*stride-pad_t+r, ox*stride-pad_l+s, ci] * dy[n,oy,ox,co]   (fp32 HWIO)
+ * dbias[co] += sum dy  (dbias may be NULL).  Accumulates: the caller zeroes the flat gradient buffer.
+ * Weight gradient of F.conv2d / F.conv_transpose2d (loss.backward()). */
+int semb_conv2d_wgrad(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy,
+                      float* dw, float* dbias, void* stream);
+
+/* ---- tensor-core (tcgen05 / TMEM) convolutions, bf16 storage ------------------------------ */
+
+/* Packs fp32 HWIO weights into the bf16 UMMA shared-memory image read by semb_conv2d_fwd_tc.
+ * flip=1 packs the spatially flipped, channel-transposed kernel so that the same implicit-GEMM
+ * kernel computes the stride-1 data gradient.  Returns the packed size in bytes when dst==NULL. */
+int64_t semb_pack_weights_tc(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout,
+                             int32_t flip, void* dst, void* stream);
+
+/* Same contract as semb_conv2d_fwd for stride 1, R,S in {1,3}, bf16 storage, pitch % 8 == 0,
+ * coff % 8 == 0; implicit GEMM on tcgen05.mma with the accumulator in TMEM. */
+int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
+                       const semb_tensor* y, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                       int32_t accumulate, void* stream);
+
+/* ---- normalisation + activation (fused elementwise) --------------------------------------- */
+
+/* From moments to the affine that BatchNormalization / GroupNormalization applies.
+ * For i in [0, groups*C): mean = sum/count, var = sumsq/count - mean^2 (Keras ops.moments),
+ * invstd = rsqrt(var+eps), scale = gamma[c]*invstd (gamma NULL -> 1), shift = beta[c]-mean*scale.
+ * Writes scale, shift, mean, invstd (each groups x cstride, fp32).  If moving_mean != NULL
+ * (BatchNorm training): moving = moving*momentum + batch*(1-momentum) with the biased variance.
+ * UNet_Segmentation.py:422,470,473,494,502; CycleGAN.py:329,335,342,355,374. */
+int semb_norm_finalize(const float* stats, int32_t groups, int32_t C, int32_t cstride, int32_t stats_nstride,
+                       float count, float eps, const float* gamma, const float* beta,
+                       float* scale, float* shift, float* mean, float* invstd,
+                       float* moving_mean, float* moving_var, float momentum, void* stream);
+
+/* Inference-mode BatchNorm affine from moving statistics (no reduction). */
+int semb_norm_from_moving(int32_t C, float eps, const float* gamma, const float* beta,
+                          const float* moving_mean, const float* moving_var,
+                          float* scale, float* shift, void* stream);
+
+/* y = act( A(a) + actb(B(b)) )   with  A(a) = a*scale_a[g,c]+shift_a[g,c]  (mode_a)  and the same for b
+ * (b optional: b==NULL).  g = n when *_nstride != 0 (per-sample / InstanceNorm), else 0.
+ * Optionally accumulates moments of y into stats (same layout as semb_conv2d_fwd).
+ * Covers BatchNormalization+Activation, add+Activation+BatchNormalization of multi_res_block /
+ * res_path (UNet_Segmentation.py:425,469-473,492-494), GroupNormalization+ReLU/LeakyReLU and the
+ * residual add of CycleGAN.py:329-336, and the final tanh/sigmoid. */
+typedef struct {
+    int32_t N, HW, C;
+    int32_t dtype;
+    int32_t act, actb;
+    int32_t mode_a, mode_b;           /* SEMB_AFF_* */
+    int32_t aff_nstride;              /* 0 = per-channel, else per-sample stride of scale/shift arrays */
+} semb_affine_desc;
+
+int semb_affine_act_fwd(const semb_affine_desc* d,
+                        const semb_tensor* a, const float* scale_a, const float* shift_a,
+                        const semb_tensor* b, const float* scale_b, const float* shift_b,
+                        const semb_tensor* y, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                        void* stream);
+
+/* Backward of semb_affine_act_fwd, pass 1 of 2: with g = dy*act'(y), gb = g*actb'(B(b)) accumulates
+ * sums[0]=sum g, sums[1]=sum g*a, sums[2]=sum gb, sums[3]=sum gb*b  (each at k*cstride + c, plus
+ * n*nstride for per-sample mode).  y is the saved forward output. */
+int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
+                               const semb_tensor* a, const semb_tensor* b,
+                               const float* scale_b, const float* shift_b,
+                               float* sums, int32_t sums_nstride, int32_t sums_cstride, void* stream);
+
+/* C-length finalize of the BN/IN backward: for operand `which` (0=a, 1=b) turns the sums into
+ * c1 = sum(g)/count, c2 = sum(g*xhat)/count, and accumulates dgamma += sum(g*xhat), dbeta += sum(g)
+ * (either may be NULL; per-sample mode accumulates over samples). */
+int semb_norm_bwd_finalize(const float* sums, int32_t which, int32_t groups, int32_t C, int32_t cstride,
+                           int32_t sums_nstride, float count, const float* mean, const float* invstd,
+                           float* c1, float* c2, float* dgamma, float* dbeta, void* stream);
+
+/* pass 2 of 2: da (+)= scale_a*(g - c1_a - xhat_a*c2_a)   [SEMB_AFF_BATCH]
+ *                     = scale_a*g [PLAIN] = g [NONE];  same for db.  da/db may be NULL. */
+int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
+                              const semb_tensor* a, const semb_tensor* b,
+                              const float* scale_a, const float* mean_a, const float* invstd_a,
+                              const float* c1_a, const float* c2_a,
+                              const float* scale_b, const float* shift_b, const float* mean_b,
+                              const float* invstd_b, const float* c1_b, const float* c2_b,
+                              const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b,
+                              void* stream);
+
+/* ---- pooling / padding ------------------------------------------------------------------- */
+
+/* keras.layers.MaxPooling2D((2,2)) (UNet_Segmentation.py:525-537); bwd routes to the first maximum
+ * in window scan order like ATen's max_pool2d backward. */
+int semb_maxpool2x2_fwd(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t H, int32_t W,
+                        int32_t dtype, void* stream);
+int semb_maxpool2x2_bwd(const semb_tensor* x, const semb_tensor* dy, const semb_tensor* dx, int32_t N,
+                        int32_t H, int32_t W, int32_t dtype, int32_t accumulate, void* stream);
+
+/* mode 0: y = reflect_pad(x) (ReflectionPadding2D, UNet_Segmentation.py:578-589)
+ * mode 1: y = crop(x)        (Cropping2D, :554)            top/left = offsets into x
+ * mode 2: y (+)= zero_pad(x) (gradient of crop)
+ * mode 3: y (+)= reflect_fold(x) (gradient of reflect_pad: mirrored borders are added back)
+ * (H,W) is the size of x, (OH,OW) of y. */
+int semb_pad_crop(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t H, int32_t W,
+                  int32_t OH, int32_t OW, int32_t top, int32_t left, int32_t mode, int32_t dtype,
+                  int32_t accumulate, void* stream);
+
+/* ---- losses ------------------------------------------------------------------------------ */
+
+/* weighted_bce (UNet_Segmentation.py:379-384) + the 'mae' and 'acc' metrics (:395) + d(loss)/d(p).
+ * out[0] += sum w*bce, out[1] += sum |y-p|, out[2] += #((p>0.5)==y); caller divides by count.
+ * dp = w*(-(y/p)+(1-y)/(1-p))/count inside the Keras clip range [1e-7,1-1e-7], else 0 (dp may be NULL). */
+int semb_loss_wbce(const semb_tensor* p, const float* y_true, const semb_tensor* dp, int64_t count,
+                   float weighting, float* out, int32_t dtype, void* stream);
+
+/* sum |a-b| (kind 0, MeanAbsoluteError) or sum (a-b)^2 (kind 1, MeanSquaredError) into out[0];
+ * b==NULL compares against the constant `target` (LSGAN labels, CycleGAN.py:301-308).
+ * da (+)= gscale * d/da, gscale already containing lambda/count. */
+int semb_loss_l1_l2(const semb_tensor* a, const semb_tensor* b, float target, int32_t kind, int64_t n_pixels,
+                    float gscale, const semb_tensor* da, int32_t accumulate, float* out, int32_t dtype,
+                    void* stream);
+
+/* ---- optimizer / utilities --------------------------------------------------------------- */
+
+/* keras.optimizers.Adam over one flat fp32 buffer (UNet_Segmentation.py:390-393, CycleGAN.py:168-171):
+ * m += (g-m)(1-b1); v += (g*g-v)(1-b2); w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
+ * gscale multiplies g first (1/world_size after the NCCL sum). step_ptr: device int64 step counter t
+ * (incremented by the kernel, so the call is CUDA-graph replayable); lr_ptr: device float. */
+int semb_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const float* lr_ptr,
+                   float beta1, float beta2, float eps, float gscale, int64_t* step_ptr, void* stream);
+
+int semb_fill_f32(float* p, int64_t n, float value, void* stream);
+/* dst(dtype, NHWC view) = src fp32 dense [N*HW, C] and back; the NHWC float32 boundary of the Keras model call. */
+int semb_cast_in(const float* src, const semb_tensor* dst, int64_t n_pixels, int32_t dtype, void* stream);
+int semb_cast_out(const semb_tensor* src, float* dst, int64_t n_pixels, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMB200_H */
