@@ -1,0 +1,128 @@
+"""ctypes binding of libsemb200.so (the C ABI declared in include/semb200.h).
+
+The product path has NO fallback: if the shared library cannot be loaded (or built from
+csrc/ with nvcc) every entry point raises, and on a machine with a GPU `require_device()`
+raises unless the device is sm_100.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+OK = 0
+F32, BF16 = 0, 1
+PAD_ZERO, PAD_REFLECT = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+AFF_NONE, AFF_PLAIN, AFF_BATCH = 0, 1, 2
+
+_ERR_NAMES = {-1: "SEMB_ESHAPE", -2: "SEMB_EALIGN", -3: "SEMB_EARCH", -4: "SEMB_EWORKSPACE", -5: "SEMB_ECUDA"}
+
+
+class Tensor(C.Structure):
+    """semb_tensor"""
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("pitch", C.c_int32), ("coff", C.c_int32)]
+
+
+class ConvGeom(C.Structure):
+    """semb_conv_geom"""
+    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "OH", "OW", "Cin", "Cout", "R", "S", "stride", "pad_t", "pad_l",
+                                         "pad_mode", "dtype")]
+
+
+class AffineDesc(C.Structure):
+    """semb_affine_desc"""
+    _fields_ = [(n, C.c_int32) for n in ("N", "HW", "C", "dtype", "act", "actb", "mode_a", "mode_b", "aff_nstride")]
+
+
+_P = C.c_void_p
+_I = C.c_int32
+_L = C.c_int64
+_F = C.c_float
+_TP = C.POINTER(Tensor)
+_GP = C.POINTER(ConvGeom)
+_AP = C.POINTER(AffineDesc)
+
+# name -> (restype, argtypes); must list every symbol declared in include/semb200.h
+SIGNATURES = {
+    "semb_version": (C.c_int, []),
+    "semb_last_error": (C.c_char_p, []),
+    "semb_launch_count": (C.c_int64, []),
+    "semb_device_ok": (C.c_int, []),
+    "semb_conv2d_fwd": (C.c_int, [_GP, _TP, _P, _P, _TP, _P, _I, _I, _I, _P]),
+    "semb_conv2d_dgrad": (C.c_int, [_GP, _TP, _P, _P, _TP, _P, _I, _I, _I, _P]),
+    "semb_conv2d_wgrad": (C.c_int, [_GP, _TP, _TP, _P, _P, _P]),
+    "semb_norm_finalize": (C.c_int, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
+    "semb_norm_from_moving": (C.c_int, [_I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "semb_affine_act_fwd": (C.c_int, [_AP, _TP, _P, _P, _TP, _P, _P, _TP, _P, _I, _I, _P]),
+    "semb_affine_act_bwd_reduce": (C.c_int, [_AP, _TP, _TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "semb_norm_bwd_finalize": (C.c_int, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "semb_affine_act_bwd_apply": (C.c_int, [_AP, _TP, _TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                            _TP, _I, _TP, _I, _P]),
+    "semb_channel_sum": (C.c_int, [_TP, _I, _I, _P, _I, _P]),
+    "semb_maxpool2x2_fwd": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _P]),
+    "semb_maxpool2x2_bwd": (C.c_int, [_TP, _TP, _TP, _I, _I, _I, _I, _I, _P]),
+    "semb_pad_crop": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "semb_loss_wbce": (C.c_int, [_TP, _P, _TP, _L, _F, _P, _I, _P]),
+    "semb_loss_l1_l2": (C.c_int, [_TP, _TP, _F, _I, _L, _I, _F, _TP, _I, _P, _I, _P]),
+    "semb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P]),
+    "semb_fill_f32": (C.c_int, [_P, _L, _F, _P]),
+    "semb_cast_in": (C.c_int, [_P, _I, _TP, _L, _I, _P]),
+    "semb_cast_out": (C.c_int, [_TP, _P, _I, _L, _I, _P]),
+}
+
+_lib = None
+
+
+class SembError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen libsemb200.so, building it first when only the sources are present."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build()  # raises when nvcc is unavailable: no fallback path exists
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library is stale: rebuild
+        fn.restype = res
+        fn.argtypes = args
+    if lib.semb_version() != 100:
+        raise SembError(f"libsemb200.so version {lib.semb_version()} does not match the binding (100)")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().semb_last_error().decode()
+
+
+def check(rc: int):
+    """status code -> exception (shape/alignment problems are ValueError like Keras', the rest RuntimeError)."""
+    if rc == OK:
+        return
+    msg = f"{_ERR_NAMES.get(rc, rc)}: {last_error()}"
+    if rc in (-1, -2):
+        raise ValueError(msg)
+    raise SembError(msg)
+
+
+def require_device():
+    import torch
+    if not torch.cuda.is_available():
+        raise SembError("libsemb200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if not load().semb_device_ok():
+        raise SembError(last_error())
+
+
+def launch_count() -> int:
+    return int(load().semb_launch_count())

@@ -1,0 +1,490 @@
+// Fused normalisation / activation / residual kernels (HBM-bound, 128-bit accesses).
+//
+// Every tensor is NHWC with 8-padded channels, so one thread always moves 8 channels of one pixel
+// (16 B of bf16, 32 B of fp32).  A block owns a contiguous range of pixels of ONE sample and all
+// channels; per-channel reductions (BatchNorm / InstanceNorm moments and their backward sums) are
+// carried in registers across the block's pixel loop, combined in shared memory and flushed with one
+// atomic per channel per block.
+#include "common.cuh"
+
+namespace semb {
+
+struct View { const void* ptr; int pitch, coff; };
+static inline View mkview(const semb_tensor* t) { return t ? View{t->ptr, t->pitch, t->coff} : View{nullptr, 0, 0}; }
+
+template <typename T>
+__device__ __forceinline__ const T* vptr(const View& v, long long pixel, int c) {
+    return reinterpret_cast<const T*>(v.ptr) + (size_t)pixel * v.pitch + v.coff + c;
+}
+template <typename T>
+__device__ __forceinline__ T* vptr_mut(const View& v, long long pixel, int c) {
+    return reinterpret_cast<T*>(const_cast<void*>(v.ptr)) + (size_t)pixel * v.pitch + v.coff + c;
+}
+
+// Block geometry shared by all kernels of this file: C8 = C/8 channel lanes, rows = 256 / C8 pixel rows.
+struct Lanes {
+    int c8, rows, cg, prow;
+    bool active;
+    __device__ Lanes(int C) {
+        c8 = C >> 3;
+        rows = 256 / c8;
+        cg = threadIdx.x % c8;
+        prow = threadIdx.x / c8;
+        active = prow < rows;
+    }
+};
+
+struct AffArgs {
+    int N, HW, C, act, actb, mode_a, mode_b, aff_nstride;
+    View a, b, y, dy, da, db;
+    const float *scale_a, *shift_a, *scale_b, *shift_b;
+    const float *mean_a, *invstd_a, *c1_a, *c2_a, *mean_b, *invstd_b, *c1_b, *c2_b;
+    float* stats; double* dstats; int stats_nstride, stats_cstride;
+    int acc_a, acc_b;
+    int ppb;  // pixels per block
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_fwd_kernel(const AffArgs p) {
+    extern __shared__ float sm[];  // [rows][2][C] when moments are requested
+    const Lanes L(p.C);
+    const int n = blockIdx.y;
+    const int c = L.cg * 8;
+    const long long pix0 = (long long)n * p.HW;
+    const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
+    const size_t aoff = (size_t)n * p.aff_nstride + c;
+
+    float sa[8], ta[8], sb[8], tb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; }
+    if (L.active) {
+        if (p.mode_a != SEMB_AFF_NONE)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sa[i] = p.scale_a[aoff + i]; ta[i] = p.shift_a[aoff + i]; }
+        if (p.b.ptr && p.mode_b != SEMB_AFF_NONE)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sb[i] = p.scale_b[aoff + i]; tb[i] = p.shift_b[aoff + i]; }
+    }
+    float s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+
+    if (L.active) {
+        for (int px = begin + L.prow; px < end; px += L.rows) {
+            float va[8], vy[8];
+            Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vy[i] = fmaf(va[i], sa[i], ta[i]);
+            if (p.b.ptr) {
+                float vb[8];
+                Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vy[i] += act_fwd(fmaf(vb[i], sb[i], tb[i]), p.actb);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                vy[i] = act_fwd(vy[i], p.act);
+                s1[i] += vy[i];
+                s2[i] += vy[i] * vy[i];
+            }
+            Vec8<T>::store(vptr_mut<T>(p.y, pix0 + px, c), vy);
+        }
+    }
+    if (p.dstats) {
+        // deterministic: partials [rows][2][C] in shared memory, fixed-order column sums, fp64 atomics across blocks
+        if (L.active) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sm[(L.prow * 2) * p.C + c + i] = s1[i];
+                sm[(L.prow * 2 + 1) * p.C + c + i] = s2[i];
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < p.C; i += 256) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int r = 0; r < L.rows; ++r) { t1 += sm[(r * 2) * p.C + i]; t2 += sm[(r * 2 + 1) * p.C + i]; }
+            double* st = p.dstats + (size_t)n * p.stats_nstride + i;
+            atomicAdd(st, (double)t1);
+            atomicAdd(st + p.stats_cstride, (double)t2);
+        }
+    }
+}
+
+// backward pass 1: sums[0]=sum g, [1]=sum g*xhat_a, [2]=sum gb, [3]=sum gb*xhat_b
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_bwd_reduce_kernel(const AffArgs p) {
+    extern __shared__ float sm[];  // [4][C]
+    const Lanes L(p.C);
+    const int n = blockIdx.y;
+    const int c = L.cg * 8;
+    const long long pix0 = (long long)n * p.HW;
+    const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
+    const size_t aoff = (size_t)n * p.aff_nstride + c;
+    const bool has_b = p.b.ptr != nullptr;
+    const bool red_a = p.mode_a == SEMB_AFF_BATCH, red_b = has_b && p.mode_b == SEMB_AFF_BATCH;
+
+    float ma[8], ia[8], mb[8], ib[8], sb[8], tb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ma[i] = 0.f; ia[i] = 1.f; mb[i] = 0.f; ib[i] = 1.f; sb[i] = 1.f; tb[i] = 0.f; }
+    if (L.active) {
+        if (red_a)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ma[i] = p.mean_a[aoff + i]; ia[i] = p.invstd_a[aoff + i]; }
+        if (red_b)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { mb[i] = p.mean_b[aoff + i]; ib[i] = p.invstd_b[aoff + i]; }
+        if (has_b && p.mode_b != SEMB_AFF_NONE)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { sb[i] = p.scale_b[aoff + i]; tb[i] = p.shift_b[aoff + i]; }
+    }
+    float q0[8], q1[8], q2[8], q3[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { q0[i] = q1[i] = q2[i] = q3[i] = 0.f; }
+
+    if (L.active) {
+        for (int px = begin + L.prow; px < end; px += L.rows) {
+            float g[8], vy[8];
+            Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g);
+            if (p.act != SEMB_ACT_NONE) {
+                Vec8<T>::load(vptr<T>(p.y, pix0 + px, c), vy);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] *= act_bwd_from_y(vy[i], p.act);
+            }
+            if (red_a) {
+                float va[8];
+                Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { q0[i] += g[i]; q1[i] += g[i] * (va[i] - ma[i]) * ia[i]; }
+            }
+            if (red_b) {
+                float vb[8];
+                Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float gb = g[i];
+                    if (p.actb != SEMB_ACT_NONE) gb *= act_bwd_from_y(act_fwd(fmaf(vb[i], sb[i], tb[i]), p.actb), p.actb);
+                    q2[i] += gb;
+                    q3[i] += gb * (vb[i] - mb[i]) * ib[i];
+                }
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < 4 * p.C; i += 256) sm[i] = 0.f;
+    __syncthreads();
+    if (L.active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (red_a) { atomicAdd(&sm[c + i], q0[i]); atomicAdd(&sm[p.C + c + i], q1[i]); }
+            if (red_b) { atomicAdd(&sm[2 * p.C + c + i], q2[i]); atomicAdd(&sm[3 * p.C + c + i], q3[i]); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += 256) {
+        float* st = p.stats + (size_t)n * p.stats_nstride + i;
+        if (red_a) { atomicAdd(st, sm[i]); atomicAdd(st + p.stats_cstride, sm[p.C + i]); }
+        if (red_b) { atomicAdd(st + 2 * p.stats_cstride, sm[2 * p.C + i]); atomicAdd(st + 3 * p.stats_cstride, sm[3 * p.C + i]); }
+    }
+}
+
+// backward pass 2
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_bwd_apply_kernel(const AffArgs p) {
+    const Lanes L(p.C);
+    if (!L.active) return;
+    const int n = blockIdx.y;
+    const int c = L.cg * 8;
+    const long long pix0 = (long long)n * p.HW;
+    const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
+    const size_t aoff = (size_t)n * p.aff_nstride + c;
+    const bool has_b = p.b.ptr != nullptr;
+
+    float sa[8], ma[8], ia[8], k1a[8], k2a[8], sb[8], tb[8], mb[8], ib[8], k1b[8], k2b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sa[i] = 1.f; ma[i] = 0.f; ia[i] = 0.f; k1a[i] = 0.f; k2a[i] = 0.f;
+        sb[i] = 1.f; tb[i] = 0.f; mb[i] = 0.f; ib[i] = 0.f; k1b[i] = 0.f; k2b[i] = 0.f;
+    }
+    if (p.mode_a != SEMB_AFF_NONE)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sa[i] = p.scale_a[aoff + i];
+    if (p.mode_a == SEMB_AFF_BATCH)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ma[i] = p.mean_a[aoff + i]; ia[i] = p.invstd_a[aoff + i]; k1a[i] = p.c1_a[aoff + i]; k2a[i] = p.c2_a[aoff + i]; }
+    if (has_b && p.mode_b != SEMB_AFF_NONE)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sb[i] = p.scale_b[aoff + i]; tb[i] = p.shift_b[aoff + i]; }
+    if (has_b && p.mode_b == SEMB_AFF_BATCH)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mb[i] = p.mean_b[aoff + i]; ib[i] = p.invstd_b[aoff + i]; k1b[i] = p.c1_b[aoff + i]; k2b[i] = p.c2_b[aoff + i]; }
+
+    for (int px = begin + L.prow; px < end; px += L.rows) {
+        float g[8], vy[8];
+        Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g);
+        if (p.act != SEMB_ACT_NONE) {
+            Vec8<T>::load(vptr<T>(p.y, pix0 + px, c), vy);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] *= act_bwd_from_y(vy[i], p.act);
+        }
+        if (p.da.ptr) {
+            float d[8];
+            if (p.mode_a == SEMB_AFF_BATCH) {
+                float va[8];
+                Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = sa[i] * (g[i] - k1a[i] - (va[i] - ma[i]) * ia[i] * k2a[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] = sa[i] * g[i];
+            }
+            T* o = vptr_mut<T>(p.da, pix0 + px, c);
+            if (p.acc_a) {
+                float old[8];
+                Vec8<T>::load(o, old);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] += old[i];
+            }
+            Vec8<T>::store(o, d);
+        }
+        if (has_b && p.db.ptr) {
+            float d[8], vb[8];
+            const bool need_b = p.mode_b == SEMB_AFF_BATCH || p.actb != SEMB_ACT_NONE;
+            if (need_b) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float gb = g[i];
+                if (p.actb != SEMB_ACT_NONE) gb *= act_bwd_from_y(act_fwd(fmaf(vb[i], sb[i], tb[i]), p.actb), p.actb);
+                if (p.mode_b == SEMB_AFF_BATCH) d[i] = sb[i] * (gb - k1b[i] - (vb[i] - mb[i]) * ib[i] * k2b[i]);
+                else d[i] = sb[i] * gb;
+            }
+            T* o = vptr_mut<T>(p.db, pix0 + px, c);
+            if (p.acc_b) {
+                float old[8];
+                Vec8<T>::load(o, old);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] += old[i];
+            }
+            Vec8<T>::store(o, d);
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(const AffArgs p) {
+    extern __shared__ float sm[];  // [C]
+    const Lanes L(p.C);
+    const int n = blockIdx.y;
+    const int c = L.cg * 8;
+    const long long pix0 = (long long)n * p.HW;
+    const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
+    float s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1[i] = 0.f;
+    if (L.active) {
+        for (int px = begin + L.prow; px < end; px += L.rows) {
+            float va[8];
+            Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1[i] += va[i];
+        }
+    }
+    for (int i = threadIdx.x; i < p.C; i += 256) sm[i] = 0.f;
+    __syncthreads();
+    if (L.active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(&sm[c + i], s1[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.C; i += 256) atomicAdd(p.stats + i, sm[i]);
+}
+
+static int pick_ppb(int HW, int N, int C) {
+    const int rows = 256 / (C / 8);
+    long long target_blocks = 148LL * 8;
+    int ppb = (int)cdivl((long long)HW * N, target_blocks);
+    int min_ppb = rows * 4;
+    if (ppb < min_ppb) ppb = min_ppb;
+    ppb = cdiv(ppb, rows) * rows;
+    return ppb;
+}
+
+static int check_aff(const semb_affine_desc* d) {
+    SEMB_REQUIRE(d, SEMB_ESHAPE, "affine: null desc");
+    SEMB_REQUIRE(d->N > 0 && d->HW > 0 && d->C > 0 && d->C % 8 == 0 && d->C <= 2048, SEMB_ESHAPE,
+                 "affine: bad shape N=%d HW=%d C=%d", d->N, d->HW, d->C);
+    SEMB_REQUIRE(d->dtype == SEMB_F32 || d->dtype == SEMB_BF16, SEMB_ESHAPE, "affine: bad dtype");
+    return SEMB_OK;
+}
+
+__global__ void norm_finalize_kernel(const double* stats, int groups, int C, int cstride, int stats_nstride, float count,
+                                     float eps, const float* gamma, const float* beta, float* scale, float* shift,
+                                     float* mean_o, float* invstd_o, float* mm, float* mv, float momentum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups * C) return;
+    const int g = i / C, c = i % C;
+    const double* st = stats + (size_t)g * stats_nstride;
+    const double dm = st[c] / (double)count;
+    const float mean = (float)dm;
+    const float var = (float)(st[cstride + c] / (double)count - dm * dm);   // Keras: E[x^2] - E[x]^2 (biased)
+    const float inv = rsqrtf(var + eps);
+    const float ga = gamma ? gamma[c] : 1.f;
+    const float sc = ga * inv;
+    const size_t o = (size_t)g * cstride + c;
+    scale[o] = sc;
+    shift[o] = beta[c] - mean * sc;
+    if (mean_o) mean_o[o] = mean;
+    if (invstd_o) invstd_o[o] = inv;
+    if (mm) {
+        mm[c] = mm[c] * momentum + mean * (1.f - momentum);
+        mv[c] = mv[c] * momentum + var * (1.f - momentum);
+    }
+}
+
+__global__ void norm_from_moving_kernel(int C, float eps, const float* gamma, const float* beta, const float* mm,
+                                        const float* mv, float* scale, float* shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = (gamma ? gamma[c] : 1.f) * rsqrtf(mv[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - mm[c] * sc;
+}
+
+__global__ void norm_bwd_finalize_kernel(const float* sums, int which, int groups, int C, int cstride, int sums_nstride,
+                                         float count, float* c1, float* c2, float* dgamma, float* dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float tg = 0.f, tb = 0.f;
+    for (int g = 0; g < groups; ++g) {
+        const float* s = sums + (size_t)g * sums_nstride + (size_t)(2 * which) * cstride;
+        const float s0 = s[c], s1 = s[cstride + c];
+        c1[(size_t)g * cstride + c] = s0 / count;
+        c2[(size_t)g * cstride + c] = s1 / count;
+        tb += s0;
+        tg += s1;
+    }
+    if (dgamma) dgamma[c] += tg;
+    if (dbeta) dbeta[c] += tb;
+}
+
+}  // namespace semb
+
+using namespace semb;
+
+extern "C" int semb_norm_finalize(const void* stats, int32_t groups, int32_t C, int32_t cstride, int32_t stats_nstride,
+                                  float count, float eps, const float* gamma, const float* beta, float* scale,
+                                  float* shift, float* mean, float* invstd, float* moving_mean, float* moving_var,
+                                  float momentum, void* stream) {
+    SEMB_REQUIRE(stats && beta && scale && shift && groups > 0 && C > 0, SEMB_ESHAPE, "norm_finalize: bad arguments");
+    SEMB_REQUIRE(!moving_mean || groups == 1, SEMB_ESHAPE, "norm_finalize: moving statistics need groups==1");
+    const int n = groups * C;
+    norm_finalize_kernel<<<cdiv(n, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const double*>(stats), groups, C, cstride, stats_nstride, count, eps,
+                                                                     gamma, beta, scale, shift, mean, invstd,
+                                                                     moving_mean, moving_var, momentum);
+    return check_launch("norm_finalize");
+}
+
+extern "C" int semb_norm_from_moving(int32_t C, float eps, const float* gamma, const float* beta, const float* moving_mean,
+                                     const float* moving_var, float* scale, float* shift, void* stream) {
+    SEMB_REQUIRE(C > 0 && beta && moving_mean && moving_var && scale && shift, SEMB_ESHAPE, "norm_from_moving: bad arguments");
+    norm_from_moving_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(C, eps, gamma, beta, moving_mean, moving_var, scale, shift);
+    return check_launch("norm_from_moving");
+}
+
+extern "C" int semb_norm_bwd_finalize(const float* sums, int32_t which, int32_t groups, int32_t C, int32_t cstride,
+                                      int32_t sums_nstride, float count, const float* mean, const float* invstd,
+                                      float* c1, float* c2, float* dgamma, float* dbeta, void* stream) {
+    (void)mean; (void)invstd;
+    SEMB_REQUIRE(sums && c1 && c2 && groups > 0 && C > 0 && (which == 0 || which == 1), SEMB_ESHAPE, "norm_bwd_finalize: bad arguments");
+    norm_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(sums, which, groups, C, cstride, sums_nstride,
+                                                                         count, c1, c2, dgamma, dbeta);
+    return check_launch("norm_bwd_finalize");
+}
+
+extern "C" int semb_affine_act_fwd(const semb_affine_desc* d, const semb_tensor* a, const float* scale_a,
+                                   const float* shift_a, const semb_tensor* b, const float* scale_b, const float* shift_b,
+                                   const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
+                                   void* stream) {
+    int rc = check_aff(d);
+    if (rc) return rc;
+    SEMB_REQUIRE(view_ok(a) && view_ok(y) && (!b || view_ok(b)), SEMB_EALIGN, "affine fwd: bad tensor view");
+    SEMB_REQUIRE(a->C == d->C && y->C == d->C && (!b || b->C == d->C), SEMB_ESHAPE, "affine fwd: channel mismatch");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_NONE || (scale_a && shift_a), SEMB_ESHAPE, "affine fwd: missing scale/shift a");
+    SEMB_REQUIRE(!b || d->mode_b == SEMB_AFF_NONE || (scale_b && shift_b), SEMB_ESHAPE, "affine fwd: missing scale/shift b");
+    AffArgs p{};
+    p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
+    p.aff_nstride = d->aff_nstride;
+    p.a = mkview(a); p.b = mkview(b); p.y = mkview(y);
+    p.scale_a = scale_a; p.shift_a = shift_a; p.scale_b = scale_b; p.shift_b = shift_b;
+    p.dstats = reinterpret_cast<double*>(stats); p.stats_nstride = stats_nstride; p.stats_cstride = stats_cstride;
+    p.ppb = pick_ppb(d->HW, d->N, d->C);
+    dim3 grid(cdiv(d->HW, p.ppb), d->N);
+    const size_t smem = stats ? (size_t)(256 / (d->C / 8)) * 2 * d->C * sizeof(float) : 0;
+    if (d->dtype == SEMB_BF16) affine_act_fwd_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(p);
+    else affine_act_fwd_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(p);
+    return check_launch("affine_act_fwd");
+}
+
+extern "C" int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
+                                          const semb_tensor* a, const semb_tensor* b, const float* mean_a,
+                                          const float* invstd_a, const float* scale_b, const float* shift_b,
+                                          const float* mean_b, const float* invstd_b, float* sums,
+                                          int32_t sums_nstride, int32_t sums_cstride, void* stream) {
+    int rc = check_aff(d);
+    if (rc) return rc;
+    SEMB_REQUIRE(view_ok(dy) && view_ok(a) && (!b || view_ok(b)) && (d->act == SEMB_ACT_NONE || view_ok(y)), SEMB_EALIGN,
+                 "affine bwd reduce: bad tensor view");
+    SEMB_REQUIRE(sums, SEMB_ESHAPE, "affine bwd reduce: null sums");
+    SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (mean_a && invstd_a), SEMB_ESHAPE, "affine bwd reduce: missing mean/invstd a");
+    SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (mean_b && invstd_b), SEMB_ESHAPE, "affine bwd reduce: missing mean/invstd b");
+    AffArgs p{};
+    p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
+    p.aff_nstride = d->aff_nstride;
+    p.a = mkview(a); p.b = mkview(b); p.y = mkview(y); p.dy = mkview(dy);
+    p.mean_a = mean_a; p.invstd_a = invstd_a; p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
+    p.stats = sums; p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
+    p.ppb = pick_ppb(d->HW, d->N, d->C);
+    dim3 grid(cdiv(d->HW, p.ppb), d->N);
+    const size_t smem = 4 * d->C * sizeof(float);
+    if (d->dtype == SEMB_BF16) affine_act_bwd_reduce_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(p);
+    else affine_act_bwd_reduce_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(p);
+    return check_launch("affine_act_bwd_reduce");
+}
+
+extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
+                                         const semb_tensor* a, const semb_tensor* b, const float* scale_a,
+                                         const float* mean_a, const float* invstd_a, const float* c1_a, const float* c2_a,
+                                         const float* scale_b, const float* shift_b, const float* mean_b,
+                                         const float* invstd_b, const float* c1_b, const float* c2_b,
+                                         const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b,
+                                         void* stream) {
+    int rc = check_aff(d);
+    if (rc) return rc;
+    SEMB_REQUIRE(view_ok(dy) && (d->act == SEMB_ACT_NONE || view_ok(y)), SEMB_EALIGN, "affine bwd apply: bad dy/y view");
+    SEMB_REQUIRE((!da || view_ok(da)) && (!db || view_ok(db)) && (!b || view_ok(b)), SEMB_EALIGN, "affine bwd apply: bad view");
+    SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (view_ok(a) && scale_a && mean_a && invstd_a && c1_a && c2_a), SEMB_ESHAPE,
+                 "affine bwd apply: missing batch-norm terms for a");
+    SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (scale_b && shift_b && mean_b && invstd_b && c1_b && c2_b), SEMB_ESHAPE,
+                 "affine bwd apply: missing batch-norm terms for b");
+    AffArgs p{};
+    p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
+    p.aff_nstride = d->aff_nstride;
+    p.a = mkview(a); p.b = mkview(b); p.y = mkview(y); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
+    p.scale_a = scale_a; p.mean_a = mean_a; p.invstd_a = invstd_a; p.c1_a = c1_a; p.c2_a = c2_a;
+    p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b; p.c1_b = c1_b; p.c2_b = c2_b;
+    p.acc_a = acc_a; p.acc_b = acc_b;
+    p.ppb = pick_ppb(d->HW, d->N, d->C);
+    dim3 grid(cdiv(d->HW, p.ppb), d->N);
+    if (d->dtype == SEMB_BF16) affine_act_bwd_apply_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(p);
+    else affine_act_bwd_apply_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(p);
+    return check_launch("affine_act_bwd_apply");
+}
+
+extern "C" int semb_channel_sum(const semb_tensor* x, int32_t N, int32_t HW, float* out, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(x) && out && N > 0 && HW > 0 && x->C <= 2048, SEMB_ESHAPE, "channel_sum: bad arguments");
+    AffArgs p{};
+    p.N = N; p.HW = HW; p.C = x->C; p.a = mkview(x); p.stats = out;
+    p.ppb = pick_ppb(HW, N, x->C);
+    dim3 grid(cdiv(HW, p.ppb), N);
+    if (dtype == SEMB_BF16) channel_sum_kernel<bf16><<<grid, 256, x->C * sizeof(float), as_stream(stream)>>>(p);
+    else channel_sum_kernel<float><<<grid, 256, x->C * sizeof(float), as_stream(stream)>>>(p);
+    return check_launch("channel_sum");
+}

@@ -1,0 +1,367 @@
+// Pooling, padding, losses, optimizer and boundary casts.  All HBM-bound, 8-channel vectors.
+#include "common.cuh"
+
+namespace semb {
+
+struct PView { void* ptr; int pitch, coff; };
+static inline PView pv(const semb_tensor* t) { return t ? PView{t->ptr, t->pitch, t->coff} : PView{nullptr, 0, 0}; }
+template <typename T>
+__device__ __forceinline__ T* at(const PView& v, size_t pixel, int c) {
+    return reinterpret_cast<T*>(v.ptr) + pixel * v.pitch + v.coff + c;
+}
+
+// ---- MaxPooling2D((2,2)) ------------------------------------------------------------------------
+template <typename T, bool BWD>
+__global__ void maxpool_kernel(PView x, PView y /* fwd: out, bwd: dy */, PView dx, int N, int H, int W, int C8, int acc) {
+    const int OH = H / 2, OW = W / 2;
+    const long long total = (long long)N * OH * OW * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const long long op = i / C8;
+        const int ox = (int)(op % OW), oy = (int)((op / OW) % OH), n = (int)(op / ((long long)OW * OH));
+        const size_t p00 = ((size_t)n * H + 2 * oy) * W + 2 * ox;
+        float v[4][8];
+        Vec8<T>::load(at<T>(x, p00, c), v[0]);
+        Vec8<T>::load(at<T>(x, p00 + 1, c), v[1]);
+        Vec8<T>::load(at<T>(x, p00 + W, c), v[2]);
+        Vec8<T>::load(at<T>(x, p00 + W + 1, c), v[3]);
+        if (!BWD) {
+            float m[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(fmaxf(v[0][k], v[1][k]), fmaxf(v[2][k], v[3][k]));
+            Vec8<T>::store(at<T>(y, (size_t)op, c), m);
+        } else {
+            float g[8], d[4][8];
+            Vec8<T>::load(at<T>(y, (size_t)op, c), g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int arg = 0;
+                float best = v[0][k];
+#pragma unroll
+                for (int q = 1; q < 4; ++q)
+                    if (v[q][k] > best) { best = v[q][k]; arg = q; }   // first maximum wins (ATen)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d[q][k] = (q == arg) ? g[k] : 0.f;
+            }
+            const size_t pos[4] = {p00, p00 + 1, p00 + W, p00 + W + 1};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                T* o = at<T>(dx, pos[q], c);
+                if (acc) {
+                    float old[8];
+                    Vec8<T>::load(o, old);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) d[q][k] += old[k];
+                }
+                Vec8<T>::store(o, d[q]);
+            }
+        }
+    }
+}
+
+// ---- reflect pad / crop / zero pad / reflect fold -------------------------------------------------
+template <typename T>
+__global__ void pad_crop_kernel(PView x, PView y, int N, int H, int W, int OH, int OW, int top, int left, int mode,
+                                int C8, int acc) {
+    const long long total = (long long)N * OH * OW * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const long long op = i / C8;
+        const int ox = (int)(op % OW), oy = (int)((op / OW) % OH), n = (int)(op / ((long long)OW * OH));
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        if (mode == 0) {
+            const int sy = reflect_index(oy - top, H), sx = reflect_index(ox - left, W);
+            Vec8<T>::load(at<T>(x, ((size_t)n * H + sy) * W + sx, c), v);
+        } else if (mode == 1) {
+            Vec8<T>::load(at<T>(x, ((size_t)n * H + oy + top) * W + ox + left, c), v);
+        } else if (mode == 2) {
+            const int sy = oy - top, sx = ox - left;
+            if (sy >= 0 && sy < H && sx >= 0 && sx < W) Vec8<T>::load(at<T>(x, ((size_t)n * H + sy) * W + sx, c), v);
+        } else {
+            // gradient of reflect_pad: x is the padded-domain gradient (H,W); y the unpadded one (OH,OW)
+            const int bot = H - OH - top, right = W - OW - left;
+            int ys[3], xs[3], ny = 0, nx = 0;
+            ys[ny++] = oy + top;
+            if (oy >= 1 && oy <= top) ys[ny++] = top - oy;
+            if (oy <= OH - 2 && oy >= OH - 1 - bot) ys[ny++] = top + 2 * (OH - 1) - oy;
+            xs[nx++] = ox + left;
+            if (ox >= 1 && ox <= left) xs[nx++] = left - ox;
+            if (ox <= OW - 2 && ox >= OW - 1 - right) xs[nx++] = left + 2 * (OW - 1) - ox;
+            for (int a = 0; a < ny; ++a)
+                for (int b = 0; b < nx; ++b) {
+                    float t[8];
+                    Vec8<T>::load(at<T>(x, ((size_t)n * H + ys[a]) * W + xs[b], c), t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] += t[k];
+                }
+        }
+        T* o = at<T>(y, (size_t)op, c);
+        if (acc) {
+            float old[8];
+            Vec8<T>::load(o, old);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += old[k];
+        }
+        Vec8<T>::store(o, v);
+    }
+}
+
+// ---- losses -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int K>
+__device__ __forceinline__ void block_flush(float (&v)[K], float* out) {
+    __shared__ float red[K][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        v[k] = warp_sum(v[k]);
+        if (lane == 0) red[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+        atomicAdd(out + threadIdx.x, s);
+    }
+}
+
+// weighted BCE on channel 0 of p (the head has one logical channel)
+template <typename T>
+__global__ void __launch_bounds__(256) loss_wbce_kernel(PView p, const float* __restrict__ yt, PView dp, long long count,
+                                                        float weighting, float* out) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    const float eps = 1e-7f, inv_count = 1.f / (float)count;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        Vec8<T>::load(at<T>(p, (size_t)i, 0), v);
+        const float pr = v[0], y = yt[i];
+        const float pc = fminf(fmaxf(pr, eps), 1.f - eps);
+        const float w = y * (weighting - 1.f) + 1.f;
+        acc[0] += -w * (y * logf(pc) + (1.f - y) * logf(1.f - pc));
+        acc[1] += fabsf(y - pr);
+        acc[2] += ((pr > 0.5f ? 1.f : 0.f) == y) ? 1.f : 0.f;
+        if (dp.ptr) {
+            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (pr >= eps && pr <= 1.f - eps) g[0] = w * (-(y / pc) + (1.f - y) / (1.f - pc)) * inv_count;
+            Vec8<T>::store(at<T>(dp, (size_t)i, 0), g);
+        }
+    }
+    block_flush<3>(acc, out);
+}
+
+// L1 / L2 between a and b (or a constant target) over all 8-padded channels (pads are zero in both)
+template <typename T>
+__global__ void __launch_bounds__(256) loss_l1_l2_kernel(PView a, PView b, float target, int kind, long long n_pixels, int C8,
+                                                         int c_logical, float gscale, PView da, int acc, float* out) {
+    float sum[1] = {0.f};
+    const long long total = n_pixels * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const size_t px = (size_t)(i / C8);
+        float va[8], vb[8], g[8];
+        Vec8<T>::load(at<T>(a, px, c), va);
+        if (b.ptr) Vec8<T>::load(at<T>(b, px, c), vb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool real = (c + k) < c_logical;
+            const float d = real ? va[k] - (b.ptr ? vb[k] : target) : 0.f;
+            if (kind == 0) { sum[0] += fabsf(d); g[k] = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f); }
+            else { sum[0] += d * d; g[k] = 2.f * d * gscale; }
+        }
+        if (da.ptr) {
+            T* o = at<T>(da, px, c);
+            if (acc) {
+                float old[8];
+                Vec8<T>::load(o, old);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] += old[k];
+            }
+            Vec8<T>::store(o, g);
+        }
+    }
+    block_flush<1>(sum, out);
+}
+
+// ---- Adam ---------------------------------------------------------------------------------------------------
+struct AdamState { long long t; float alpha; float pad; };
+
+__global__ void adam_tick_kernel(AdamState* st, const float* lr, float b1, float b2) {
+    const long long t = st->t + 1;
+    st->t = t;
+    st->alpha = (float)((double)lr[0] * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, const AdamState* st, float b1, float b2,
+                                                   float eps, float gscale) {
+    const float alpha = st->alpha;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+        if (i + 4 <= n) {
+            float4 g4 = *reinterpret_cast<const float4*>(g + i);
+            float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i), w4 = *reinterpret_cast<float4*>(w + i);
+            float gg[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+            float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mm[k] += (gg[k] - mm[k]) * (1.f - b1);
+                vv[k] += (gg[k] * gg[k] - vv[k]) * (1.f - b2);
+                ww[k] -= alpha * mm[k] / (sqrtf(vv[k]) + eps);
+            }
+            *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+            *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            *reinterpret_cast<float4*>(w + i) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+        } else {
+            for (long long j = i; j < n; ++j) {
+                const float gg = g[j] * gscale;
+                m[j] += (gg - m[j]) * (1.f - b1);
+                v[j] += (gg * gg - v[j]) * (1.f - b2);
+                w[j] -= alpha * m[j] / (sqrtf(v[j]) + eps);
+            }
+        }
+    }
+}
+
+__global__ void fill_kernel(float* p, long long n, float value) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = value;
+}
+
+template <typename T>
+__global__ void cast_in_kernel(const float* __restrict__ src, int src_C, PView dst, long long n_pixels, int C8) {
+    const long long total = n_pixels * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const size_t px = (size_t)(i / C8);
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (c + k < src_C) ? src[px * src_C + c + k] : 0.f;
+        Vec8<T>::store(at<T>(dst, px, c), v);
+    }
+}
+
+template <typename T>
+__global__ void cast_out_kernel(PView src, float* __restrict__ dst, int dst_C, long long n_pixels, int C8) {
+    const long long total = n_pixels * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const size_t px = (size_t)(i / C8);
+        float v[8];
+        Vec8<T>::load(at<T>(src, px, c), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c + k < dst_C) dst[px * dst_C + c + k] = v[k];
+    }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+    long long b = cdivl(total, block);
+    const long long cap = 148LL * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace semb
+
+using namespace semb;
+
+extern "C" int semb_maxpool2x2_fwd(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t H, int32_t W,
+                                   int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(x) && view_ok(y) && x->C == y->C, SEMB_EALIGN, "maxpool fwd: bad views");
+    SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, SEMB_ESHAPE, "maxpool fwd: H,W must be even");
+    const int C8 = x->C / 8;
+    const long long total = (long long)N * (H / 2) * (W / 2) * C8;
+    if (dtype == SEMB_BF16) maxpool_kernel<bf16, false><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), PView{}, N, H, W, C8, 0);
+    else maxpool_kernel<float, false><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), PView{}, N, H, W, C8, 0);
+    return check_launch("maxpool_fwd");
+}
+
+extern "C" int semb_maxpool2x2_bwd(const semb_tensor* x, const semb_tensor* dy, const semb_tensor* dx, int32_t N, int32_t H,
+                                   int32_t W, int32_t dtype, int32_t accumulate, void* stream) {
+    SEMB_REQUIRE(view_ok(x) && view_ok(dy) && view_ok(dx) && x->C == dy->C && x->C == dx->C, SEMB_EALIGN, "maxpool bwd: bad views");
+    SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, SEMB_ESHAPE, "maxpool bwd: H,W must be even");
+    const int C8 = x->C / 8;
+    const long long total = (long long)N * (H / 2) * (W / 2) * C8;
+    if (dtype == SEMB_BF16) maxpool_kernel<bf16, true><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(dy), pv(dx), N, H, W, C8, accumulate);
+    else maxpool_kernel<float, true><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(dy), pv(dx), N, H, W, C8, accumulate);
+    return check_launch("maxpool_bwd");
+}
+
+extern "C" int semb_pad_crop(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t H, int32_t W, int32_t OH,
+                             int32_t OW, int32_t top, int32_t left, int32_t mode, int32_t dtype, int32_t accumulate,
+                             void* stream) {
+    SEMB_REQUIRE(view_ok(x) && view_ok(y) && x->C == y->C, SEMB_EALIGN, "pad_crop: bad views");
+    SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && top >= 0 && left >= 0 && mode >= 0 && mode <= 3, SEMB_ESHAPE,
+                 "pad_crop: bad geometry");
+    if (mode == 0 || mode == 2) {
+        SEMB_REQUIRE(OH >= H + top && OW >= W + left, SEMB_ESHAPE, "pad_crop: output smaller than padded input");
+        if (mode == 0) SEMB_REQUIRE(top < H && left < W && OH - H - top < H && OW - W - left < W, SEMB_ESHAPE, "pad_crop: reflect pad wider than image");
+    } else {
+        SEMB_REQUIRE(H >= OH + top && W >= OW + left, SEMB_ESHAPE, "pad_crop: crop window outside the input");
+    }
+    const int C8 = x->C / 8;
+    const long long total = (long long)N * OH * OW * C8;
+    if (dtype == SEMB_BF16) pad_crop_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), N, H, W, OH, OW, top, left, mode, C8, accumulate);
+    else pad_crop_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), N, H, W, OH, OW, top, left, mode, C8, accumulate);
+    return check_launch("pad_crop");
+}
+
+extern "C" int semb_loss_wbce(const semb_tensor* p, const float* y_true, const semb_tensor* dp, int64_t count,
+                              float weighting, float* out, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(p) && y_true && out && count > 0 && (!dp || view_ok(dp)), SEMB_ESHAPE, "loss_wbce: bad arguments");
+    if (dtype == SEMB_BF16) loss_wbce_kernel<bf16><<<grid_for(count), 256, 0, as_stream(stream)>>>(pv(p), y_true, pv(dp), count, weighting, out);
+    else loss_wbce_kernel<float><<<grid_for(count), 256, 0, as_stream(stream)>>>(pv(p), y_true, pv(dp), count, weighting, out);
+    return check_launch("loss_wbce");
+}
+
+extern "C" int semb_loss_l1_l2(const semb_tensor* a, const semb_tensor* b, float target, int32_t kind, int64_t n_pixels,
+                               int32_t c_logical, float gscale, const semb_tensor* da, int32_t accumulate, float* out,
+                               int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(a) && (!b || (view_ok(b) && b->C == a->C)) && (!da || (view_ok(da) && da->C == a->C)) && out && n_pixels > 0,
+                 SEMB_ESHAPE, "loss_l1_l2: bad arguments");
+    SEMB_REQUIRE(kind == 0 || kind == 1, SEMB_ESHAPE, "loss_l1_l2: kind must be 0 (L1) or 1 (L2)");
+    const int C8 = a->C / 8;
+    const long long total = n_pixels * C8;
+    if (dtype == SEMB_BF16) loss_l1_l2_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(a), pv(b), target, kind, n_pixels, C8, c_logical, gscale, pv(da), accumulate, out);
+    else loss_l1_l2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(a), pv(b), target, kind, n_pixels, C8, c_logical, gscale, pv(da), accumulate, out);
+    return check_launch("loss_l1_l2");
+}
+
+extern "C" int semb_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const float* lr_ptr, float beta1,
+                              float beta2, float eps, float gscale, void* state, void* stream) {
+    SEMB_REQUIRE(w && g && m && v && lr_ptr && state && n > 0, SEMB_ESHAPE, "adam: bad arguments");
+    SEMB_REQUIRE(((uintptr_t)w % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0,
+                 SEMB_EALIGN, "adam: buffers must be 16B aligned");
+    adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<AdamState*>(state), lr_ptr, beta1, beta2);
+    int rc = check_launch("adam_tick");
+    if (rc) return rc;
+    adam_kernel<<<grid_for(cdivl(n, 4)), 256, 0, as_stream(stream)>>>(w, g, m, v, n, reinterpret_cast<const AdamState*>(state), beta1, beta2, eps, gscale);
+    return check_launch("adam");
+}
+
+extern "C" int semb_fill_f32(float* p, int64_t n, float value, void* stream) {
+    SEMB_REQUIRE(p && n >= 0, SEMB_ESHAPE, "fill: bad arguments");
+    if (n == 0) return SEMB_OK;
+    fill_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, n, value);
+    return check_launch("fill");
+}
+
+extern "C" int semb_cast_in(const float* src, int32_t src_C, const semb_tensor* dst, int64_t n_pixels, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(src && view_ok(dst) && n_pixels > 0 && src_C > 0 && src_C <= dst->C, SEMB_ESHAPE, "cast_in: bad arguments");
+    const int C8 = dst->C / 8;
+    if (dtype == SEMB_BF16) cast_in_kernel<bf16><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(src, src_C, pv(dst), n_pixels, C8);
+    else cast_in_kernel<float><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(src, src_C, pv(dst), n_pixels, C8);
+    return check_launch("cast_in");
+}
+
+extern "C" int semb_cast_out(const semb_tensor* src, float* dst, int32_t dst_C, int64_t n_pixels, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(dst && view_ok(src) && n_pixels > 0 && dst_C > 0 && dst_C <= src->C, SEMB_ESHAPE, "cast_out: bad arguments");
+    const int C8 = src->C / 8;
+    if (dtype == SEMB_BF16) cast_out_kernel<bf16><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(pv(src), dst, dst_C, n_pixels, C8);
+    else cast_out_kernel<float><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(pv(src), dst, dst_C, n_pixels, C8);
+    return check_launch("cast_out");
+}

@@ -1,0 +1,534 @@
+"""Static-graph executor over libsemb200.so.
+
+A network is a list of ops recorded once for a fixed (N, H, W); `forward()` replays the list,
+`backward()` replays it in reverse calling each op's hand-written gradient.  torch is used only to
+own device memory, streams and CUDA graphs; all arithmetic happens in the C-ABI kernels.
+
+Channel padding: every activation buffer stores its channels in a *physical* layout whose segments
+are padded to multiples of 8 (see include/semb200.h).  `Layout` keeps the logical<->physical map;
+parameters are stored physically (zero in the padded rows/columns) in flat fp32 buffers so that Adam
+and the NCCL all-reduce each run over ONE contiguous tensor per network.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def pad8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+class Layout:
+    """Channel layout: list of (logical_len, physical_len) segments."""
+
+    def __init__(self, segs: Sequence[Tuple[int, int]]):
+        self.segs = [(int(l), int(p)) for l, p in segs]
+        self.logical = sum(l for l, _ in self.segs)
+        self.phys = sum(p for _, p in self.segs)
+
+    @staticmethod
+    def simple(c: int) -> "Layout":
+        return Layout([(c, pad8(c))])
+
+    @staticmethod
+    def concat(*layouts: "Layout") -> "Layout":
+        segs = []
+        for l in layouts:
+            segs.extend(l.segs)
+        return Layout(segs)
+
+    def index_map(self) -> np.ndarray:
+        """physical index of every logical channel"""
+        out, base = [], 0
+        for l, p in self.segs:
+            out.extend(range(base, base + l))
+            base += p
+        return np.asarray(out, dtype=np.int64)
+
+
+class View:
+    """Channel slice of a Buf (what the C ABI calls semb_tensor)."""
+
+    def __init__(self, buf: "Buf", coff: int, c: int, layout: Optional[Layout] = None):
+        assert coff % 8 == 0 and c % 8 == 0 and coff + c <= buf.pitch, (coff, c, buf.pitch)
+        self.buf, self.coff, self.C = buf, coff, c
+        self.layout = layout
+        self._t = None
+        self._g = None
+
+    @property
+    def t(self) -> L.Tensor:
+        if self._t is None:
+            self._t = L.Tensor(self.buf.data.data_ptr(), self.C, self.buf.pitch, self.coff)
+        return self._t
+
+    @property
+    def g(self) -> L.Tensor:
+        if self._g is None:
+            self._g = L.Tensor(self.buf.grad_tensor().data_ptr(), self.C, self.buf.pitch, self.coff)
+        return self._g
+
+    @property
+    def requires_grad(self):
+        return self.buf.requires_grad
+
+    def torch_view(self, grad: bool = False) -> torch.Tensor:
+        t = self.buf.grad_tensor() if grad else self.buf.data
+        return t[..., self.coff:self.coff + self.C]
+
+
+class Buf:
+    def __init__(self, eng: "Engine", n: int, h: int, w: int, pitch: int, name: str, requires_grad: bool = True):
+        assert pitch % 8 == 0
+        self.eng, self.N, self.H, self.W, self.pitch, self.name = eng, n, h, w, pitch, name
+        self.requires_grad = requires_grad
+        self.data = torch.zeros((n, h, w, pitch), dtype=eng.tdtype, device=eng.device)
+        self._grad = None
+        self.grad_cover: List[Tuple[int, int]] = []  # channel intervals already written in this backward plan
+
+    def grad_tensor(self) -> torch.Tensor:
+        if self._grad is None:
+            self._grad = torch.zeros_like(self.data)
+        return self._grad
+
+    def view(self, coff: int = 0, c: Optional[int] = None, layout: Optional[Layout] = None) -> View:
+        return View(self, coff, self.pitch - coff if c is None else c, layout)
+
+
+class FlatStore:
+    """Named fp32 slices of one flat device tensor (parameters, optimizer state, scratch)."""
+
+    def __init__(self):
+        self.entries: Dict[str, Tuple[int, int]] = {}
+        self.order: List[str] = []
+        self.size = 0
+        self.t: Optional[torch.Tensor] = None
+
+    def add(self, name: str, n: int) -> str:
+        assert name not in self.entries, name
+        n4 = (n + 3) // 4 * 4
+        self.entries[name] = (self.size, n)
+        self.order.append(name)
+        self.size += n4
+        return name
+
+    def alloc(self, device):
+        self.t = torch.zeros(max(self.size, 4), dtype=torch.float32, device=device)
+
+    def ptr(self, name: str, extra: int = 0) -> int:
+        return self.t.data_ptr() + 4 * (self.entries[name][0] + extra)
+
+    def get(self, name: str) -> torch.Tensor:
+        o, n = self.entries[name]
+        return self.t[o:o + n]
+
+
+class ParamSpec:
+    """One Keras variable: logical shape + how its channel axes map into the physical tensor."""
+
+    def __init__(self, name: str, kind: str, logical_shape, phys_shape, axis_maps: Dict[int, np.ndarray], trainable: bool,
+                 init: str = "zeros", fans: Tuple[int, int] = (1, 1)):
+        self.name, self.kind = name, kind
+        self.logical_shape, self.phys_shape = tuple(logical_shape), tuple(phys_shape)
+        self.axis_maps, self.trainable, self.init, self.fans = axis_maps, trainable, init, fans
+
+    def to_phys(self, arr: np.ndarray) -> np.ndarray:
+        arr = np.asarray(arr, dtype=np.float32)
+        assert tuple(arr.shape) == self.logical_shape, (self.name, arr.shape, self.logical_shape)
+        out = np.zeros(self.phys_shape, dtype=np.float32)
+        idx = [np.arange(s) for s in self.logical_shape]
+        for ax, m in self.axis_maps.items():
+            idx[ax] = m
+        out[np.ix_(*idx)] = arr
+        return out
+
+    def to_logical(self, phys: np.ndarray) -> np.ndarray:
+        idx = [np.arange(s) for s in self.logical_shape]
+        for ax, m in self.axis_maps.items():
+            idx[ax] = m
+        return np.ascontiguousarray(phys.reshape(self.phys_shape)[np.ix_(*idx)])
+
+
+class Engine:
+    """Owns buffers, parameters, scratch and the op list of ONE network instance."""
+
+    def __init__(self, n: int, dtype: str = "bf16", device: Optional[torch.device] = None, dry: bool = False):
+        # dry=True builds the op list / parameter maps on the CPU for host-logic tests; nothing can execute.
+        self.dry = dry
+        if not dry:
+            L.require_device()
+        self.lib = L.load()
+        self.N = n
+        self.dtype_name = dtype
+        self.dtype = L.BF16 if dtype == "bf16" else L.F32
+        self.tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        self.device = device or (torch.device("cpu") if dry else torch.device("cuda", torch.cuda.current_device()))
+        self.ops: List["Op"] = []
+        self.params = FlatStore()        # trainable
+        self.state = FlatStore()         # moving statistics
+        self.zeroed = FlatStore()        # scratch that must be zero at step start (moments, bwd sums, loss sums)
+        self.scratch = FlatStore()       # scale/shift/mean/invstd/c1/c2
+        self.specs: Dict[str, ParamSpec] = {}
+        self.spec_order: List[str] = []
+        self.bufs: List[Buf] = []
+        self.finalized = False
+        self.grads = self.adam_m = self.adam_v = None
+        self._keep = []
+
+    # ---- construction ------------------------------------------------------------------
+    def new_buf(self, h: int, w: int, pitch: int, name: str, requires_grad: bool = True, n: Optional[int] = None) -> Buf:
+        b = Buf(self, self.N if n is None else n, h, w, pitch, name, requires_grad)
+        self.bufs.append(b)
+        return b
+
+    def add_param(self, spec: ParamSpec):
+        self.specs[spec.name] = spec
+        self.spec_order.append(spec.name)
+        store = self.params if spec.trainable else self.state
+        store.add(spec.name, int(np.prod(spec.phys_shape)))
+
+    def add_op(self, op: "Op"):
+        self.ops.append(op)
+        return op
+
+    def finalize(self):
+        for s in (self.params, self.state, self.zeroed, self.scratch):
+            s.alloc(self.device)
+        self.grads = torch.zeros_like(self.params.t)
+        self.adam_m = torch.zeros_like(self.params.t)
+        self.adam_v = torch.zeros_like(self.params.t)
+        self.adam_state = torch.zeros(4, dtype=torch.int32, device=self.device)   # {int64 t; float alpha; float pad}
+        self.lr = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # static plan of gradient accumulation: walk the ops in backward order once
+        for op in reversed(self.ops):
+            op.plan_backward()
+        self.finalized = True
+
+    def gptr(self, name: str) -> int:
+        o, _ = self.params.entries[name]
+        return self.grads.data_ptr() + 4 * o
+
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- weights -------------------------------------------------------------------------
+    def set_param(self, name: str, arr: np.ndarray):
+        spec = self.specs[name]
+        store = self.params if spec.trainable else self.state
+        store.get(name).copy_(torch.from_numpy(spec.to_phys(arr).reshape(-1)))
+
+    def get_param(self, name: str) -> np.ndarray:
+        spec = self.specs[name]
+        store = self.params if spec.trainable else self.state
+        return spec.to_logical(store.get(name).detach().cpu().numpy())
+
+    def get_grad(self, name: str) -> np.ndarray:
+        spec = self.specs[name]
+        o, n = self.params.entries[name]
+        return spec.to_logical(self.grads[o:o + n].detach().cpu().numpy())
+
+    def init_params(self, seed: int = 0):
+        """Glorot-uniform kernels, zeros / ones elsewhere, drawn in creation order from one generator."""
+        gen = torch.Generator().manual_seed(seed)
+        for name in self.spec_order:
+            spec = self.specs[name]
+            if spec.init == "glorot":
+                fi, fo = spec.fans
+                limit = float(np.sqrt(6.0 / (fi + fo)))
+                arr = ((torch.rand(spec.logical_shape, generator=gen) * 2.0 - 1.0) * limit).numpy()
+            elif spec.init == "ones":
+                arr = np.ones(spec.logical_shape, dtype=np.float32)
+            else:
+                arr = np.zeros(spec.logical_shape, dtype=np.float32)
+            self.set_param(name, arr)
+
+    # ---- execution -------------------------------------------------------------------------
+    def zero_step(self, zero_grads: bool):
+        st = self.stream
+        L.check(self.lib.semb_fill_f32(self.zeroed.t.data_ptr(), self.zeroed.t.numel(), 0.0, st))
+        if zero_grads:
+            L.check(self.lib.semb_fill_f32(self.grads.data_ptr(), self.grads.numel(), 0.0, st))
+
+    def forward(self, training: bool):
+        if self.dry:
+            raise L.SembError("dry engine: kernels need an sm_100a device, there is no CPU execution path")
+        for op in self.ops:
+            op.fwd(training)
+
+    def backward(self):
+        for op in reversed(self.ops):
+            op.bwd()
+
+    def adam(self, beta1: float, beta2: float, eps: float, gscale: float = 1.0):
+        L.check(self.lib.semb_adam_step(self.params.t.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                        self.adam_v.data_ptr(), self.params.t.numel(), self.lr.data_ptr(),
+                                        beta1, beta2, eps, gscale, self.adam_state.data_ptr(), self.stream))
+
+
+def plan_grad_write(view: View) -> int:
+    """Returns the accumulate flag for a gradient write into `view` at this point of the backward plan."""
+    lo, hi = view.coff, view.coff + view.C
+    cover = view.buf.grad_cover
+    inside = any(a <= lo and hi <= b for a, b in cover)
+    if inside:
+        return 1
+    overlap = any(not (hi <= a or b <= lo) for a, b in cover)
+    if overlap:
+        # a wider write after narrower ones: the kernels would overwrite the earlier slices
+        raise RuntimeError(f"partial gradient overlap on {view.buf.name}: {cover} vs ({lo},{hi})")
+    cover.append((lo, hi))
+    return 0
+
+
+class Op:
+    eng: Engine
+
+    def plan_backward(self):
+        pass
+
+    def fwd(self, training: bool):
+        raise NotImplementedError
+
+    def bwd(self):
+        pass
+
+
+# --------------------------------------------------------------------------------------------------
+class ConvOp(Op):
+    """Conv2D (transposed=False) or Conv2DTranspose (transposed=True).
+
+    For transposed=True the geometry describes the equivalent strided conv that maps the OUTPUT of the
+    transposed conv back to its INPUT (see semb_conv2d_dgrad in semb200.h); x is the small tensor."""
+
+    def __init__(self, eng: Engine, x: View, y: View, hw_in: Tuple[int, int], hw_out: Tuple[int, int], w: str,
+                 bias: Optional[str], k: int, stride: int, pad_tl: Tuple[int, int], pad_mode: int, transposed: bool,
+                 stats: Optional[Tuple[str, int, int, int]] = None, n: Optional[int] = None):
+        self.eng, self.x, self.y, self.w, self.bias, self.transposed = eng, x, y, w, bias, transposed
+        n = eng.N if n is None else n
+        if not transposed:
+            h, wd = hw_in
+            oh, ow = hw_out
+            cin, cout = x.C, y.C
+        else:
+            oh, ow = hw_in     # the transposed conv's input is the strided conv's output
+            h, wd = hw_out
+            cin, cout = y.C, x.C
+        self.geom = L.ConvGeom(n, h, wd, oh, ow, cin, cout, k, k, stride, pad_tl[0], pad_tl[1], pad_mode, eng.dtype)
+        self.stats = stats  # (zeroed-store name, offset, nstride, cstride)
+        self.acc_x = 0
+
+    def plan_backward(self):
+        if self.x.requires_grad:
+            self.acc_x = plan_grad_write(self.x)
+
+    def _stats_args(self):
+        if self.stats is None:
+            return None, 0, 0
+        name, off, ns, cs = self.stats
+        return self.eng.zeroed.ptr(name, 2 * off), ns, cs      # offsets/strides are in doubles
+
+    def fwd(self, training: bool):
+        e = self.eng
+        sp, ns, cs = self._stats_args() if training else (None, 0, 0)
+        bias = e.params.ptr(self.bias) if self.bias else None
+        fn = e.lib.semb_conv2d_dgrad if self.transposed else e.lib.semb_conv2d_fwd
+        L.check(fn(C.byref(self.geom), C.byref(self.x.t), e.params.ptr(self.w), bias, C.byref(self.y.t), sp, ns, cs, 0,
+                   e.stream))
+
+    def bwd(self):
+        e = self.eng
+        dbias = e.gptr(self.bias) if self.bias else None
+        if not self.transposed:
+            L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w), dbias,
+                                            e.stream))
+            if self.x.requires_grad:
+                L.check(e.lib.semb_conv2d_dgrad(C.byref(self.geom), C.byref(self.y.g), e.params.ptr(self.w), None,
+                                                C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
+        else:
+            # d/dw of the transposed conv: wgrad of the equivalent conv with x':=d(out), dy':=in
+            L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.y.g), C.byref(self.x.t), e.gptr(self.w), None,
+                                            e.stream))
+            if dbias:
+                L.check(e.lib.semb_channel_sum(C.byref(self.y.g), self.geom.N, self.geom.H * self.geom.W, dbias, e.dtype,
+                                               e.stream))
+            if self.x.requires_grad:
+                L.check(e.lib.semb_conv2d_fwd(C.byref(self.geom), C.byref(self.y.g), e.params.ptr(self.w), None,
+                                              C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
+
+
+class NormOp(Op):
+    """Turns accumulated moments into (scale, shift, mean, invstd); BatchNorm (groups=1) or InstanceNorm (groups=N).
+
+    Owns the per-layer scratch.  Has no backward of its own: the gradient w.r.t. gamma/beta and the
+    normalisation terms are produced by the AffineOp that applies this norm."""
+
+    def __init__(self, eng: Engine, name: str, c: int, count: float, eps: float, gamma: Optional[str], beta: str,
+                 moving: Optional[Tuple[str, str]], momentum: float, groups: int = 1):
+        self.eng, self.name, self.C, self.count, self.eps = eng, name, c, float(count), eps
+        self.gamma, self.beta, self.moving, self.momentum, self.groups = gamma, beta, moving, momentum, groups
+        self.stats = eng.zeroed.add(name + "/moments", 4 * c * groups)   # fp64 accumulators: 2 moments x C x groups
+        self.sums = eng.zeroed.add(name + "/bwd_sums", 4 * c * groups)
+        for k in ("scale", "shift", "mean", "invstd", "c1", "c2"):
+            eng.scratch.add(f"{name}/{k}", c * groups)
+        self.nstride = 0 if groups == 1 else c
+        self.stats_nstride = 0 if groups == 1 else 2 * c
+
+    def s(self, k: str) -> int:
+        return self.eng.scratch.ptr(f"{self.name}/{k}")
+
+    def stats_ref(self, coff: int = 0):
+        return (self.stats, coff, self.stats_nstride, self.C)
+
+    def fwd(self, training: bool):
+        e = self.eng
+        gamma = e.params.ptr(self.gamma) if self.gamma else None
+        beta = e.params.ptr(self.beta)
+        if training or self.moving is None:
+            mm = e.state.ptr(self.moving[0]) if (self.moving and training) else None
+            mv = e.state.ptr(self.moving[1]) if (self.moving and training) else None
+            L.check(e.lib.semb_norm_finalize(e.zeroed.ptr(self.stats), self.groups, self.C, self.C, self.stats_nstride,
+                                             self.count, self.eps, gamma, beta, self.s("scale"), self.s("shift"),
+                                             self.s("mean"), self.s("invstd"), mm, mv, self.momentum, e.stream))
+        else:
+            L.check(e.lib.semb_norm_from_moving(self.C, self.eps, gamma, beta, e.state.ptr(self.moving[0]),
+                                                e.state.ptr(self.moving[1]), self.s("scale"), self.s("shift"), e.stream))
+
+    def uses_batch_stats(self, training: bool) -> bool:
+        return training or self.moving is None
+
+
+class AffineOp(Op):
+    """y = act( A(a) + actb(B(b)) ) with A/B the affines of NormOps (or identity), optional moments of y."""
+
+    def __init__(self, eng: Engine, hw: int, a: View, norm_a: Optional[NormOp], b: Optional[View], norm_b: Optional[NormOp],
+                 y: View, act: int, actb: int = L.ACT_NONE, stats_out: Optional[Tuple[str, int, int, int]] = None,
+                 n: Optional[int] = None):
+        self.eng, self.a, self.b, self.y, self.norm_a, self.norm_b = eng, a, b, y, norm_a, norm_b
+        self.act, self.actb, self.stats_out = act, actb, stats_out
+        self.coff_a = 0
+        self.hw = hw
+        self.n = eng.N if n is None else n
+        self.acc_a = self.acc_b = 0
+        groups = max(norm_a.groups if norm_a else 1, norm_b.groups if norm_b else 1)
+        self.aff_nstride = 0 if groups == 1 else (norm_a or norm_b).C
+
+    def plan_backward(self):
+        if self.a.requires_grad:
+            self.acc_a = plan_grad_write(self.a)
+        if self.b is not None and self.b.requires_grad:
+            self.acc_b = plan_grad_write(self.b)
+
+    def _desc(self, training: bool) -> L.AffineDesc:
+        def mode(norm):
+            if norm is None:
+                return L.AFF_NONE
+            return L.AFF_BATCH if norm.uses_batch_stats(training) else L.AFF_PLAIN
+        return L.AffineDesc(self.n, self.hw, self.a.C, self.eng.dtype, self.act, self.actb, mode(self.norm_a),
+                            mode(self.norm_b) if self.b is not None else L.AFF_NONE, self.aff_nstride)
+
+    def _p(self, norm: Optional[NormOp], key: str, coff: int) -> Optional[int]:
+        return None if norm is None else norm.s(key) + 4 * coff
+
+    def fwd(self, training: bool):
+        e = self.eng
+        d = self._desc(training)
+        self._last_desc = d
+        sp, ns, cs = (None, 0, 0)
+        if self.stats_out is not None and training:
+            name, off, ns, cs = self.stats_out
+            sp = e.zeroed.ptr(name, 2 * off)
+        L.check(e.lib.semb_affine_act_fwd(
+            C.byref(d), C.byref(self.a.t), self._p(self.norm_a, "scale", self.coff_a), self._p(self.norm_a, "shift", self.coff_a),
+            C.byref(self.b.t) if self.b is not None else None, self._p(self.norm_b, "scale", 0), self._p(self.norm_b, "shift", 0),
+            C.byref(self.y.t), sp, ns, cs, e.stream))
+
+    def bwd(self):
+        e = self.eng
+        d = self._last_desc
+        na, nb = self.norm_a, self.norm_b
+        ca = self.coff_a
+        bt = C.byref(self.b.t) if self.b is not None else None
+        red_a = d.mode_a == L.AFF_BATCH
+        red_b = self.b is not None and d.mode_b == L.AFF_BATCH
+        # the bwd sums of this op live in norm_a's (resp. norm_b's) scratch; slot [0,1] = a-terms, [2,3] = b-terms
+        if red_a or red_b:
+            owner = na if red_a else nb
+            sums = e.zeroed.ptr(owner.sums, ca if red_a else 0)
+            cs = owner.C
+            ns = 0 if owner.groups == 1 else 4 * owner.C
+            L.check(e.lib.semb_affine_act_bwd_reduce(
+                C.byref(d), C.byref(self.y.g), C.byref(self.y.t), C.byref(self.a.t), bt,
+                self._p(na, "mean", ca), self._p(na, "invstd", ca), self._p(nb, "scale", 0), self._p(nb, "shift", 0),
+                self._p(nb, "mean", 0), self._p(nb, "invstd", 0), sums, ns, cs, e.stream))
+            if red_a:
+                dg = e.gptr(na.gamma) + 4 * ca if na.gamma else None
+                db = e.gptr(na.beta) + 4 * ca
+                L.check(e.lib.semb_norm_bwd_finalize(sums, 0, na.groups, self.a.C, cs, ns, na.count, None, None,
+                                                     self._p(na, "c1", ca), self._p(na, "c2", ca), dg, db, e.stream))
+            if red_b:
+                dg = e.gptr(nb.gamma) if nb.gamma else None
+                db = e.gptr(nb.beta)
+                # b-terms were written at slots 2,3 of `sums`; c1/c2 of norm_b use its own arrays.  When the owner of
+                # the sums buffer is norm_a (different C stride) the b-sums still sit at 2*cs, 3*cs.
+                L.check(e.lib.semb_norm_bwd_finalize(sums, 1, nb.groups, self.a.C, cs, ns, nb.count, None, None,
+                                                     self._p(nb, "c1", 0), self._p(nb, "c2", 0), dg, db, e.stream))
+        da = C.byref(self.a.g) if self.a.requires_grad else None
+        dbv = C.byref(self.b.g) if (self.b is not None and self.b.requires_grad) else None
+        if da is None and dbv is None:
+            return
+        L.check(e.lib.semb_affine_act_bwd_apply(
+            C.byref(d), C.byref(self.y.g), C.byref(self.y.t), C.byref(self.a.t), bt,
+            self._p(na, "scale", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca), self._p(na, "c1", ca), self._p(na, "c2", ca),
+            self._p(nb, "scale", 0), self._p(nb, "shift", 0), self._p(nb, "mean", 0), self._p(nb, "invstd", 0),
+            self._p(nb, "c1", 0), self._p(nb, "c2", 0), da, self.acc_a, dbv, self.acc_b, e.stream))
+
+
+class PoolOp(Op):
+    def __init__(self, eng: Engine, x: View, y: View, h: int, w: int):
+        self.eng, self.x, self.y, self.h, self.w = eng, x, y, h, w
+        self.acc = 0
+
+    def plan_backward(self):
+        self.acc = plan_grad_write(self.x)
+
+    def fwd(self, training: bool):
+        e = self.eng
+        L.check(e.lib.semb_maxpool2x2_fwd(C.byref(self.x.t), C.byref(self.y.t), e.N, self.h, self.w, e.dtype, e.stream))
+
+    def bwd(self):
+        e = self.eng
+        L.check(e.lib.semb_maxpool2x2_bwd(C.byref(self.x.t), C.byref(self.y.g), C.byref(self.x.g), e.N, self.h, self.w,
+                                          e.dtype, self.acc, e.stream))
+
+
+class PadCropOp(Op):
+    """mode 'reflect' (ReflectionPadding2D) or 'crop' (Cropping2D)."""
+
+    def __init__(self, eng: Engine, x: View, y: View, hw_in, hw_out, top: int, left: int, mode: str):
+        self.eng, self.x, self.y, self.hw_in, self.hw_out, self.top, self.left, self.mode = eng, x, y, hw_in, hw_out, top, left, mode
+        self.acc = 0
+
+    def plan_backward(self):
+        if self.x.requires_grad:
+            self.acc = plan_grad_write(self.x)
+
+    def fwd(self, training: bool):
+        e = self.eng
+        m = 0 if self.mode == "reflect" else 1
+        L.check(e.lib.semb_pad_crop(C.byref(self.x.t), C.byref(self.y.t), e.N, self.hw_in[0], self.hw_in[1], self.hw_out[0],
+                                    self.hw_out[1], self.top, self.left, m, e.dtype, 0, e.stream))
+
+    def bwd(self):
+        if not self.x.requires_grad:
+            return
+        e = self.eng
+        m = 3 if self.mode == "reflect" else 2
+        L.check(e.lib.semb_pad_crop(C.byref(self.y.g), C.byref(self.x.g), e.N, self.hw_out[0], self.hw_out[1], self.hw_in[0],
+                                    self.hw_in[1], self.top, self.left, m, e.dtype, self.acc, e.stream))

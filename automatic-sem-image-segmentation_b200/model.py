@@ -1,0 +1,406 @@
+"""Keras-`Model`-shaped front end over the engine: `model(x, training)`, `get_weights/set_weights`,
+`compile`, `train_step`, `fit`, `save` / `load_model`.
+
+It mirrors the protocol the reference relies on (SURVEY.md 8b "Model call protocol"): NHWC float32 in and
+out, weights as a list of numpy arrays in keras.Model.layers order, Keras' TorchTrainer.train_step
+sequence (forward(training=True) -> loss -> backward -> Adam -> metrics) [K3.5].
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import Engine
+from .nets import UNetBuilder
+
+
+def _to_numpy(x) -> np.ndarray:
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+class _Instance:
+    """One engine specialised to (N, H, W)."""
+
+    def __init__(self, n, h, w, filters, dtype):
+        self.eng = Engine(n, dtype)
+        self.net = UNetBuilder(self.eng, h, w, filters)
+        e = self.eng
+        self.loss_sums = e.zeroed.add("loss/sums", 4)
+        e.finalize()
+        self.n, self.h, self.w = n, h, w
+        self.x_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
+        self.y_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
+        self.out_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
+        self.x_pin = torch.zeros((n, h, w, 1), dtype=torch.float32).pin_memory()
+        self.y_pin = torch.zeros((n, h, w, 1), dtype=torch.float32).pin_memory()
+        self.out_pin = torch.zeros((n, h, w, 1), dtype=torch.float32).pin_memory()
+        self.sums_pin = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_key = None
+
+    # ---- pieces of a step (all asynchronous on the current stream) ---------------------------------
+    def stage_in(self):
+        e = self.eng
+        L.check(e.lib.semb_cast_in(self.x_dev.data_ptr(), 1, C.byref(self.net.in_buf.view().t), self.n * self.h * self.w,
+                                   e.dtype, e.stream))
+
+    def stage_out(self):
+        e = self.eng
+        L.check(e.lib.semb_cast_out(C.byref(self.net.out_buf.view().t), self.out_dev.data_ptr(), 1, self.n * self.h * self.w,
+                                    e.dtype, e.stream))
+
+    def loss(self, weighting: float, with_grad: bool):
+        e = self.eng
+        ov = self.net.out_buf.view()
+        L.check(e.lib.semb_loss_wbce(C.byref(ov.t), self.y_dev.data_ptr(), C.byref(ov.g) if with_grad else None,
+                                     self.n * self.h * self.w, float(weighting), e.zeroed.ptr(self.loss_sums), e.dtype,
+                                     e.stream))
+
+    def fwd_bwd(self, weighting: float):
+        e = self.eng
+        e.zero_step(zero_grads=True)
+        self.stage_in()
+        e.forward(training=True)
+        self.loss(weighting, with_grad=True)
+        e.backward()
+
+
+class UNetModel:
+    """MultiRes-UNet with the Keras model protocol, running on libsemb200 (sm_100a) only."""
+
+    def __init__(self, input_shape=(256, 256, 1), filters: int = 16, output_channels: int = 1, dtype: str = "f32",
+                 batch_size: int = 1, seed: int = 0, use_cuda_graph: bool = True):
+        if len(input_shape) == 2:
+            input_shape = (input_shape[0], input_shape[1], 1)
+        assert input_shape[2] == 1 and output_channels == 1
+        self.input_shape = tuple(input_shape)
+        self.filters, self.dtype, self.seed = filters, dtype, seed
+        self.use_cuda_graph = use_cuda_graph
+        self._instances: Dict[tuple, _Instance] = {}
+        self._primary = self._instance(batch_size, input_shape[0], input_shape[1], init=True)
+        self._current = self._primary
+        self.weighting = 1.0
+        self.learning_rate = 1e-3
+        self.beta_1, self.beta_2, self.epsilon = 0.9, 0.999, 1e-7
+        self.world_size, self.rank = 1, 0
+        self.process_group = None
+        self.stop_training = False
+        self.history: List[dict] = []
+
+    # ---- instances -----------------------------------------------------------------------------------
+    def _instance(self, n, h, w, init=False) -> _Instance:
+        key = (n, h, w)
+        inst = self._instances.get(key)
+        if inst is None:
+            inst = _Instance(n, h, w, self.filters, self.dtype)
+            if init:
+                inst.eng.init_params(self.seed)
+            self._instances[key] = inst
+        return inst
+
+    def _use(self, inst: _Instance):
+        """Make `inst` hold the live weights (instances share nothing; parameters are copied flat)."""
+        cur = self._current
+        if inst is not cur:
+            inst.eng.params.t.copy_(cur.eng.params.t)
+            inst.eng.state.t.copy_(cur.eng.state.t)
+            inst.eng.adam_m.copy_(cur.eng.adam_m)
+            inst.eng.adam_v.copy_(cur.eng.adam_v)
+            inst.eng.adam_state.copy_(cur.eng.adam_state)
+            self._current = inst
+        return inst
+
+    @property
+    def engine(self) -> Engine:
+        return self._current.eng
+
+    # ---- Keras weight protocol -----------------------------------------------------------------------
+    def weight_names(self) -> List[str]:
+        """Variable names in keras.Model.get_weights() order."""
+        return self._primary.net.keras_weight_names()
+
+    def creation_names(self) -> List[str]:
+        return list(self._primary.net.creation_names)
+
+    def get_weights(self) -> List[np.ndarray]:
+        e = self._current.eng
+        return [e.get_param(n) for n in self.weight_names()]
+
+    def set_weights(self, weights: Sequence[np.ndarray]):
+        names = self.weight_names()
+        if len(weights) != len(names):
+            raise ValueError(f"You called `set_weights(weights)` on a model with {len(names)} weights, "
+                             f"but provided {len(weights)}")
+        e = self._current.eng
+        for n, w in zip(names, weights):
+            e.set_param(n, _to_numpy(w))
+
+    def get_named_weights(self) -> Dict[str, np.ndarray]:
+        e = self._current.eng
+        return {n: e.get_param(n) for n in self.creation_names()}
+
+    def set_named_weights(self, named: Dict[str, np.ndarray]):
+        e = self._current.eng
+        for n in self.creation_names():
+            e.set_param(n, _to_numpy(named[n]))
+
+    def count_params(self) -> int:
+        e = self._primary.eng
+        return int(sum(np.prod(e.specs[n].logical_shape) for n in self.creation_names()))
+
+    def to(self, device):
+        if str(device).startswith("cpu"):
+            raise L.SembError("this model runs on sm_100a only; there is no CPU path (use the reference for CPU inference)")
+        return self
+
+    # ---- inference -----------------------------------------------------------------------------------
+    def __call__(self, x, training: bool = False):
+        x = _to_numpy(x).astype(np.float32, copy=False)
+        if x.ndim != 4 or x.shape[3] != 1:
+            raise ValueError(f"expected NHWC input with one channel, got {x.shape}")
+        inst = self._use(self._instance(x.shape[0], x.shape[1], x.shape[2]))
+        e = inst.eng
+        inst.x_pin.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+        inst.x_dev.copy_(inst.x_pin, non_blocking=True)
+        if training:
+            e.zero_step(zero_grads=False)
+        inst.stage_in()
+        e.forward(training=training)
+        inst.stage_out()
+        inst.out_pin.copy_(inst.out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return inst.out_pin.clone()
+
+    def predict(self, x, batch_size: int = 8):
+        x = _to_numpy(x)
+        outs = [self(x[i:i + batch_size]).numpy() for i in range(0, x.shape[0], batch_size)]
+        return np.concatenate(outs, 0)
+
+    # ---- training ------------------------------------------------------------------------------------
+    def compile(self, weighting: float = 1.0, learning_rate: float = 1e-3, beta_1: float = 0.9, beta_2: float = 0.999,
+                epsilon: float = 1e-7):
+        self.weighting = float(weighting)
+        self.learning_rate = float(learning_rate)
+        self.beta_1, self.beta_2, self.epsilon = beta_1, beta_2, epsilon
+
+    def set_distributed(self, process_group=None):
+        """Data parallel over torch.distributed (NCCL): one flat all-reduce of the gradient buffer per step."""
+        import torch.distributed as dist
+        self.process_group = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        dist.broadcast(self._current.eng.params.t, src=0, group=process_group)
+        dist.broadcast(self._current.eng.state.t, src=0, group=process_group)
+
+    def _step_device(self, inst: _Instance):
+        """fwd + loss + bwd (+ all-reduce) + Adam on the device; inputs already in inst.x_dev / y_dev."""
+        e = inst.eng
+        e.lr.fill_(self.learning_rate)
+        single = self.world_size == 1
+        if self.use_cuda_graph:
+            key = (self.weighting, self.beta_1, self.beta_2, self.epsilon, self.world_size)
+            if inst.graph is None or inst.graph_key != key:
+                # warm-up run on a side stream (allocates lazy gradient buffers), then capture
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                saved = [t.clone() for t in (e.params.t, e.state.t, e.adam_m, e.adam_v, e.adam_state)]
+                with torch.cuda.stream(s):
+                    inst.fwd_bwd(self.weighting)
+                    e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                for t, sv in zip((e.params.t, e.state.t, e.adam_m, e.adam_v, e.adam_state), saved):
+                    t.copy_(sv)
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    inst.fwd_bwd(self.weighting)
+                    if single:
+                        e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0)
+                g2 = None
+                if not single:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
+                inst.graph, inst.graph2, inst.graph_key = g1, g2, key
+            inst.graph.replay()
+            if not single:
+                self._allreduce(e)
+                inst.graph2.replay()
+        else:
+            inst.fwd_bwd(self.weighting)
+            if not single:
+                self._allreduce(e)
+            e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
+
+    def _allreduce(self, e: Engine):
+        import torch.distributed as dist
+        dist.all_reduce(e.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+
+    def train_step(self, x, y) -> Dict[str, float]:
+        """One TorchTrainer.train_step with HOST inputs: H2D, fwd, loss, bwd, Adam, D2H of the metrics."""
+        x = _to_numpy(x).astype(np.float32, copy=False)
+        y = _to_numpy(y).astype(np.float32, copy=False)
+        inst = self._use(self._instance(x.shape[0], x.shape[1], x.shape[2]))
+        inst.x_pin.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+        inst.y_pin.copy_(torch.from_numpy(np.ascontiguousarray(y)))
+        inst.x_dev.copy_(inst.x_pin, non_blocking=True)
+        inst.y_dev.copy_(inst.y_pin, non_blocking=True)
+        self._step_device(inst)
+        return self._read_metrics(inst)
+
+    def _read_metrics(self, inst: _Instance) -> Dict[str, float]:
+        e = inst.eng
+        inst.sums_pin.copy_(e.zeroed.get(inst.loss_sums), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        cnt = float(inst.n * inst.h * inst.w)
+        s = inst.sums_pin
+        return {"loss": float(s[0]) / cnt, "mae": float(s[1]) / cnt, "acc": float(s[2]) / cnt}
+
+    def test_step(self, x, y) -> Dict[str, float]:
+        x = _to_numpy(x).astype(np.float32, copy=False)
+        y = _to_numpy(y).astype(np.float32, copy=False)
+        inst = self._use(self._instance(x.shape[0], x.shape[1], x.shape[2]))
+        e = inst.eng
+        inst.x_dev.copy_(torch.from_numpy(np.ascontiguousarray(x)))
+        inst.y_dev.copy_(torch.from_numpy(np.ascontiguousarray(y)))
+        e.zero_step(zero_grads=False)
+        inst.stage_in()
+        e.forward(training=False)
+        inst.loss(self.weighting, with_grad=False)
+        return self._read_metrics(inst)
+
+    def fit(self, data, batch_size=None, epochs: int = 1, verbose: int = 1, callbacks=None, validation_data=None):
+        """keras.Model.fit over a Sequence-like object (`__len__`, `__getitem__`, optional `on_epoch_end`)."""
+        callbacks = list(callbacks or [])
+        for cb in callbacks:
+            cb.set_model(self)
+        self.stop_training = False
+        for cb in callbacks:
+            cb.on_train_begin()
+        for epoch in range(epochs):
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch)
+            t0 = time.time()
+            agg: Dict[str, float] = {}
+            nb = len(data)
+            for i in range(nb):
+                xb, yb = data[i]
+                logs = self.train_step(xb, yb)
+                for k, v in logs.items():
+                    agg[k] = agg.get(k, 0.0) + v
+            logs = {k: v / max(nb, 1) for k, v in agg.items()}
+            if validation_data is not None and len(validation_data) > 0:
+                vagg: Dict[str, float] = {}
+                for i in range(len(validation_data)):
+                    xb, yb = validation_data[i]
+                    for k, v in self.test_step(xb, yb).items():
+                        vagg[k] = vagg.get(k, 0.0) + v
+                logs.update({"val_" + k: v / len(validation_data) for k, v in vagg.items()})
+            logs["learning_rate"] = self.learning_rate
+            if verbose and self.rank == 0:
+                msg = " - ".join(f"{k}: {v:.4f}" for k, v in logs.items())
+                print(f"Epoch {epoch + 1}/{epochs} - {time.time() - t0:.1f}s - {msg}", flush=True)
+            self.history.append(dict(logs, epoch=epoch))
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, logs)
+            if hasattr(data, "on_epoch_end"):
+                data.on_epoch_end()
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            cb.on_train_end()
+        return self.history
+
+    # ---- persistence ---------------------------------------------------------------------------------
+    def save(self, path: str):
+        """Writes `<path>` as an .npz of creation-order variables plus a JSON config.  (The reference's
+        `.keras` zip needs h5py, which this image lacks -- SURVEY.md 8f N4.)"""
+        named = self.get_named_weights()
+        cfg = {"class": "MultiResUNet", "input_shape": list(self.input_shape), "filters": self.filters,
+               "dtype": self.dtype, "weighting": self.weighting, "format": "semb200-npz-1"}
+        with open(path, "wb") as fh:
+            np.savez(fh, __config__=np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8), **named)
+
+    @staticmethod
+    def load(path: str, dtype: Optional[str] = None, batch_size: int = 1) -> "UNetModel":
+        with np.load(path) as z:
+            cfg = json.loads(bytes(z["__config__"]).decode())
+            named = {k: z[k] for k in z.files if k != "__config__"}
+        m = UNetModel(tuple(cfg["input_shape"]), cfg["filters"], 1, dtype or cfg["dtype"], batch_size)
+        m.set_named_weights(named)
+        m.weighting = cfg.get("weighting", 1.0)
+        return m
+
+
+def load_model(path: str, custom_objects=None, **kw) -> UNetModel:
+    """keras.models.load_model stand-in (custom_objects accepted and ignored, UNet_Segmentation.py:303)."""
+    return UNetModel.load(path, **kw)
+
+
+# ---- callbacks (the three the reference uses: UNet_Segmentation.py:262-272) --------------------------------
+class Callback:
+    model: UNetModel = None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_train_begin(self): pass
+    def on_train_end(self): pass
+    def on_epoch_begin(self, epoch): pass
+    def on_epoch_end(self, epoch, logs): pass
+
+
+class ModelCheckpoint(Callback):
+    def __init__(self, filepath, monitor="loss", verbose=0, save_best_only=False, mode="min"):
+        self.filepath, self.monitor, self.verbose, self.save_best_only = filepath, monitor, verbose, save_best_only
+        self.best = math.inf if mode == "min" else -math.inf
+        self.mode = mode
+
+    def on_epoch_end(self, epoch, logs):
+        if self.model.rank != 0:
+            return
+        path = self.filepath.format(epoch=epoch + 1)
+        cur = logs.get(self.monitor)
+        if self.save_best_only:
+            better = cur is not None and (cur < self.best if self.mode == "min" else cur > self.best)
+            if not better:
+                return
+            self.best = cur
+        if self.verbose:
+            print(f"Epoch {epoch + 1}: saving model to {path}")
+        self.model.save(path)
+
+
+class CSVLogger(Callback):
+    def __init__(self, filename, separator=",", append=False):
+        self.filename, self.sep, self.append = filename, separator, append
+        self.keys = None
+
+    def on_epoch_end(self, epoch, logs):
+        if self.model.rank != 0:
+            return
+        new = not (self.append and os.path.exists(self.filename)) and self.keys is None
+        if self.keys is None:
+            self.keys = sorted(logs.keys())
+        with open(self.filename, "w" if new else "a") as fh:
+            if new:
+                fh.write(self.sep.join(["epoch"] + self.keys) + "\n")
+            fh.write(self.sep.join([str(epoch)] + [repr(float(logs[k])) for k in self.keys]) + "\n")
+
+
+class LearningRateScheduler(Callback):
+    def __init__(self, schedule):
+        self.schedule = schedule
+
+    def on_epoch_begin(self, epoch):
+        self.model.learning_rate = float(self.schedule(epoch, self.model.learning_rate))

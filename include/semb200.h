@@ -76,13 +76,15 @@ int         semb_device_ok(void);
 
 /* y[n,oy,ox,co] (+)= bias[co] + sum_{r,s,ci} x[n, oy*stride-pad_t+r, ox*stride-pad_l+s, ci] * w[r,s,ci,co]
  * w: fp32 HWIO (Keras Conv2D kernel layout).  bias may be NULL.
- * stats (may be NULL): fp32, sum at stats[n*stats_nstride + c], sum of squares at
- * stats[n*stats_nstride + stats_cstride + c]; nstride = 0 gives BatchNorm (per-channel)
- * moments, nstride = 2*cstride gives GroupNormalization(groups=-1) (per-sample) moments.
+ * stats (may be NULL): FP64 accumulators (strides in doubles), sum at stats[n*stats_nstride + c], sum of
+ * squares at stats[n*stats_nstride + stats_cstride + c]; nstride = 0 gives BatchNorm (per-channel)
+ * moments, nstride = 2*cstride gives GroupNormalization(groups=-1) (per-sample) moments.  Partials are
+ * reduced in a fixed order inside a CTA and combined across CTAs with fp64 atomics, so the forward pass is
+ * reproducible run to run (fp32 atomics were observed to flip ReLU/max-pool decisions in backward).
  * Replaces F.conv2d under keras.layers.Conv2D + the keras.ops.moments pass of the following
  * BatchNormalization / GroupNormalization (UNet_Segmentation.py:421-422, CycleGAN.py:327-329). */
 int semb_conv2d_fwd(const semb_conv_geom* g, const semb_tensor* x, const float* w, const float* bias,
-                    const semb_tensor* y, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                    const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                     int32_t accumulate, void* stream);
 
 /* dx[n,iy,ix,ci] (+)= bias[ci] + sum_{r,s,co : iy = oy*stride-pad_t+r} dy[n,oy,ox,co] * w[r,s,ci,co]
@@ -93,7 +95,7 @@ int semb_conv2d_fwd(const semb_conv_geom* g, const semb_tensor* x, const float* 
  * equivalent strided conv that maps the transposed-conv OUTPUT back to its INPUT.  bias/stats as above
  * (indexed by ci). */
 int semb_conv2d_dgrad(const semb_conv_geom* g, const semb_tensor* dy, const float* w, const float* bias,
-                      const semb_tensor* dx, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                      const semb_tensor* dx, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                       int32_t accumulate, void* stream);
 
 /* dw[r,s,ci,co] += sum_{n,oy,ox} x[n, oy*stride-pad_t+r, ox*stride-pad_l+s, ci] * dy[n,oy,ox,co]   (fp32 HWIO)
@@ -102,29 +104,16 @@ int semb_conv2d_dgrad(const semb_conv_geom* g, const semb_tensor* dy, const floa
 int semb_conv2d_wgrad(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy,
                       float* dw, float* dbias, void* stream);
 
-/* ---- tensor-core (tcgen05 / TMEM) convolutions, bf16 storage ------------------------------ */
-
-/* Packs fp32 HWIO weights into the bf16 UMMA shared-memory image read by semb_conv2d_fwd_tc.
- * flip=1 packs the spatially flipped, channel-transposed kernel so that the same implicit-GEMM
- * kernel computes the stride-1 data gradient.  Returns the packed size in bytes when dst==NULL. */
-int64_t semb_pack_weights_tc(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout,
-                             int32_t flip, void* dst, void* stream);
-
-/* Same contract as semb_conv2d_fwd for stride 1, R,S in {1,3}, bf16 storage, pitch % 8 == 0,
- * coff % 8 == 0; implicit GEMM on tcgen05.mma with the accumulator in TMEM. */
-int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
-                       const semb_tensor* y, float* stats, int32_t stats_nstride, int32_t stats_cstride,
-                       int32_t accumulate, void* stream);
-
 /* ---- normalisation + activation (fused elementwise) --------------------------------------- */
 
 /* From moments to the affine that BatchNormalization / GroupNormalization applies.
+ * stats: the FP64 moment accumulators written by the conv / affine kernels.
  * For i in [0, groups*C): mean = sum/count, var = sumsq/count - mean^2 (Keras ops.moments),
  * invstd = rsqrt(var+eps), scale = gamma[c]*invstd (gamma NULL -> 1), shift = beta[c]-mean*scale.
  * Writes scale, shift, mean, invstd (each groups x cstride, fp32).  If moving_mean != NULL
  * (BatchNorm training): moving = moving*momentum + batch*(1-momentum) with the biased variance.
  * UNet_Segmentation.py:422,470,473,494,502; CycleGAN.py:329,335,342,355,374. */
-int semb_norm_finalize(const float* stats, int32_t groups, int32_t C, int32_t cstride, int32_t stats_nstride,
+int semb_norm_finalize(const void* stats, int32_t groups, int32_t C, int32_t cstride, int32_t stats_nstride,
                        float count, float eps, const float* gamma, const float* beta,
                        float* scale, float* shift, float* mean, float* invstd,
                        float* moving_mean, float* moving_var, float momentum, void* stream);
@@ -151,15 +140,18 @@ typedef struct {
 int semb_affine_act_fwd(const semb_affine_desc* d,
                         const semb_tensor* a, const float* scale_a, const float* shift_a,
                         const semb_tensor* b, const float* scale_b, const float* shift_b,
-                        const semb_tensor* y, float* stats, int32_t stats_nstride, int32_t stats_cstride,
+                        const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                         void* stream);
 
-/* Backward of semb_affine_act_fwd, pass 1 of 2: with g = dy*act'(y), gb = g*actb'(B(b)) accumulates
- * sums[0]=sum g, sums[1]=sum g*a, sums[2]=sum gb, sums[3]=sum gb*b  (each at k*cstride + c, plus
- * n*nstride for per-sample mode).  y is the saved forward output. */
+/* Backward of semb_affine_act_fwd, pass 1 of 2: with g = dy*act'(y), gb = g*actb'(B(b)) and
+ * xhat = (x-mean)*invstd accumulates sums[0]=sum g, sums[1]=sum g*xhat_a, sums[2]=sum gb,
+ * sums[3]=sum gb*xhat_b (each at k*cstride + c, plus n*nstride for per-sample mode); only operands in
+ * SEMB_AFF_BATCH mode are reduced.  y is the saved forward output (needed when act != NONE). */
 int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
                                const semb_tensor* a, const semb_tensor* b,
+                               const float* mean_a, const float* invstd_a,
                                const float* scale_b, const float* shift_b,
+                               const float* mean_b, const float* invstd_b,
                                float* sums, int32_t sums_nstride, int32_t sums_cstride, void* stream);
 
 /* C-length finalize of the BN/IN backward: for operand `which` (0=a, 1=b) turns the sums into
@@ -179,6 +171,9 @@ int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy, 
                               const float* invstd_b, const float* c1_b, const float* c2_b,
                               const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b,
                               void* stream);
+
+/* out[c] += sum over pixels of x[.,c]   (bias gradient of Conv2DTranspose / biased Conv2D) */
+int semb_channel_sum(const semb_tensor* x, int32_t N, int32_t HW, float* out, int32_t dtype, void* stream);
 
 /* ---- pooling / padding ------------------------------------------------------------------- */
 
@@ -206,26 +201,28 @@ int semb_pad_crop(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t
 int semb_loss_wbce(const semb_tensor* p, const float* y_true, const semb_tensor* dp, int64_t count,
                    float weighting, float* out, int32_t dtype, void* stream);
 
-/* sum |a-b| (kind 0, MeanAbsoluteError) or sum (a-b)^2 (kind 1, MeanSquaredError) into out[0];
- * b==NULL compares against the constant `target` (LSGAN labels, CycleGAN.py:301-308).
- * da (+)= gscale * d/da, gscale already containing lambda/count. */
+/* sum |a-b| (kind 0, MeanAbsoluteError) or sum (a-b)^2 (kind 1, MeanSquaredError) into out[0] over the
+ * first c_logical channels; b==NULL compares against the constant `target` (LSGAN labels,
+ * CycleGAN.py:301-308).  da (+)= gscale * d/da, gscale already containing lambda/count. */
 int semb_loss_l1_l2(const semb_tensor* a, const semb_tensor* b, float target, int32_t kind, int64_t n_pixels,
-                    float gscale, const semb_tensor* da, int32_t accumulate, float* out, int32_t dtype,
-                    void* stream);
+                    int32_t c_logical, float gscale, const semb_tensor* da, int32_t accumulate, float* out,
+                    int32_t dtype, void* stream);
 
 /* ---- optimizer / utilities --------------------------------------------------------------- */
 
 /* keras.optimizers.Adam over one flat fp32 buffer (UNet_Segmentation.py:390-393, CycleGAN.py:168-171):
- * m += (g-m)(1-b1); v += (g*g-v)(1-b2); w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps).
- * gscale multiplies g first (1/world_size after the NCCL sum). step_ptr: device int64 step counter t
- * (incremented by the kernel, so the call is CUDA-graph replayable); lr_ptr: device float. */
+ * m += (g-m)(1-b1); v += (g*g-v)(1-b2); w -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps)  (epsilon OUTSIDE
+ * the bias correction, unlike torch.optim.Adam).  gscale multiplies g first (1/world_size after the NCCL
+ * sum).  state: 16 device bytes {int64 t; float alpha; float pad}, zero-initialised by the caller; t is
+ * incremented on the device so the call replays inside a CUDA graph.  lr_ptr: device float. */
 int semb_adam_step(float* w, const float* g, float* m, float* v, int64_t n, const float* lr_ptr,
-                   float beta1, float beta2, float eps, float gscale, int64_t* step_ptr, void* stream);
+                   float beta1, float beta2, float eps, float gscale, void* state, void* stream);
 
 int semb_fill_f32(float* p, int64_t n, float value, void* stream);
-/* dst(dtype, NHWC view) = src fp32 dense [N*HW, C] and back; the NHWC float32 boundary of the Keras model call. */
-int semb_cast_in(const float* src, const semb_tensor* dst, int64_t n_pixels, int32_t dtype, void* stream);
-int semb_cast_out(const semb_tensor* src, float* dst, int64_t n_pixels, int32_t dtype, void* stream);
+/* The NHWC float32 boundary of the Keras model call: dst view (dtype, 8-padded) <- src fp32 dense
+ * [n_pixels, src_C] (extra channels zero-filled), and back (first dst_C channels). */
+int semb_cast_in(const float* src, int32_t src_C, const semb_tensor* dst, int64_t n_pixels, int32_t dtype, void* stream);
+int semb_cast_out(const semb_tensor* src, float* dst, int32_t dst_C, int64_t n_pixels, int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,429 @@
+"""Op-level parity of the C-ABI kernels against the oracle layer restatements (torch CPU fp32).
+
+fp32 storage: rtol 1e-4 (normalised by max|ref|).  bf16 storage: inputs are rounded to bf16 first and the
+oracle runs on the rounded values, so the only differences are the bf16 rounding of the stored result
+(2^-8 relative) and fp32 summation order; tolerance 1e-2 on stored tensors, 1e-4 on fp32 outputs
+(moments, weight gradients).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers as OL
+from tests import util as U
+from sem_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+DT = ["f32", "bf16"]
+
+
+def _tol(dtype):
+    return 1e-4 if dtype == "f32" else 1e-2
+
+
+def _prep(x, dtype):
+    return U.bf16_round(x) if dtype == "bf16" else x
+
+
+# (N,H,W,Cin,Cout,k,stride,padding,pad_mode)
+CONV_CASES = [
+    (2, 16, 16, 1, 4, 3, 1, "same", "zero"),
+    (2, 24, 20, 8, 13, 3, 1, "same", "zero"),
+    (1, 16, 16, 25, 51, 1, 1, "same", "zero"),
+    (2, 16, 24, 51, 32, 3, 1, "same", "zero"),
+    (1, 8, 8, 212, 71, 3, 1, "same", "zero"),
+    (1, 12, 12, 105, 212, 1, 1, "same", "zero"),
+    (2, 16, 16, 16, 32, 3, 2, "same", "zero"),      # CycleGAN generator downsample (asymmetric 0/1 pad)
+    (1, 18, 18, 32, 32, 3, 1, "reflect1", "reflect"),  # residual block: reflect-pad 1 + valid
+    (1, 22, 22, 1, 16, 7, 1, "reflect3", "reflect"),   # generator stem
+    (2, 20, 20, 1, 24, 4, 2, "valid", "zero"),      # PatchGAN d0
+    (1, 15, 15, 24, 48, 4, 2, "valid", "zero"),     # odd input
+    (1, 12, 12, 48, 1, 4, 1, "valid", "zero"),      # PatchGAN output conv
+    (1, 17, 19, 5, 7, 3, 1, "same", "zero"),        # ragged sizes, partial tiles
+]
+
+
+def _geom(n, h, w, cin, cout, k, stride, padding, pad_mode, dtype):
+    if padding == "same":
+        if stride == 1:
+            pt = pl = (k - 1) // 2
+            oh, ow = h, w
+        else:
+            pt, _ = OL.same_pad_amounts(h, k, stride)
+            pl, _ = OL.same_pad_amounts(w, k, stride)
+            oh, ow = -(-h // stride), -(-w // stride)
+    elif padding == "valid":
+        pt = pl = 0
+        oh, ow = (h - k) // stride + 1, (w - k) // stride + 1
+    else:  # reflectP: reflect pad P each side then valid
+        p = int(padding[-1])
+        pt = pl = p
+        oh, ow = h + 2 * p - k + 1, w + 2 * p - k + 1
+    pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
+    return L.ConvGeom(n, h, w, oh, ow, U.pad8(cin), U.pad8(cout), k, k, stride, pt, pl, pm, U.ldtype(dtype)), (oh, ow)
+
+
+def _oracle_conv(x, w, b, stride, padding):
+    if padding.startswith("reflect"):
+        p = int(padding[-1])
+        return OL.conv2d(OL.reflection_pad(x, 2 * p, 2 * p), w, b, stride, "valid")
+    return OL.conv2d(x, w, b, stride, padding)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(case, dtype):
+    n, h, w_, cin, cout, k, stride, padding, pad_mode = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = _prep(torch.randn(n, h, w_, cin, generator=g), dtype)
+    wt = torch.randn(k, k, cin, cout, generator=g) * 0.2
+    bias = torch.randn(cout, generator=g)
+    geom, (oh, ow) = _geom(n, h, w_, cin, cout, k, stride, padding, pad_mode, dtype)
+
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    y_ref = _oracle_conv(xr, wr, br, stride, padding)
+    assert y_ref.shape[1:3] == (oh, ow)
+    dy = _prep(torch.randn(y_ref.shape, generator=g), dtype)
+    y_ref.backward(dy)
+
+    xd = U.to_dev(x, dtype, pitch=U.pad8(cin) + 8, coff=8)           # exercise pitch/coff
+    yd = torch.zeros((n, oh, ow, U.pad8(cout) + 16), dtype=U.tdtype(dtype), device="cuda")
+    wd, bd = U.pad_w(wt), U.pad_v(bias)
+    stats = torch.zeros(2 * U.pad8(cout), device="cuda", dtype=torch.float64)
+    xv, yv = U.view(xd, 8, U.pad8(cin)), U.view(yd, 8, U.pad8(cout))
+    L.check(lib.semb_conv2d_fwd(C.byref(geom), C.byref(xv), wd.data_ptr(), bd.data_ptr(), C.byref(yv), stats.data_ptr(), 0,
+                                U.pad8(cout), 0, U.stream()))
+    torch.cuda.synchronize()
+    y = yd[..., 8:8 + cout].float().cpu()
+    assert U.rel_err(y, y_ref) < _tol(dtype)
+    assert float(yd[..., :8].abs().max()) == 0 and float(yd[..., 8 + U.pad8(cout):].abs().max()) == 0
+    # moments come from the fp32 accumulators
+    s_ref = y_ref.detach().sum(dim=(0, 1, 2))
+    q_ref = (y_ref.detach() ** 2).sum(dim=(0, 1, 2))
+    assert U.rel_err(stats[:cout], s_ref) < 1e-4 and U.rel_err(stats[U.pad8(cout):U.pad8(cout) + cout], q_ref) < 1e-4
+
+    # wgrad (+ dbias)
+    dyd = U.to_dev(dy, dtype)
+    dw = torch.zeros_like(wd)
+    db = torch.zeros_like(bd)
+    dyv = U.view(dyd)
+    L.check(lib.semb_conv2d_wgrad(C.byref(geom), C.byref(xv), C.byref(dyv), dw.data_ptr(), db.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(dw[:, :, :cin, :cout], wr.grad) < 1e-4
+    assert U.rel_err(db[:cout], br.grad) < 1e-4
+    assert float(dw[:, :, cin:, :].abs().max() if U.pad8(cin) > cin else 0) == 0
+
+    # dgrad (zero padding only; reflect is folded separately)
+    if pad_mode == "zero":
+        dxd = torch.zeros((n, h, w_, U.pad8(cin)), dtype=U.tdtype(dtype), device="cuda")
+        dxv = U.view(dxd)
+        L.check(lib.semb_conv2d_dgrad(C.byref(geom), C.byref(dyv), wd.data_ptr(), None, C.byref(dxv), None, 0, 0, 0, U.stream()))
+        torch.cuda.synchronize()
+        assert U.rel_err(dxd[..., :cin], xr.grad) < _tol(dtype)
+        # accumulate flag adds on top
+        L.check(lib.semb_conv2d_dgrad(C.byref(geom), C.byref(dyv), wd.data_ptr(), None, C.byref(dxv), None, 0, 0, 1, U.stream()))
+        torch.cuda.synchronize()
+        assert U.rel_err(dxd[..., :cin], 2 * xr.grad) < 2 * _tol(dtype)
+    else:
+        # gradient on the padded domain, then reflect-fold
+        p = geom.pad_t
+        g2 = L.ConvGeom(n, h + 2 * p, w_ + 2 * p, oh, ow, geom.Cin, geom.Cout, k, k, stride, 0, 0, L.PAD_ZERO, geom.dtype)
+        dxp = torch.zeros((n, h + 2 * p, w_ + 2 * p, U.pad8(cin)), dtype=U.tdtype(dtype), device="cuda")
+        dxd = torch.zeros((n, h, w_, U.pad8(cin)), dtype=U.tdtype(dtype), device="cuda")
+        dxpv, dxv = U.view(dxp), U.view(dxd)
+        L.check(lib.semb_conv2d_dgrad(C.byref(g2), C.byref(dyv), wd.data_ptr(), None, C.byref(dxpv), None, 0, 0, 0, U.stream()))
+        L.check(lib.semb_pad_crop(C.byref(dxpv), C.byref(dxv), n, h + 2 * p, w_ + 2 * p, h, w_, p, p, 3, geom.dtype, 0, U.stream()))
+        torch.cuda.synchronize()
+        assert U.rel_err(dxd[..., :cin], xr.grad) < 2 * _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("case", [(2, 8, 8, 51, 16, 2), (1, 6, 10, 426, 128, 2), (2, 8, 8, 32, 16, 3)])
+def test_conv_transpose(case, dtype):
+    """Conv2DTranspose 2x2 s2 (UNet up path, with bias) and 3x3 s2 (CycleGAN upsample) via the dgrad kernel."""
+    n, h, w_, cin, cout, k = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(7)
+    x = _prep(torch.randn(n, h, w_, cin, generator=g), dtype)
+    wt = torch.randn(k, k, cout, cin, generator=g) * 0.1        # Keras layout (kh,kw,Cout,Cin)
+    bias = torch.randn(cout, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    y_ref = OL.conv2d_transpose(xr, wr, br, 2)
+    assert y_ref.shape == (n, 2 * h, 2 * w_, cout)
+    dy = _prep(torch.randn(y_ref.shape, generator=g), dtype)
+    y_ref.backward(dy)
+    p, _ = OL.conv_transpose_pads(k, 2)
+    geom = L.ConvGeom(n, 2 * h, 2 * w_, h, w_, U.pad8(cout), U.pad8(cin), k, k, 2, p, p, L.PAD_ZERO, U.ldtype(dtype))
+    xd, yd = U.to_dev(x, dtype), torch.zeros((n, 2 * h, 2 * w_, U.pad8(cout)), dtype=U.tdtype(dtype), device="cuda")
+    wd, bd = U.pad_w(wt), U.pad_v(bias)
+    xv, yv = U.view(xd), U.view(yd)
+    L.check(lib.semb_conv2d_dgrad(C.byref(geom), C.byref(xv), wd.data_ptr(), bd.data_ptr(), C.byref(yv), None, 0, 0, 0, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(yd[..., :cout], y_ref) < _tol(dtype)
+    # backward: d_in = conv(d_out), dW = wgrad(d_out, in), dbias = channel_sum(d_out)
+    dyd = U.to_dev(dy, dtype)
+    dyv = U.view(dyd)
+    dxd = torch.zeros_like(xd)
+    dxv = U.view(dxd)
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    L.check(lib.semb_conv2d_fwd(C.byref(geom), C.byref(dyv), wd.data_ptr(), None, C.byref(dxv), None, 0, 0, 0, U.stream()))
+    L.check(lib.semb_conv2d_wgrad(C.byref(geom), C.byref(dyv), C.byref(xv), dw.data_ptr(), None, U.stream()))
+    L.check(lib.semb_channel_sum(C.byref(dyv), n, 4 * h * w_, db.data_ptr(), U.ldtype(dtype), U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(dxd[..., :cin], xr.grad) < _tol(dtype)
+    assert U.rel_err(dw[:, :, :cout, :cin], wr.grad) < 1e-4
+    assert U.rel_err(db[:cout], br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_norm_affine_fwd_bwd(dtype, per_sample):
+    """y = relu(BN_a(a) + relu(BN_b(b))) with batch statistics (res_path unit) and the InstanceNorm variant,
+    forward + both gradient passes against torch autograd on the oracle formulas."""
+    lib = L.load()
+    n, h, w_, c = 3, 10, 12, 24
+    cp = U.pad8(c)
+    g = torch.Generator().manual_seed(3)
+    a = _prep(torch.randn(n, h, w_, c, generator=g) * 2 + 0.5, dtype)
+    b = _prep(torch.randn(n, h, w_, c, generator=g) - 0.3, dtype)
+    gamma_b = torch.rand(c, generator=g) + 0.5
+    beta_a, beta_b = torch.randn(c, generator=g) * 0.1, torch.randn(c, generator=g) * 0.1
+    ar, br_ = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    gb, ba, bb = gamma_b.clone().requires_grad_(True), beta_a.clone().requires_grad_(True), beta_b.clone().requires_grad_(True)
+    eps = 1e-5 if per_sample else 1e-3
+    if per_sample:
+        ya = OL.instance_norm(ar, torch.ones(c), ba, eps)
+        yb = OL.instance_norm(br_, gb, bb, eps)
+    else:
+        ya, _, _ = OL.batch_norm(ar, None, ba, torch.zeros(c), torch.ones(c), True)
+        yb, _, _ = OL.batch_norm(br_, gb, bb, torch.zeros(c), torch.ones(c), True)
+    y_ref = torch.relu(ya + torch.relu(yb))
+    dy = _prep(torch.randn(y_ref.shape, generator=g), dtype)
+    y_ref.backward(dy)
+
+    groups = n if per_sample else 1
+    count = float(h * w_ if per_sample else n * h * w_)
+    ad, bd, yd = U.to_dev(a, dtype), U.to_dev(b, dtype), torch.zeros((n, h, w_, cp), dtype=U.tdtype(dtype), device="cuda")
+    av, bv, yv = U.view(ad), U.view(bd), U.view(yd)
+
+    def moments(t):
+        tt = t.double()
+        dims = (1, 2) if per_sample else (0, 1, 2)
+        st = torch.zeros(groups, 2, cp, dtype=torch.float64)
+        st[:, 0, :c] = tt.sum(dim=dims).reshape(groups, c)
+        st[:, 1, :c] = (tt * tt).sum(dim=dims).reshape(groups, c)
+        return st.cuda().contiguous()
+
+    nstride = 2 * cp if per_sample else 0
+    arrs = {}
+    keep = []       # device temporaries must outlive the asynchronous launches that read them
+    for tag, t, gam, bet in (("a", a, None, beta_a), ("b", b, gamma_b, beta_b)):
+        st = moments(t)
+        o = {k: torch.zeros(groups * cp, device="cuda") for k in ("scale", "shift", "mean", "invstd", "c1", "c2")}
+        gam_d = U.pad_v(gam) if gam is not None else None
+        bet_d = U.pad_v(bet)
+        keep += [st, gam_d, bet_d]
+        L.check(lib.semb_norm_finalize(st.data_ptr(), groups, cp, cp, nstride, count, eps,
+                                       gam_d.data_ptr() if gam_d is not None else None, bet_d.data_ptr(),
+                                       o["scale"].data_ptr(), o["shift"].data_ptr(), o["mean"].data_ptr(), o["invstd"].data_ptr(),
+                                       None, None, 0.99, U.stream()))
+        arrs[tag] = o
+    d = L.AffineDesc(n, h * w_, cp, U.ldtype(dtype), L.ACT_RELU, L.ACT_RELU, L.AFF_BATCH, L.AFF_BATCH, cp if per_sample else 0)
+    ystats = torch.zeros(groups * 2 * cp, device="cuda", dtype=torch.float64)
+    L.check(lib.semb_affine_act_fwd(C.byref(d), C.byref(av), arrs["a"]["scale"].data_ptr(), arrs["a"]["shift"].data_ptr(),
+                                    C.byref(bv), arrs["b"]["scale"].data_ptr(), arrs["b"]["shift"].data_ptr(), C.byref(yv),
+                                    ystats.data_ptr(), nstride, cp, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(yd[..., :c], y_ref) < _tol(dtype)
+    ys = ystats.view(groups, 2, cp)
+    dims = (1, 2) if per_sample else (0, 1, 2)
+    assert U.rel_err(ys[:, 0, :c], y_ref.detach().sum(dim=dims).reshape(groups, c)) < (1e-4 if dtype == "f32" else 1e-2)
+
+    # backward
+    dyd = U.to_dev(dy, dtype)
+    dyv = U.view(dyd)
+    # the saved forward output must be the one the kernel produced
+    sums = torch.zeros(groups * 4 * cp, device="cuda")
+    L.check(lib.semb_affine_act_bwd_reduce(C.byref(d), C.byref(dyv), C.byref(yv), C.byref(av), C.byref(bv),
+                                           arrs["a"]["mean"].data_ptr(), arrs["a"]["invstd"].data_ptr(),
+                                           arrs["b"]["scale"].data_ptr(), arrs["b"]["shift"].data_ptr(),
+                                           arrs["b"]["mean"].data_ptr(), arrs["b"]["invstd"].data_ptr(),
+                                           sums.data_ptr(), 4 * cp if per_sample else 0, cp, U.stream()))
+    dgam_b, dbeta_a, dbeta_b = torch.zeros(cp, device="cuda"), torch.zeros(cp, device="cuda"), torch.zeros(cp, device="cuda")
+    L.check(lib.semb_norm_bwd_finalize(sums.data_ptr(), 0, groups, cp, cp, 4 * cp if per_sample else 0, count, None, None,
+                                       arrs["a"]["c1"].data_ptr(), arrs["a"]["c2"].data_ptr(), None, dbeta_a.data_ptr(), U.stream()))
+    L.check(lib.semb_norm_bwd_finalize(sums.data_ptr(), 1, groups, cp, cp, 4 * cp if per_sample else 0, count, None, None,
+                                       arrs["b"]["c1"].data_ptr(), arrs["b"]["c2"].data_ptr(), dgam_b.data_ptr(), dbeta_b.data_ptr(),
+                                       U.stream()))
+    dad, dbd = torch.zeros_like(ad), torch.zeros_like(bd)
+    dav, dbv = U.view(dad), U.view(dbd)
+    A, B = arrs["a"], arrs["b"]
+    L.check(lib.semb_affine_act_bwd_apply(C.byref(d), C.byref(dyv), C.byref(yv), C.byref(av), C.byref(bv),
+                                          A["scale"].data_ptr(), A["mean"].data_ptr(), A["invstd"].data_ptr(), A["c1"].data_ptr(), A["c2"].data_ptr(),
+                                          B["scale"].data_ptr(), B["shift"].data_ptr(), B["mean"].data_ptr(), B["invstd"].data_ptr(),
+                                          B["c1"].data_ptr(), B["c2"].data_ptr(), C.byref(dav), 0, C.byref(dbv), 0, U.stream()))
+    torch.cuda.synchronize()
+    tol = 1e-3 if dtype == "f32" else 2e-2
+    assert U.rel_err(dad[..., :c], ar.grad) < tol
+    assert U.rel_err(dbd[..., :c], br_.grad) < tol
+    assert U.rel_err(dgam_b[:c], gb.grad) < tol
+    assert U.rel_err(dbeta_a[:c], ba.grad) < tol and U.rel_err(dbeta_b[:c], bb.grad) < tol
+
+
+def test_norm_finalize_moving_stats():
+    lib = L.load()
+    c = 16
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4, 6, 6, c, generator=g) * 3 + 1
+    mm, mv = torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5
+    y_ref, m_ref, v_ref = OL.batch_norm(x, None, torch.zeros(c), mm, mv, True)
+    st = torch.stack([x.double().sum(dim=(0, 1, 2)), (x.double() ** 2).sum(dim=(0, 1, 2))]).cuda().contiguous()
+    mmd, mvd = mm.cuda(), mv.cuda()
+    outs = [torch.zeros(c, device="cuda") for _ in range(4)]
+    beta0 = torch.zeros(c, device="cuda")
+    L.check(lib.semb_norm_finalize(st.data_ptr(), 1, c, c, 0, float(4 * 36), 1e-3, None, beta0.data_ptr(),
+                                   outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(), outs[3].data_ptr(),
+                                   mmd.data_ptr(), mvd.data_ptr(), 0.99, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(mmd, m_ref) < 1e-5 and U.rel_err(mvd, v_ref) < 1e-5
+    assert U.rel_err(x.cuda() * outs[0] + outs[1], y_ref) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_maxpool(dtype):
+    lib = L.load()
+    g = torch.Generator().manual_seed(1)
+    x = _prep(torch.randn(2, 8, 12, 13, generator=g), dtype)
+    x[0, 0, 0, 0] = x[0, 0, 1, 0] = x[0, 1, 0, 0] = x[0, 1, 1, 0] = 1.5      # a 4-way tie: first position wins
+    xr = x.clone().requires_grad_(True)
+    y_ref = OL.max_pool_2x2(xr)
+    dy = _prep(torch.randn(y_ref.shape, generator=g), dtype)
+    y_ref.backward(dy)
+    xd, yd = U.to_dev(x, dtype), torch.zeros((2, 4, 6, 16), dtype=U.tdtype(dtype), device="cuda")
+    xv, yv = U.view(xd), U.view(yd)
+    L.check(lib.semb_maxpool2x2_fwd(C.byref(xv), C.byref(yv), 2, 8, 12, U.ldtype(dtype), U.stream()))
+    dyd, dxd = U.to_dev(dy, dtype), torch.zeros_like(xd)
+    dyv, dxv = U.view(dyd), U.view(dxd)
+    L.check(lib.semb_maxpool2x2_bwd(C.byref(xv), C.byref(dyv), C.byref(dxv), 2, 8, 12, U.ldtype(dtype), 0, U.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(yd[..., :13].float().cpu(), y_ref.detach())
+    assert torch.equal(dxd[..., :13].float().cpu(), xr.grad)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_pad_crop_modes(dtype):
+    lib = L.load()
+    g = torch.Generator().manual_seed(2)
+    n, h, w_, c = 2, 9, 11, 8
+    x = _prep(torch.randn(n, h, w_, c, generator=g), dtype)
+    xr = x.clone().requires_grad_(True)
+    y_ref = OL.reflection_pad(xr, 5, 7)      # totals: w 5 -> (2,3), h 7 -> (3,4)
+    dy = _prep(torch.randn(y_ref.shape, generator=g), dtype)
+    y_ref.backward(dy)
+    oh, ow = h + 7, w_ + 5
+    xd, yd = U.to_dev(x, dtype), torch.zeros((n, oh, ow, c), dtype=U.tdtype(dtype), device="cuda")
+    xv, yv = U.view(xd), U.view(yd)
+    L.check(lib.semb_pad_crop(C.byref(xv), C.byref(yv), n, h, w_, oh, ow, 3, 2, 0, U.ldtype(dtype), 0, U.stream()))
+    dyd, dxd = U.to_dev(dy, dtype), torch.zeros_like(xd)
+    dyv, dxv = U.view(dyd), U.view(dxd)
+    L.check(lib.semb_pad_crop(C.byref(dyv), C.byref(dxv), n, oh, ow, h, w_, 3, 2, 3, U.ldtype(dtype), 0, U.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(yd.float().cpu(), y_ref.detach())
+    assert U.rel_err(dxd, xr.grad) < _tol(dtype)
+    # crop and its gradient (zero pad)
+    cd = torch.zeros((n, h, w_, c), dtype=U.tdtype(dtype), device="cuda")
+    cv = U.view(cd)
+    L.check(lib.semb_pad_crop(C.byref(yv), C.byref(cv), n, oh, ow, h, w_, 3, 2, 1, U.ldtype(dtype), 0, U.stream()))
+    zd = torch.ones((n, oh, ow, c), dtype=U.tdtype(dtype), device="cuda")
+    zv = U.view(zd)
+    L.check(lib.semb_pad_crop(C.byref(xv), C.byref(zv), n, h, w_, oh, ow, 3, 2, 2, U.ldtype(dtype), 0, U.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(cd.float().cpu(), x)
+    ref = torch.zeros(n, oh, ow, c)
+    ref[:, 3:3 + h, 2:2 + w_] = x
+    assert torch.equal(zd.float().cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_loss_wbce(dtype):
+    lib = L.load()
+    g = torch.Generator().manual_seed(5)
+    n, h, w_ = 2, 16, 16
+    p = torch.rand(n, h, w_, 1, generator=g)
+    p[0, 0, 0, 0], p[0, 0, 1, 0] = 0.0, 1.0          # outside the clip range -> zero gradient
+    p = _prep(p, dtype)
+    y = (torch.rand(n, h, w_, 1, generator=g) < 0.3).float()
+    pr = p.clone().requires_grad_(True)
+    loss = OL.weighted_bce(y, pr, 4.5)
+    loss.backward()
+    pd = U.to_dev(p, dtype)
+    dpd = torch.zeros_like(pd)
+    out = torch.zeros(4, device="cuda")
+    pv, dpv = U.view(pd), U.view(dpd)
+    yd = y.cuda().contiguous()
+    L.check(lib.semb_loss_wbce(C.byref(pv), yd.data_ptr(), C.byref(dpv), n * h * w_, 4.5, out.data_ptr(),
+                               U.ldtype(dtype), U.stream()))
+    torch.cuda.synchronize()
+    cnt = n * h * w_
+    assert abs(float(out[0]) / cnt - float(loss)) < 1e-5 * max(1.0, abs(float(loss)))
+    assert abs(float(out[1]) / cnt - float((y - p).abs().mean())) < 1e-5
+    assert abs(float(out[2]) / cnt - float(((p > 0.5).float() == y).float().mean())) < 1e-6
+    assert U.rel_err(dpd[..., :1], pr.grad) < (1e-5 if dtype == "f32" else 1e-2)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_loss_l1_l2(kind):
+    lib = L.load()
+    g = torch.Generator().manual_seed(6)
+    a, b = torch.randn(2, 8, 8, 1, generator=g), torch.randn(2, 8, 8, 1, generator=g)
+    ar = a.clone().requires_grad_(True)
+    ref = (OL.mae(ar, b) if kind == 0 else OL.mse(ar, b)) * 10.0
+    ref.backward()
+    ad, bd = U.to_dev(a, "f32"), U.to_dev(b, "f32")
+    dad = torch.zeros_like(ad)
+    out = torch.zeros(1, device="cuda")
+    av, bv, dav = U.view(ad), U.view(bd), U.view(dad)
+    L.check(lib.semb_loss_l1_l2(C.byref(av), C.byref(bv), 0.0, kind, 128, 1, 10.0 / 128, C.byref(dav), 0, out.data_ptr(), L.F32, U.stream()))
+    torch.cuda.synchronize()
+    assert abs(float(out[0]) * 10.0 / 128 - float(ref)) < 1e-5 * abs(float(ref))
+    assert U.rel_err(dad[..., :1], ar.grad) < 1e-5
+    # constant target (LSGAN label)
+    out.zero_()
+    L.check(lib.semb_loss_l1_l2(C.byref(av), None, 1.0, 1, 128, 1, 1.0 / 128, None, 0, out.data_ptr(), L.F32, U.stream()))
+    torch.cuda.synchronize()
+    assert abs(float(out[0]) / 128 - float(OL.mse(a, torch.ones_like(a)))) < 1e-5
+
+
+def test_adam_matches_keras_formula():
+    lib = L.load()
+    g = torch.Generator().manual_seed(8)
+    n = 1003
+    w0, grads = torch.randn(n, generator=g), [torch.randn(n, generator=g) for _ in range(3)]
+    wr = w0.clone()
+    opt = OL.KerasAdam([wr], lr=2e-4, beta_1=0.5)
+    wd, m, v = w0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    state = torch.zeros(4, dtype=torch.int32, device="cuda")
+    lr = torch.full((1,), 2e-4, device="cuda")
+    for gr in grads:
+        opt.apply([gr], [wr])
+        gd = (gr * 4.0).cuda()       # gscale = 1/4 emulates the 1/world_size after an all-reduce sum
+        L.check(lib.semb_adam_step(wd.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, lr.data_ptr(), 0.5, 0.999, 1e-7,
+                                   0.25, state.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    assert int(state.view(torch.int64)[0]) == 3
+    assert U.rel_err(wd, wr) < 1e-6
+
+
+def test_error_codes():
+    lib = L.load()
+    t = torch.zeros((1, 4, 4, 12), device="cuda")       # 12 channels: not 8-padded
+    v = L.Tensor(t.data_ptr(), 12, 12, 0)
+    with pytest.raises(ValueError):
+        L.check(lib.semb_maxpool2x2_fwd(C.byref(v), C.byref(v), 1, 4, 4, L.F32, U.stream()))
+    assert "maxpool" in L.last_error()
