@@ -1,0 +1,339 @@
+// Implicit-GEMM convolutions on the 5th-generation tensor cores (tcgen05.mma, accumulator in TMEM).
+//
+// im2col-free: a CTA stages the NHWC halo of its 16x8 output-pixel tile ONCE into shared memory in
+// "channel-group planes" [Cin/8][halo_h][halo_w][8 x bf16], which is exactly the no-swizzle K-major UMMA
+// canonical layout (8 consecutive pixels of one row = one 128-byte core matrix, SBO = halo row pitch,
+// LBO = plane pitch).  The 3x3 taps are then nine shared-memory DESCRIPTORS that point at shifted starts
+// inside the same halo tile -- no im2col matrix, no re-load per tap.  Weights are pre-packed on the device
+// into the matching [tap][Cin/8][Cout][8] image.  One elected thread issues the MMAs; all four warps drain
+// the 128-lane accumulator with tcgen05.ld in the epilogue (bias, fp32 BatchNorm/InstanceNorm moments,
+// bf16 store at a channel offset of the destination buffer = skip-concat for free).
+//
+// Replaces F.conv2d / its data gradient under keras.layers.Conv2D for the stride-1 3x3 and 1x1 layers
+// (UNet_Segmentation.py:421,465-468,490-499; CycleGAN.py:327,333).
+#include "common.cuh"
+
+namespace semb {
+
+constexpr int TILE_H = 16, TILE_W = 8;          // 128 output pixels = UMMA M
+constexpr int TC_THREADS = 128;
+
+struct TcPlan { int KC, NC, nchunks, kchunks, tmem_cols; };
+
+// Shared-memory budget: A planes + B taps must leave room for 2 CTAs per SM.
+static inline TcPlan tc_plan(int Cin, int Cout, int taps) {
+    TcPlan p;
+    const int c16 = (Cout + 15) / 16 * 16;
+    p.nchunks = (c16 + 255) / 256;
+    p.NC = ((c16 + p.nchunks - 1) / p.nchunks + 15) / 16 * 16;
+    const int cin16 = (Cin + 15) / 16 * 16;
+    int kc = 64;
+    while (kc > 16 && (size_t)taps * kc * p.NC * 2 + (size_t)kc * 362 > 96 * 1024) kc >>= 1;
+    if (kc > cin16) kc = cin16 <= 16 ? 16 : (cin16 <= 32 ? 32 : 64);
+    p.KC = kc;
+    p.kchunks = (Cin + kc - 1) / kc;
+    p.tmem_cols = p.NC <= 32 ? 32 : (p.NC <= 64 ? 64 : (p.NC <= 128 ? 128 : 256));
+    return p;
+}
+
+// ---- weight packing ----------------------------------------------------------------------------------
+// dst[nchunk][kchunk][tap][KC/8][NC][8] (bf16)  <-  w[r][s][ci][co] (fp32 HWIO), zero padded.
+// flip: the packed operator is the stride-1 data gradient: k runs over co, n over ci, taps mirrored.
+__global__ void pack_weights_kernel(const float* __restrict__ w, int R, int S, int Cin, int Cout, int flip, TcPlan p,
+                                    bf16* __restrict__ dst, long long total) {
+    const int taps = R * S;
+    const int K = flip ? Cout : Cin;      // reduction channels of the packed operator
+    const int N = flip ? Cin : Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int ke = (int)(t % 8); t /= 8;
+        const int nl = (int)(t % p.NC); t /= p.NC;
+        const int k8 = (int)(t % (p.KC / 8)); t /= (p.KC / 8);
+        const int tap = (int)(t % taps); t /= taps;
+        const int kch = (int)(t % p.kchunks); t /= p.kchunks;
+        const int nch = (int)t;
+        const int k = kch * p.KC + k8 * 8 + ke, n = nch * p.NC + nl;
+        float v = 0.f;
+        if (k < K && n < N) {
+            if (!flip) v = w[((size_t)tap * Cin + k) * Cout + n];
+            else v = w[((size_t)(taps - 1 - tap) * Cin + n) * Cout + k];
+        }
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    // bounded spin: a descriptor bug must trap, not hang the GPU box
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+    int N, H, W, OH, OW, Cin, Cout, R, S, pad_t, pad_l, pad_mode;
+    const bf16* x; int x_pitch, x_coff;
+    bf16* y; int y_pitch, y_coff;
+    const bf16* wp; const float* bias;
+    double* stats; int stats_nstride, stats_cstride;
+    int accumulate;
+    int tiles_x, tiles_y;
+    TcPlan p;
+    int plane_bytes, halo_h, halo_w;
+};
+
+template <int COLS>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int taps = a.R * a.S;
+    const int KC = a.p.KC, NC = a.p.NC;
+    uint8_t* As = smem;                                              // [KC/8][plane]
+    uint8_t* Bs = smem + (KC / 8) * a.plane_bytes;                   // [tap][KC/8][NC][16 B]
+    float* part = reinterpret_cast<float*>(Bs + (size_t)taps * KC * NC * 2);   // [2][4][NC] epilogue partials
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int n = tile / (a.tiles_x * a.tiles_y);
+    const int trem = tile % (a.tiles_x * a.tiles_y);
+    const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
+    const int nchunk = blockIdx.y;
+    const int halo_pix = a.halo_h * a.halo_w;
+
+    if (warp == 0) tmem_alloc<COLS>(smem_u32(&tmem_slot));
+    if (tid == 0) mbar_init(smem_u32(&mbar), 1);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = instr_desc(128, NC, 0, 0);
+    uint32_t phase = 0;
+
+    for (int kc = 0; kc < a.p.kchunks; ++kc) {
+        const int cvalid = min(KC, a.Cin - kc * KC);                // multiple of 8
+        const int ksteps = (cvalid + 15) / 16;
+        const int planes = 2 * ksteps;
+        // ---- A: halo tile of this channel chunk -> channel-group planes
+        for (int idx = tid; idx < planes * halo_pix; idx += TC_THREADS) {
+            const int k8 = idx % planes, pix = idx / planes;
+            const int hy = pix / a.halo_w, hx = pix % a.halo_w;
+            int iy = y0 - a.pad_t + hy, ix = x0 - a.pad_l + hx;
+            if (a.pad_mode == SEMB_PAD_REFLECT) {
+                // positions that only feed out-of-range output pixels may fall outside the reflectable band
+                if (iy > -a.H && iy < 2 * a.H - 1) iy = reflect_index(iy, a.H);
+                if (ix > -a.W && ix < 2 * a.W - 1) ix = reflect_index(ix, a.W);
+            }
+            const int ch = kc * KC + k8 * 8;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W && ch < a.Cin)
+                v = *reinterpret_cast<const uint4*>(a.x + ((size_t)(n * a.H + iy) * a.W + ix) * a.x_pitch + a.x_coff + ch);
+            *reinterpret_cast<uint4*>(As + (size_t)k8 * a.plane_bytes + pix * 16) = v;
+        }
+        // ---- B: packed weights of (nchunk, kc): one contiguous block
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(a.wp + ((size_t)nchunk * a.p.kchunks + kc) * taps * KC * NC);
+            uint4* dstp = reinterpret_cast<uint4*>(Bs);
+            const int n16 = taps * KC * NC / 8;
+            for (int idx = tid; idx < n16; idx += TC_THREADS) dstp[idx] = src[idx];
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+            for (int tap = 0; tap < taps; ++tap) {
+                const int r = tap / a.S, s = tap % a.S;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t ad = smem_desc(a_base + (2 * ks) * a.plane_bytes + (r * a.halo_w + s) * 16, a.plane_bytes, a.halo_w * 16);
+                    const uint64_t bd = smem_desc(b_base + (tap * (KC / 8) + 2 * ks) * NC * 16, NC * 16, 128);
+                    umma_bf16(tmem, ad, bd, idesc, (kc | tap | ks) != 0);
+                }
+            }
+            umma_commit(smem_u32(&mbar));
+        }
+        mbar_wait(smem_u32(&mbar), phase);
+        phase ^= 1;
+    }
+    tc_fence_after();
+
+    // ---- epilogue: TMEM lane = output pixel, columns = output channels
+    const int m = warp * 32 + lane;
+    const int oy = y0 + m / TILE_W, ox = x0 + m % TILE_W;
+    const bool pvalid = oy < a.OH && ox < a.OW;
+    bf16* yp = a.y + ((size_t)(n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
+    const int c_begin = nchunk * NC;
+    for (int g = 0; g < NC / 8; ++g) {
+        const int c = c_begin + g * 8;
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + g * 8, v);     // warp-collective: before any divergence
+        const bool cvalid = c < a.Cout;
+        if (a.bias && cvalid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
+        }
+        if (a.stats) {
+            float s1[8], s2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s1[i] = pvalid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+                    s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+                }
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { part[warp * NC + g * 8 + i] = s1[i]; part[(4 + warp) * NC + g * 8 + i] = s2[i]; }
+            }
+        }
+        if (pvalid && cvalid) {
+            if (a.accumulate) {
+                float o[8];
+                Vec8<bf16>::load(yp + c, o);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += o[i];
+            }
+            Vec8<bf16>::store(yp + c, v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (a.stats) {
+        for (int i = tid; i < NC; i += TC_THREADS) {
+            const int c = c_begin + i;
+            if (c < a.Cout) {
+                const float t1 = ((part[i] + part[NC + i]) + part[2 * NC + i]) + part[3 * NC + i];
+                const float t2 = ((part[4 * NC + i] + part[5 * NC + i]) + part[6 * NC + i]) + part[7 * NC + i];
+                double* st = a.stats + (size_t)n * a.stats_nstride + c;
+                atomicAdd(st, (double)t1);
+                atomicAdd(st + a.stats_cstride, (double)t2);
+            }
+        }
+    }
+    if (warp == 0) tmem_dealloc<COLS>(tmem);
+}
+
+static size_t tc_smem_bytes(const TcPlan& p, int taps, int plane_bytes) {
+    return (size_t)(p.KC / 8) * plane_bytes + (size_t)taps * p.KC * p.NC * 2 + (size_t)8 * p.NC * sizeof(float);
+}
+
+}  // namespace semb
+
+using namespace semb;
+
+extern "C" int64_t semb_pack_weights_tc(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout, int32_t flip,
+                                        void* dst, void* stream) {
+    if (!((R == 1 && S == 1) || (R == 3 && S == 3)) || Cin <= 0 || Cout <= 0 || Cin % 8 || Cout % 8) {
+        set_error("pack_weights_tc: need 1x1 or 3x3 and 8-padded channels (got %dx%d, %d->%d)", R, S, Cin, Cout);
+        return SEMB_ESHAPE;
+    }
+    const int K = flip ? Cout : Cin, N = flip ? Cin : Cout;
+    const TcPlan p = tc_plan(K, N, R * S);
+    const long long total = (long long)p.nchunks * p.kchunks * R * S * p.KC * p.NC;
+    if (!dst) return total * 2;
+    if (!w) { set_error("pack_weights_tc: null weights"); return SEMB_ESHAPE; }
+    long long blocks = cdivl(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    pack_weights_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(w, R, S, Cin, Cout, flip, p, reinterpret_cast<bf16*>(dst), total);
+    const int rc = check_launch("pack_weights_tc");
+    return rc ? rc : total * 2;
+}
+
+extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
+                                  const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
+                                  int32_t accumulate, void* stream) {
+    SEMB_REQUIRE(g && x && y && w_packed, SEMB_ESHAPE, "conv_tc: null argument");
+    SEMB_REQUIRE(g->dtype == SEMB_BF16, SEMB_ESHAPE, "conv_tc: bf16 storage only");
+    SEMB_REQUIRE(g->stride == 1 && ((g->R == 1 && g->S == 1) || (g->R == 3 && g->S == 3)), SEMB_ESHAPE,
+                 "conv_tc: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
+    SEMB_REQUIRE(view_ok(x) && view_ok(y) && x->C == g->Cin && y->C == g->Cout, SEMB_EALIGN, "conv_tc: bad tensor views");
+    SEMB_REQUIRE(g->N > 0 && g->OH > 0 && g->OW > 0 && g->pad_t >= 0 && g->pad_l >= 0 && g->pad_t < g->R + TILE_H && g->pad_l < g->S + TILE_W,
+                 SEMB_ESHAPE, "conv_tc: bad geometry");
+    TcArgs a{};
+    a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
+    a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
+    a.x = reinterpret_cast<const bf16*>(x->ptr); a.x_pitch = x->pitch; a.x_coff = x->coff;
+    a.y = reinterpret_cast<bf16*>(y->ptr); a.y_pitch = y->pitch; a.y_coff = y->coff;
+    a.wp = reinterpret_cast<const bf16*>(w_packed); a.bias = bias;
+    a.stats = reinterpret_cast<double*>(stats); a.stats_nstride = stats_nstride; a.stats_cstride = stats_cstride;
+    a.accumulate = accumulate;
+    a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
+    a.p = tc_plan(g->Cin, g->Cout, g->R * g->S);
+    a.halo_h = TILE_H + g->R - 1; a.halo_w = TILE_W + g->S - 1;
+    a.plane_bytes = a.halo_h * a.halo_w * 16 + 16;          // +16: consecutive planes start in different banks
+    const size_t smem = tc_smem_bytes(a.p, g->R * g->S, a.plane_bytes);
+    SEMB_REQUIRE(smem <= 200 * 1024, SEMB_EWORKSPACE, "conv_tc: %zu bytes of shared memory needed", smem);
+    dim3 grid(g->N * a.tiles_x * a.tiles_y, a.p.nchunks);
+    cudaError_t e = cudaSuccess;
+#define SEMB_TC_LAUNCH(COLS)                                                                                         \
+    e = cudaFuncSetAttribute(conv_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e == cudaSuccess) conv_tc_kernel<COLS><<<grid, TC_THREADS, smem, as_stream(stream)>>>(a);
+    switch (a.p.tmem_cols) {
+        case 32: SEMB_TC_LAUNCH(32) break;
+        case 64: SEMB_TC_LAUNCH(64) break;
+        case 128: SEMB_TC_LAUNCH(128) break;
+        default: SEMB_TC_LAUNCH(256) break;
+    }
+#undef SEMB_TC_LAUNCH
+    if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
+    return check_launch("conv_tc");
+}

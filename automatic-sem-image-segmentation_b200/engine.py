@@ -158,7 +158,8 @@ class ParamSpec:
 class Engine:
     """Owns buffers, parameters, scratch and the op list of ONE network instance."""
 
-    def __init__(self, n: int, dtype: str = "bf16", device: Optional[torch.device] = None, dry: bool = False):
+    def __init__(self, n: int, dtype: str = "bf16", device: Optional[torch.device] = None, dry: bool = False,
+                 use_tc: bool = True):
         # dry=True builds the op list / parameter maps on the CPU for host-logic tests; nothing can execute.
         self.dry = dry
         if not dry:
@@ -180,6 +181,10 @@ class Engine:
         self.finalized = False
         self.grads = self.adam_m = self.adam_v = None
         self._keep = []
+        # tensor-core path: bf16 storage only; packed bf16 weight images are refreshed after every weight change
+        self.tc_enabled = bool(use_tc) and dtype == "bf16"
+        self.tc_packs: List[dict] = []
+        self._pack_dirty = True
 
     # ---- construction ------------------------------------------------------------------
     def new_buf(self, h: int, w: int, pitch: int, name: str, requires_grad: bool = True, n: Optional[int] = None) -> Buf:
@@ -208,7 +213,28 @@ class Engine:
         # static plan of gradient accumulation: walk the ops in backward order once
         for op in reversed(self.ops):
             op.plan_backward()
+        for pk in self.tc_packs:
+            nbytes = int(self.lib.semb_pack_weights_tc(None, pk["R"], pk["S"], pk["Cin"], pk["Cout"], pk["flip"], None, None))
+            if nbytes < 0:
+                L.check(nbytes)
+            pk["buf"] = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device=self.device)
         self.finalized = True
+
+    def tc_pack(self, w: str, R: int, S: int, cin: int, cout: int, flip: int) -> dict:
+        pk = {"w": w, "R": R, "S": S, "Cin": cin, "Cout": cout, "flip": flip, "buf": None}
+        self.tc_packs.append(pk)
+        return pk
+
+    def repack(self):
+        """fp32 master weights -> packed bf16 UMMA images (after set_weights / Adam)."""
+        if not self.dry:
+            st = self.stream
+            for pk in self.tc_packs:
+                rc = self.lib.semb_pack_weights_tc(self.params.ptr(pk["w"]), pk["R"], pk["S"], pk["Cin"], pk["Cout"], pk["flip"],
+                                                   pk["buf"].data_ptr(), st)
+                if rc < 0:
+                    L.check(int(rc))
+        self._pack_dirty = False
 
     def gptr(self, name: str) -> int:
         o, _ = self.params.entries[name]
@@ -223,6 +249,7 @@ class Engine:
         spec = self.specs[name]
         store = self.params if spec.trainable else self.state
         store.get(name).copy_(torch.from_numpy(spec.to_phys(arr).reshape(-1)))
+        self._pack_dirty = True
 
     def get_param(self, name: str) -> np.ndarray:
         spec = self.specs[name]
@@ -259,6 +286,8 @@ class Engine:
     def forward(self, training: bool):
         if self.dry:
             raise L.SembError("dry engine: kernels need an sm_100a device, there is no CPU execution path")
+        if self._pack_dirty and self.tc_packs:
+            self.repack()
         for op in self.ops:
             op.fwd(training)
 
@@ -270,6 +299,8 @@ class Engine:
         L.check(self.lib.semb_adam_step(self.params.t.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                                         self.adam_v.data_ptr(), self.params.t.numel(), self.lr.data_ptr(),
                                         beta1, beta2, eps, gscale, self.adam_state.data_ptr(), self.stream))
+        if self.tc_packs:
+            self.repack()
 
 
 def plan_grad_write(view: View) -> int:
@@ -323,6 +354,15 @@ class ConvOp(Op):
         self.geom = L.ConvGeom(n, h, wd, oh, ow, cin, cout, k, k, stride, pad_tl[0], pad_tl[1], pad_mode, eng.dtype)
         self.stats = stats  # (zeroed-store name, offset, nstride, cstride)
         self.acc_x = 0
+        self.use_tc = (eng.tc_enabled and not transposed and stride == 1 and k in (1, 3))
+        if self.use_tc:
+            self.pk_fwd = eng.tc_pack(w, k, k, cin, cout, 0)
+            self.pk_bwd = None
+            if x.requires_grad and pad_mode == L.PAD_ZERO:
+                self.pk_bwd = eng.tc_pack(w, k, k, cin, cout, 1)
+                # stride-1 data gradient = conv of dy with the mirrored, transposed kernel, pad k-1-pad
+                self.geom_d = L.ConvGeom(n, oh, ow, h, wd, cout, cin, k, k, 1, k - 1 - pad_tl[0], k - 1 - pad_tl[1],
+                                         L.PAD_ZERO, eng.dtype)
 
     def plan_backward(self):
         if self.x.requires_grad:
@@ -338,6 +378,10 @@ class ConvOp(Op):
         e = self.eng
         sp, ns, cs = self._stats_args() if training else (None, 0, 0)
         bias = e.params.ptr(self.bias) if self.bias else None
+        if self.use_tc:
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom), C.byref(self.x.t), self.pk_fwd["buf"].data_ptr(), bias,
+                                             C.byref(self.y.t), sp, ns, cs, 0, e.stream))
+            return
         fn = e.lib.semb_conv2d_dgrad if self.transposed else e.lib.semb_conv2d_fwd
         L.check(fn(C.byref(self.geom), C.byref(self.x.t), e.params.ptr(self.w), bias, C.byref(self.y.t), sp, ns, cs, 0,
                    e.stream))
@@ -349,8 +393,12 @@ class ConvOp(Op):
             L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w), dbias,
                                             e.stream))
             if self.x.requires_grad:
-                L.check(e.lib.semb_conv2d_dgrad(C.byref(self.geom), C.byref(self.y.g), e.params.ptr(self.w), None,
-                                                C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
+                if self.use_tc and self.pk_bwd is not None:
+                    L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_d), C.byref(self.y.g), self.pk_bwd["buf"].data_ptr(), None,
+                                                     C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
+                else:
+                    L.check(e.lib.semb_conv2d_dgrad(C.byref(self.geom), C.byref(self.y.g), e.params.ptr(self.w), None,
+                                                    C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
         else:
             # d/dw of the transposed conv: wgrad of the equivalent conv with x':=d(out), dy':=in
             L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.y.g), C.byref(self.x.t), e.gptr(self.w), None,

@@ -31,8 +31,8 @@ def _to_numpy(x) -> np.ndarray:
 class _Instance:
     """One engine specialised to (N, H, W)."""
 
-    def __init__(self, n, h, w, filters, dtype):
-        self.eng = Engine(n, dtype)
+    def __init__(self, n, h, w, filters, dtype, use_tc=True):
+        self.eng = Engine(n, dtype, use_tc=use_tc)
         self.net = UNetBuilder(self.eng, h, w, filters)
         e = self.eng
         self.loss_sums = e.zeroed.add("loss/sums", 4)
@@ -79,13 +79,14 @@ class UNetModel:
     """MultiRes-UNet with the Keras model protocol, running on libsemb200 (sm_100a) only."""
 
     def __init__(self, input_shape=(256, 256, 1), filters: int = 16, output_channels: int = 1, dtype: str = "f32",
-                 batch_size: int = 1, seed: int = 0, use_cuda_graph: bool = True):
+                 batch_size: int = 1, seed: int = 0, use_cuda_graph: bool = True, use_tc: bool = True):
         if len(input_shape) == 2:
             input_shape = (input_shape[0], input_shape[1], 1)
         assert input_shape[2] == 1 and output_channels == 1
         self.input_shape = tuple(input_shape)
         self.filters, self.dtype, self.seed = filters, dtype, seed
         self.use_cuda_graph = use_cuda_graph
+        self.use_tc = use_tc
         self._instances: Dict[tuple, _Instance] = {}
         self._primary = self._instance(batch_size, input_shape[0], input_shape[1], init=True)
         self._current = self._primary
@@ -102,7 +103,7 @@ class UNetModel:
         key = (n, h, w)
         inst = self._instances.get(key)
         if inst is None:
-            inst = _Instance(n, h, w, self.filters, self.dtype)
+            inst = _Instance(n, h, w, self.filters, self.dtype, self.use_tc)
             if init:
                 inst.eng.init_params(self.seed)
             self._instances[key] = inst
@@ -117,6 +118,7 @@ class UNetModel:
             inst.eng.adam_m.copy_(cur.eng.adam_m)
             inst.eng.adam_v.copy_(cur.eng.adam_v)
             inst.eng.adam_state.copy_(cur.eng.adam_state)
+            inst.eng._pack_dirty = True
             self._current = inst
         return inst
 
@@ -221,6 +223,7 @@ class UNetModel:
                 torch.cuda.synchronize()
                 for t, sv in zip((e.params.t, e.state.t, e.adam_m, e.adam_v, e.adam_state), saved):
                     t.copy_(sv)
+                e.repack()          # packed tensor-core weights follow the restored master weights
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
                     inst.fwd_bwd(self.weighting)

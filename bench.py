@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- MultiRes-UNet 256x256 tiles/sec, full training step (fwd + weighted-BCE + bwd + Adam).
+
+    python bench.py --gpus N --steps K --warmup W            (driver: torchrun for N>1)
+    python bench.py --impl reference ...                     (the CPU arm: oracle on the host cores)
+
+Workload = BASELINE.json configs[1]: "UNet training 256x256x1 tiles bf16 batch 32 on 1xB200"; with N GPUs every
+rank trains batch 32 (weak scaling) and gradients are summed with ONE NCCL all-reduce of the flat gradient buffer.
+Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_TILE_FWD_BWD = {256: 31.669e9, 512: 126.676e9}     # SURVEY.md 8d / BASELINE.md section 2 (true channel counts)
+METRIC = "UNet 256x256 tiles/sec fwd+bwd"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_throughput(size: int, batch: int, steps: int, warmup: int):
+    """Oracle (torch-CPU restatement of the Keras-torch path) train step on the host cores; tiles/s."""
+    from oracle import unet as OU
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = OU.UNetSpec(16)
+    x, y, wgt = OU.synthetic_batch(batch, size, size)
+    tr = OU.UNetTrainer(spec, spec.init_params(0), wgt)
+    for _ in range(warmup):
+        tr.train_step(x, y)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(x, y)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    batch = args.cpu_batch
+    steps, warmup = min(args.steps, 4), min(args.warmup, 1)
+    tps, spt, cores = cpu_train_throughput(args.size, batch, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": tps, "unit": "tiles/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"MultiRes-UNet filters=16 {args.size}x{args.size}x1 full train step (fwd+wBCE+bwd+Adam)",
+                   "sample": f"batch {batch} per step on the host cores (the GPU arm runs batch {args.batch})"},
+        "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps of batch {batch}, oracle/ (torch {torch.__version__} CPU fp32, ATen/oneDNN; Keras is not installable here)"},
+        "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def profile_ops(inst, weighting, peaks, size, batch):
+    """One eager fwd+bwd with CUDA events around every engine op; returns the per-op table and the dominant conv."""
+    import sem_b200  # noqa: F401
+    from sem_b200.engine import ConvOp
+    e = inst.eng
+    recs = []
+
+    def timed(label, op, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        recs.append((label, op, a, b))
+
+    e.zero_step(zero_grads=True)
+    inst.stage_in()
+    for op in e.ops:
+        timed("fwd", op, lambda op=op: op.fwd(True))
+    inst.loss(weighting, with_grad=True)
+    for op in reversed(e.ops):
+        timed("bwd", op, lambda op=op: op.bwd())
+    torch.cuda.synchronize()
+    rows = []
+    for label, op, a, b in recs:
+        ms = a.elapsed_time(b)
+        row = {"phase": label, "op": type(op).__name__, "ms": ms}
+        if isinstance(op, ConvOp):
+            g = op.geom
+            taps = g.R * g.S
+            pix = g.N * g.OH * g.OW
+            esz = 2 if e.dtype_name == "bf16" else 4
+            flops_fwd = 2.0 * pix * taps * g.Cin * g.Cout                    # physical (8-padded) channels
+            row.update({"geom": f"{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.R} s{g.stride}{' T' if op.transposed else ''}",
+                        "flops": flops_fwd * (1 if label == "fwd" else 2),
+                        "bytes": (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz * (1 if label == "fwd" else 2)})
+        rows.append(row)
+    return rows
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import sem_b200
+    from sem_b200 import UNetModel, _lib as L
+    from oracle import unet as OU   # only for the synthetic inputs definition and the cpu_baseline leg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+    size, batch = args.size, args.batch
+
+    x, y, wgt = OU.synthetic_batch(batch, size, size)
+    if world > 1:   # each rank gets its own tiles
+        g = torch.Generator().manual_seed(1000 + rank)
+        x = torch.rand(x.shape, generator=g)
+    m = UNetModel((size, size, 1), 16, dtype=args.dtype, batch_size=batch, seed=0, use_cuda_graph=not args.no_graph)
+    m.compile(weighting=wgt, learning_rate=1e-3)
+    if world > 1:
+        m.set_distributed()
+    inst = m._current
+    xn, yn = x.numpy(), y.numpy()
+
+    # launches per step, counted on an eager step (graph replays do not pass through the host-side counter)
+    saved_graph = m.use_cuda_graph
+    m.use_cuda_graph = False
+    c0 = L.launch_count()
+    m.train_step(xn, yn)
+    launches_per_step = L.launch_count() - c0
+    m.use_cuda_graph = saved_graph
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (`value`)
+    for _ in range(max(args.warmup, 3)):
+        m.train_step(xn, yn)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        m._step_device(inst)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    # ---- end-to-end timing through the public API with HOST buffers (`e2e`)
+    barrier()
+    t0 = time.perf_counter()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    last = None
+    for _ in range(args.steps):
+        last = m.train_step(xn, yn)
+    ev3.record()
+    barrier()
+    e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    tiles = batch * world * args.steps
+    value = tiles / (dev_ms / 1e3)
+    e2e_value = tiles / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- per-op profile (eager, CUDA events) -> dominant kernel roofline
+    rows = profile_ops(inst, wgt, peaks, size, batch)
+    total_ms = sum(r["ms"] for r in rows)
+    convs = [r for r in rows if "flops" in r]
+    top = max(convs, key=lambda r: r["ms"])
+    conv_ms = sum(r["ms"] for r in convs)
+    ridge = peaks["tflops_burst"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    ai = top["flops"] / top["bytes"]
+    if ai >= ridge:
+        roof = {"bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["traffic"] = None
+    roof["kernel"] = f"{top['op']}.{top['phase']} {top['geom']}"
+    roof["kernel_ms"] = top["ms"]
+    roof["kernel_share_of_step"] = top["ms"] / total_ms
+    roof["arithmetic_intensity_flop_per_byte"] = ai
+    roof["peak_source"] = peaks["source"] + ", burst figure (kernel timed alone)"
+    net_tflops = value / world * FLOP_PER_TILE_FWD_BWD.get(size, 31.669e9 * (size / 256) ** 2) / 1e12
+    roof["net_conv_tflops"] = net_tflops
+    roof["net_frac_of_tensor_peak_sustained"] = net_tflops / peaks["tflops_sustained"]
+    roof["conv_share_of_step"] = conv_ms / total_ms
+
+    # ---- CPU baseline beside it (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        tps, spt, cores = cpu_train_throughput(size, args.cpu_batch, 2, 1)
+        cpu = {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port",
+               "sample": f"2 steps of batch {args.cpu_batch} after 1 warm-up, oracle/ train step (torch CPU fp32)"}
+
+    esz = 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "tiles/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"MultiRes-UNet filters=16 {size}x{size}x1 full train step (fwd+wBCE+bwd+Adam), batch {batch} per GPU",
+                   "global_batch": batch * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                   "l2": "per-step working set (activations+gradients, several GB) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": "tiles/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(2 * batch * size * size * esz), "d2h_bytes_per_step": 16},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "launches_per_step": int(launches_per_step),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "last_step_metrics": last,
+    }
+    print(json.dumps(line), flush=True)
+    if args.profile_out:
+        with open(args.profile_out, "w") as fh:
+            json.dump({"total_ms_eager": total_ms, "rows": rows}, fh, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -104,6 +104,25 @@ int semb_conv2d_dgrad(const semb_conv_geom* g, const semb_tensor* dy, const floa
 int semb_conv2d_wgrad(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy,
                       float* dw, float* dbias, void* stream);
 
+/* ---- tensor-core (tcgen05 / TMEM) convolutions, bf16 storage ------------------------------ */
+
+/* Packs fp32 HWIO weights (8-padded channels) into the bf16 UMMA shared-memory image read by
+ * semb_conv2d_fwd_tc: [n-chunk][k-chunk][tap][k/8][n][8].  flip=1 packs the spatially mirrored,
+ * channel-transposed kernel, so that the same implicit-GEMM kernel computes the stride-1 data gradient
+ * (call semb_conv2d_fwd_tc with x:=dy, y:=dx, Cin/Cout swapped, pad := k-1-pad).
+ * Returns the packed size in bytes (also when dst==NULL, for sizing) or a negative SEMB_E* code. */
+int64_t semb_pack_weights_tc(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout,
+                             int32_t flip, void* dst, void* stream);
+
+/* Same contract as semb_conv2d_fwd for stride 1, R=S in {1,3}, bf16 storage: im2col-free implicit GEMM on
+ * tcgen05.mma (M = 128 output pixels per CTA, N = Cout, K = taps x Cin) with the fp32 accumulator in TMEM.
+ * The A operand is the NHWC halo tile staged once in shared memory; the nine taps are shifted UMMA
+ * descriptors over that tile.  Zero or reflect padding.  UNet_Segmentation.py:421,465-468,490-499;
+ * CycleGAN.py:327,333. */
+int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
+                       const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
+                       int32_t accumulate, void* stream);
+
 /* ---- normalisation + activation (fused elementwise) --------------------------------------- */
 
 /* From moments to the affine that BatchNormalization / GroupNormalization applies.

@@ -427,3 +427,74 @@ def test_error_codes():
     with pytest.raises(ValueError):
         L.check(lib.semb_maxpool2x2_fwd(C.byref(v), C.byref(v), 1, 4, 4, L.F32, U.stream()))
     assert "maxpool" in L.last_error()
+
+
+# ---- tcgen05 implicit-GEMM conv -----------------------------------------------------------------------------
+# (N,H,W,Cin,Cout,k,pad_mode)
+TC_CASES = [
+    (2, 32, 24, 8, 16, 3, "zero"),
+    (1, 16, 16, 32, 8, 3, "zero"),
+    (2, 16, 16, 64, 24, 3, "zero"),
+    (1, 16, 16, 144, 216, 3, "zero"),      # K chunks of 16
+    (1, 16, 8, 216, 432, 1, "zero"),       # two N chunks
+    (1, 20, 12, 24, 40, 3, "zero"),        # partial tiles
+    (1, 16, 16, 256, 72, 3, "zero"),
+    (2, 16, 16, 56, 32, 1, "zero"),
+    (1, 16, 16, 32, 32, 3, "reflect"),     # CycleGAN residual block conv
+    (4, 64, 64, 16, 16, 3, "zero"),        # many tiles
+    (1, 16, 16, 13, 26, 3, "zero"),        # channel counts that are not multiples of 8 (padded lanes)
+    (1, 16, 16, 105, 51, 1, "zero"),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_fwd_and_dgrad(case):
+    """bf16 tensor-core conv vs the oracle on bf16-rounded operands (x and w): only fp32 summation order and the
+    bf16 rounding of the stored output differ."""
+    n, h, w_, cin, cout, k, pad_mode = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(11)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wt = U.bf16_round(torch.randn(k, k, cin, cout, generator=g) * 0.1)
+    bias = torch.randn(cout, generator=g)
+    p = (k - 1) // 2
+    xr = x.clone().requires_grad_(True)
+    if pad_mode == "reflect":
+        y_ref = OL.conv2d(OL.reflection_pad(xr, 2 * p, 2 * p), wt, bias, 1, "valid")
+    else:
+        y_ref = OL.conv2d(xr, wt, bias, 1, "same")
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    cpi, cpo = U.pad8(cin), U.pad8(cout)
+    pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
+    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, pm, L.BF16)
+    xd = U.to_dev(x, "bf16", pitch=cpi + 8, coff=8)
+    yd = torch.zeros((n, h, w_, cpo + 16), dtype=torch.bfloat16, device="cuda")
+    wd, bd = U.pad_w(wt), U.pad_v(bias)
+    nbytes = lib.semb_pack_weights_tc(None, k, k, cpi, cpo, 0, None, None)
+    assert nbytes > 0
+    wp = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+    assert lib.semb_pack_weights_tc(wd.data_ptr(), k, k, cpi, cpo, 0, wp.data_ptr(), U.stream()) == nbytes
+    stats = torch.zeros(2 * cpo, device="cuda", dtype=torch.float64)
+    xv, yv = U.view(xd, 8, cpi), U.view(yd, 8, cpo)
+    L.check(lib.semb_conv2d_fwd_tc(C.byref(geom), C.byref(xv), wp.data_ptr(), bd.data_ptr(), C.byref(yv), stats.data_ptr(), 0, cpo,
+                                   0, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(yd[..., 8:8 + cout], y_ref) < 1e-2
+    assert float(yd[..., :8].abs().max()) == 0 and float(yd[..., 8 + cpo:].abs().max()) == 0
+    if cpo > cout:
+        assert float(yd[..., 8 + cout:8 + cpo].abs().max()) == 0      # padded output channels stay exactly zero
+    assert U.rel_err(stats[:cout], y_ref.detach().double().sum(dim=(0, 1, 2))) < 1e-4
+    assert U.rel_err(stats[cpo:cpo + cout], (y_ref.detach().double() ** 2).sum(dim=(0, 1, 2))) < 1e-4
+    if pad_mode != "zero":
+        return
+    # data gradient through the SAME kernel with the mirrored / transposed pack, accumulate on top of ones
+    wpf = torch.zeros(lib.semb_pack_weights_tc(None, k, k, cpi, cpo, 1, None, None) // 2, dtype=torch.bfloat16, device="cuda")
+    assert lib.semb_pack_weights_tc(wd.data_ptr(), k, k, cpi, cpo, 1, wpf.data_ptr(), U.stream()) > 0
+    gd = L.ConvGeom(n, h, w_, h, w_, cpo, cpi, k, k, 1, k - 1 - p, k - 1 - p, L.PAD_ZERO, L.BF16)
+    dyd = U.to_dev(dy, "bf16")
+    dxd = torch.ones((n, h, w_, cpi), dtype=torch.bfloat16, device="cuda")
+    dyv, dxv = U.view(dyd), U.view(dxd)
+    L.check(lib.semb_conv2d_fwd_tc(C.byref(gd), C.byref(dyv), wpf.data_ptr(), None, C.byref(dxv), None, 0, 0, 1, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(dxd[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2

@@ -73,10 +73,10 @@ def test_weights_roundtrip_keras_order():
         m.set_weights(w[:-1])
 
 
-@pytest.mark.parametrize("shape", [(2, 32, 32), (1, 40, 24)])
+@pytest.mark.parametrize("shape", [(2, 32, 32), (2, 44, 52)])
 def test_train_step_matches_oracle_f32(shape):
     """One full TorchTrainer.train_step: loss/metrics, every gradient, post-Adam weights, moving statistics.
-    (1,40,24) exercises the reflect-pad to a multiple of 16 and the crop."""
+    (2,44,52) exercises the reflect-pad to a multiple of 16 and the crop."""
     n, h, w = shape
     spec = OU.UNetSpec(16)
     p0 = spec.init_params(seed=0)
