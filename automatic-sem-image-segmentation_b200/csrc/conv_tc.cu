@@ -272,6 +272,153 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const TcArgs a) {
     if (warp == 0) tmem_dealloc<COLS>(tmem);
 }
 
+// ---- weight gradient on the tensor cores ------------------------------------------------------------------
+// dW[tap][ci][co] = sum_pixels x[pixel+tap][ci] * dy[pixel][co]  as  D[M=co][N=ci] += A[co][k] * B[ci][k], k = pixels.
+// Both operands are read straight from their NHWC channel-group planes as MN-MAJOR UMMA operands (the same
+// shared-memory image the forward kernel uses as K-major): 8 consecutive pixels of a row are the 8 K-rows of a
+// core matrix, LBO = next pixel row, SBO = next channel-group plane.  Each tap owns a block of TMEM columns;
+// a CTA walks many pixel tiles (split-K over pixels), accumulating in TMEM, and flushes once with coalesced
+// fp32 reductions into the HWIO gradient.
+struct WgPlan { int NCH, nchunks, tpp, tapgroups, mtiles, cols, splits; };
+
+static inline WgPlan wg_plan(int Cin, int Cout, int taps, long long total_tiles) {
+    WgPlan p;
+    const int cin16 = (Cin + 15) / 16 * 16;
+    p.NCH = cin16 < 256 ? cin16 : 256;
+    p.nchunks = (cin16 + p.NCH - 1) / p.NCH;
+    // <= 128 TMEM columns per CTA so that four CTAs share an SM and hide each other's load / MMA latency
+    int tpp = 128 / p.NCH;
+    if (tpp < 1) tpp = 1;
+    if (tpp > taps) tpp = taps;
+    p.tpp = tpp;
+    p.tapgroups = (taps + p.tpp - 1) / p.tpp;
+    p.mtiles = (Cout + 127) / 128;
+    int c = p.tpp * p.NCH;
+    p.cols = c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512)));
+    const int work = p.mtiles * p.tapgroups * p.nchunks;
+    const int per_sm = 512 / p.cols > 6 ? 6 : 512 / p.cols;
+    long long s = (148LL * per_sm + work - 1) / work;
+    if (s > total_tiles) s = total_tiles;
+    if (s < 1) s = 1;
+    p.splits = (int)s;
+    return p;
+}
+
+struct WgArgs {
+    int N, H, W, OH, OW, Cin, Cout, R, S, pad_t, pad_l, pad_mode;
+    const bf16* x; int x_pitch, x_coff;
+    const bf16* dy; int dy_pitch, dy_coff;
+    float* dw;
+    int tiles_x, tiles_y, total_tiles;
+    WgPlan p;
+    int plane_a, plane_b, halo_h, halo_w;
+};
+
+template <int COLS>
+__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const WgArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* As = smem;                               // dy tile : [16 co-groups][128 pixels][16 B]
+    uint8_t* Bs = smem + 16 * a.plane_a;              // x halo  : [NCH/8 ci-groups][halo pixels][16 B]
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int taps = a.R * a.S;
+    const int NCH = a.p.NCH;
+    int wi = blockIdx.y;
+    const int nc = wi % a.p.nchunks; wi /= a.p.nchunks;
+    const int tg = wi % a.p.tapgroups; wi /= a.p.tapgroups;
+    const int mt = wi;
+    const int tap0 = tg * a.p.tpp;
+    const int ntaps = min(a.p.tpp, taps - tap0);
+    const int co0 = mt * 128, ci0 = nc * NCH;
+    const int planes_a = min(16, (a.Cout - co0 + 7) / 8);
+    const int planes_b = min(NCH / 8, (a.Cin - ci0 + 7) / 8);
+    const int halo_pix = a.halo_h * a.halo_w;
+
+    if (warp == 0) tmem_alloc<COLS>(smem_u32(&tmem_slot));
+    if (tid == 0) mbar_init(smem_u32(&mbar), 1);
+    // channel-group planes that are never loaded must still be finite zeros for the N side (they feed valid rows)
+    for (int idx = tid; idx < (NCH / 8 - planes_b) * halo_pix; idx += TC_THREADS) {
+        const int k8 = planes_b + idx / halo_pix, pix = idx % halo_pix;
+        *reinterpret_cast<uint4*>(Bs + (size_t)k8 * a.plane_b + pix * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = instr_desc(128, NCH, 1, 1);
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += a.p.splits, ++it) {
+        const int n = t / (a.tiles_x * a.tiles_y);
+        const int trem = t % (a.tiles_x * a.tiles_y);
+        const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
+        // ---- A: dy tile (no halo)
+        for (int idx = tid; idx < planes_a * 128; idx += TC_THREADS) {
+            const int k8 = idx % planes_a, pix = idx / planes_a;
+            const int oy = y0 + pix / TILE_W, ox = x0 + pix % TILE_W;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (oy < a.OH && ox < a.OW)
+                v = *reinterpret_cast<const uint4*>(a.dy + ((size_t)(n * a.OH + oy) * a.OW + ox) * a.dy_pitch + a.dy_coff + co0 + k8 * 8);
+            *reinterpret_cast<uint4*>(As + (size_t)k8 * a.plane_a + pix * 16) = v;
+        }
+        // ---- B: x halo tile
+        for (int idx = tid; idx < planes_b * halo_pix; idx += TC_THREADS) {
+            const int k8 = idx % planes_b, pix = idx / planes_b;
+            const int hy = pix / a.halo_w, hx = pix % a.halo_w;
+            int iy = y0 - a.pad_t + hy, ix = x0 - a.pad_l + hx;
+            if (a.pad_mode == SEMB_PAD_REFLECT) {
+                if (iy > -a.H && iy < 2 * a.H - 1) iy = reflect_index(iy, a.H);
+                if (ix > -a.W && ix < 2 * a.W - 1) ix = reflect_index(ix, a.W);
+            }
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+                v = *reinterpret_cast<const uint4*>(a.x + ((size_t)(n * a.H + iy) * a.W + ix) * a.x_pitch + a.x_coff + ci0 + k8 * 8);
+            *reinterpret_cast<uint4*>(Bs + (size_t)k8 * a.plane_b + pix * 16) = v;
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const int tap = tap0 + tl, r = tap / a.S, s = tap % a.S;
+                for (int ks = 0; ks < TILE_H / 2; ++ks) {       // 16 pixels (two rows of 8) per MMA
+                    const uint64_t ad = smem_desc(a_base + ks * 2 * TILE_W * 16, TILE_W * 16, a.plane_a);
+                    const uint64_t bd = smem_desc(b_base + ((2 * ks + r) * a.halo_w + s) * 16, a.halo_w * 16, a.plane_b);
+                    umma_bf16(tmem + tl * NCH, ad, bd, idesc, (it | ks) != 0);
+                }
+            }
+            umma_commit(smem_u32(&mbar));
+        }
+        mbar_wait(smem_u32(&mbar), phase);
+        phase ^= 1;
+    }
+    tc_fence_after();
+    // ---- flush: TMEM lane = co, columns = [tap][ci]; lanes of a warp hit consecutive co -> coalesced reductions
+    if (it > 0) {
+        const int co = co0 + warp * 32 + lane;
+        for (int tl = 0; tl < ntaps; ++tl) {
+            const int tap = tap0 + tl;
+            for (int g = 0; g < NCH / 8; ++g) {
+                float v[8];
+                tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + tl * NCH + g * 8, v);
+                if (co < a.Cout) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = ci0 + g * 8 + i;
+                        if (ci < a.Cin) atomicAdd(a.dw + ((size_t)tap * a.Cin + ci) * a.Cout + co, v[i]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<COLS>(tmem);
+}
+
 static size_t tc_smem_bytes(const TcPlan& p, int taps, int plane_bytes) {
     return (size_t)(p.KC / 8) * plane_bytes + (size_t)taps * p.KC * p.NC * 2 + (size_t)8 * p.NC * sizeof(float);
 }
@@ -336,4 +483,42 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
 #undef SEMB_TC_LAUNCH
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
     return check_launch("conv_tc");
+}
+
+extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw,
+                                    void* stream) {
+    SEMB_REQUIRE(g && x && dy && dw, SEMB_ESHAPE, "wgrad_tc: null argument");
+    SEMB_REQUIRE(g->dtype == SEMB_BF16, SEMB_ESHAPE, "wgrad_tc: bf16 storage only");
+    SEMB_REQUIRE(g->stride == 1 && ((g->R == 1 && g->S == 1) || (g->R == 3 && g->S == 3)), SEMB_ESHAPE,
+                 "wgrad_tc: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
+    SEMB_REQUIRE(view_ok(x) && view_ok(dy) && x->C == g->Cin && dy->C == g->Cout, SEMB_EALIGN, "wgrad_tc: bad tensor views");
+    WgArgs a{};
+    a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
+    a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
+    a.x = reinterpret_cast<const bf16*>(x->ptr); a.x_pitch = x->pitch; a.x_coff = x->coff;
+    a.dy = reinterpret_cast<const bf16*>(dy->ptr); a.dy_pitch = dy->pitch; a.dy_coff = dy->coff;
+    a.dw = dw;
+    a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
+    a.total_tiles = g->N * a.tiles_x * a.tiles_y;
+    a.p = wg_plan(g->Cin, g->Cout, g->R * g->S, a.total_tiles);
+    a.halo_h = TILE_H + g->R - 1; a.halo_w = TILE_W + g->S - 1;
+    a.plane_a = TILE_H * TILE_W * 16 + 16;
+    a.plane_b = a.halo_h * a.halo_w * 16 + 16;
+    const size_t smem = (size_t)16 * a.plane_a + (size_t)(a.p.NCH / 8) * a.plane_b;
+    SEMB_REQUIRE(smem <= 200 * 1024, SEMB_EWORKSPACE, "wgrad_tc: %zu bytes of shared memory needed", smem);
+    dim3 grid(a.p.splits, a.p.mtiles * a.p.tapgroups * a.p.nchunks);
+    cudaError_t e = cudaSuccess;
+#define SEMB_WG_LAUNCH(COLS)                                                                                          \
+    e = cudaFuncSetAttribute(wgrad_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e == cudaSuccess) wgrad_tc_kernel<COLS><<<grid, TC_THREADS, smem, as_stream(stream)>>>(a);
+    switch (a.p.cols) {
+        case 32: SEMB_WG_LAUNCH(32) break;
+        case 64: SEMB_WG_LAUNCH(64) break;
+        case 128: SEMB_WG_LAUNCH(128) break;
+        case 256: SEMB_WG_LAUNCH(256) break;
+        default: SEMB_WG_LAUNCH(512) break;
+    }
+#undef SEMB_WG_LAUNCH
+    if (e != cudaSuccess) { set_error("wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
+    return check_launch("wgrad_tc");
 }

@@ -44,9 +44,28 @@ struct AffArgs {
     int ppb;  // pixels per block
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) affine_act_fwd_kernel(const AffArgs p) {
+__device__ __forceinline__ float act_bwd_from_u(float u, int act) {
+    switch (act) {
+        case SEMB_ACT_RELU: return u > 0.f ? 1.f : 0.f;
+        case SEMB_ACT_LEAKY: return u > 0.f ? 1.f : 0.2f;
+        case SEMB_ACT_SIGMOID: { const float s = 1.f / (1.f + expf(-u)); return s * (1.f - s); }
+        case SEMB_ACT_TANH: { const float t = tanhf(u); return 1.f - t * t; }
+        default: return 1.f;
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void ld_params(const float* p, size_t off, float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = p[off + i];
+}
+
+// y = act(a*sa+ta [+ actb(b*sb+tb)]), optional fp64 moments of y.  U pixels per thread are loaded before any is used.
+template <typename T, bool HAS_B, int ACT, int ACTB>
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_fwd_kernel(const AffArgs p) {
     extern __shared__ float sm[];  // [rows][2][C] when moments are requested
+    constexpr int U = 2;
+    const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     const int n = blockIdx.y;
     const int c = L.cg * 8;
@@ -58,36 +77,40 @@ __global__ void __launch_bounds__(256) affine_act_fwd_kernel(const AffArgs p) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; }
     if (L.active) {
-        if (p.mode_a != SEMB_AFF_NONE)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { sa[i] = p.scale_a[aoff + i]; ta[i] = p.shift_a[aoff + i]; }
-        if (p.b.ptr && p.mode_b != SEMB_AFF_NONE)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { sb[i] = p.scale_b[aoff + i]; tb[i] = p.shift_b[aoff + i]; }
+        if (p.mode_a != SEMB_AFF_NONE) { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
+        if (HAS_B && p.mode_b != SEMB_AFF_NONE) { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
     }
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 
     if (L.active) {
-        for (int px = begin + L.prow; px < end; px += L.rows) {
-            float va[8], vy[8];
-            Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
+        for (int base = begin + L.prow; base < end; base += L.rows * U) {
+            float va[U][8], vb[U][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vy[i] = fmaf(va[i], sa[i], ta[i]);
-            if (p.b.ptr) {
-                float vb[8];
-                Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vy[i] += act_fwd(fmaf(vb[i], sb[i], tb[i]), p.actb);
+            for (int u = 0; u < U; ++u) {
+                const int px = base + u * L.rows;
+                if (px < end) {
+                    Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va[u]);
+                    if (HAS_B) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb[u]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                vy[i] = act_fwd(vy[i], p.act);
-                s1[i] += vy[i];
-                s2[i] += vy[i] * vy[i];
+            for (int u = 0; u < U; ++u) {
+                const int px = base + u * L.rows;
+                if (px < end) {
+                    float vy[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float t = fmaf(va[u][i], sa[i], ta[i]);
+                        if (HAS_B) t += act_fwd(fmaf(vb[u][i], sb[i], tb[i]), actb);
+                        vy[i] = act_fwd(t, act);
+                        s1[i] += vy[i];
+                        s2[i] += vy[i] * vy[i];
+                    }
+                    Vec8<T>::store(vptr_mut<T>(p.y, pix0 + px, c), vy);
+                }
             }
-            Vec8<T>::store(vptr_mut<T>(p.y, pix0 + px, c), vy);
         }
     }
     if (p.dstats) {
@@ -110,85 +133,99 @@ __global__ void __launch_bounds__(256) affine_act_fwd_kernel(const AffArgs p) {
     }
 }
 
-// backward pass 1: sums[0]=sum g, [1]=sum g*xhat_a, [2]=sum gb, [3]=sum gb*xhat_b
-template <typename T>
-__global__ void __launch_bounds__(256) affine_act_bwd_reduce_kernel(const AffArgs p) {
-    extern __shared__ float sm[];  // [4][C]
+// backward pass 1: sums[0]=sum g, [1]=sum g*xhat_a, [2]=sum gb, [3]=sum gb*xhat_b.  The activation derivative is
+// recomputed from the pre-activation u = A(a)+actb(B(b)) (same fp32 arithmetic as the forward), so the saved
+// output y is never re-read.
+template <typename T, bool HAS_B, int ACT, int ACTB>
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kernel(const AffArgs p) {
+    extern __shared__ float sm[];  // [rows][4][C]
+    constexpr int U = HAS_B ? 1 : 2;
+    const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     const int n = blockIdx.y;
     const int c = L.cg * 8;
     const long long pix0 = (long long)n * p.HW;
     const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
     const size_t aoff = (size_t)n * p.aff_nstride + c;
-    const bool has_b = p.b.ptr != nullptr;
-    const bool red_a = p.mode_a == SEMB_AFF_BATCH, red_b = has_b && p.mode_b == SEMB_AFF_BATCH;
+    const bool red_a = p.mode_a == SEMB_AFF_BATCH, red_b = HAS_B && p.mode_b == SEMB_AFF_BATCH;
 
-    float ma[8], ia[8], mb[8], ib[8], sb[8], tb[8];
+    float sa[8], ta[8], ma[8], sb[8], tb[8], mb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ma[i] = 0.f; ia[i] = 1.f; mb[i] = 0.f; ib[i] = 1.f; sb[i] = 1.f; tb[i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; ma[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; mb[i] = 0.f; }
     if (L.active) {
-        if (red_a)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { ma[i] = p.mean_a[aoff + i]; ia[i] = p.invstd_a[aoff + i]; }
-        if (red_b)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { mb[i] = p.mean_b[aoff + i]; ib[i] = p.invstd_b[aoff + i]; }
-        if (has_b && p.mode_b != SEMB_AFF_NONE)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { sb[i] = p.scale_b[aoff + i]; tb[i] = p.shift_b[aoff + i]; }
+        if (p.mode_a != SEMB_AFF_NONE) { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
+        if (red_a) ld_params<0>(p.mean_a, aoff, ma);
+        if (HAS_B && p.mode_b != SEMB_AFF_NONE) { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
+        if (red_b) ld_params<0>(p.mean_b, aoff, mb);
     }
     float q0[8], q1[8], q2[8], q3[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { q0[i] = q1[i] = q2[i] = q3[i] = 0.f; }
 
     if (L.active) {
-        for (int px = begin + L.prow; px < end; px += L.rows) {
-            float g[8], vy[8];
-            Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g);
-            if (p.act != SEMB_ACT_NONE) {
-                Vec8<T>::load(vptr<T>(p.y, pix0 + px, c), vy);
+        for (int base = begin + L.prow; base < end; base += L.rows * U) {
+            float g[U][8], va[U][8], vb[U][8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] *= act_bwd_from_y(vy[i], p.act);
+            for (int u = 0; u < U; ++u) {
+                const int px = base + u * L.rows;
+                if (px < end) {
+                    Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g[u]);
+                    Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va[u]);
+                    if (HAS_B) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb[u]);
+                }
             }
-            if (red_a) {
-                float va[8];
-                Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { q0[i] += g[i]; q1[i] += g[i] * (va[i] - ma[i]) * ia[i]; }
-            }
-            if (red_b) {
-                float vb[8];
-                Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb);
+            for (int u = 0; u < U; ++u) {
+                const int px = base + u * L.rows;
+                if (px < end) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float gb = g[i];
-                    if (p.actb != SEMB_ACT_NONE) gb *= act_bwd_from_y(act_fwd(fmaf(vb[i], sb[i], tb[i]), p.actb), p.actb);
-                    q2[i] += gb;
-                    q3[i] += gb * (vb[i] - mb[i]) * ib[i];
+                    for (int i = 0; i < 8; ++i) {
+                        float ub = 0.f, t = fmaf(va[u][i], sa[i], ta[i]);
+                        if (HAS_B) { ub = fmaf(vb[u][i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                        const float gg = g[u][i] * act_bwd_from_u(t, act);
+                        q0[i] += gg;
+                        q1[i] += gg * (va[u][i] - ma[i]);
+                        if (HAS_B) {
+                            const float gb = gg * act_bwd_from_u(ub, actb);
+                            q2[i] += gb;
+                            q3[i] += gb * (vb[u][i] - mb[i]);
+                        }
+                    }
                 }
             }
         }
     }
-    for (int i = threadIdx.x; i < 4 * p.C; i += 256) sm[i] = 0.f;
-    __syncthreads();
+    // block combine without shared-memory atomics (fp32 smem atomics are CAS loops: 256-way contention for small C):
+    // partials [rows][4][C], then one thread per channel adds the rows in a fixed order
     if (L.active) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (red_a) { atomicAdd(&sm[c + i], q0[i]); atomicAdd(&sm[p.C + c + i], q1[i]); }
-            if (red_b) { atomicAdd(&sm[2 * p.C + c + i], q2[i]); atomicAdd(&sm[3 * p.C + c + i], q3[i]); }
+            sm[(L.prow * 4 + 0) * p.C + c + i] = q0[i];
+            sm[(L.prow * 4 + 1) * p.C + c + i] = q1[i];
+            sm[(L.prow * 4 + 2) * p.C + c + i] = q2[i];
+            sm[(L.prow * 4 + 3) * p.C + c + i] = q3[i];
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < p.C; i += 256) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+        for (int r = 0; r < L.rows; ++r) {
+            t0 += sm[(r * 4 + 0) * p.C + i]; t1 += sm[(r * 4 + 1) * p.C + i];
+            t2 += sm[(r * 4 + 2) * p.C + i]; t3 += sm[(r * 4 + 3) * p.C + i];
+        }
         float* st = p.stats + (size_t)n * p.stats_nstride + i;
-        if (red_a) { atomicAdd(st, sm[i]); atomicAdd(st + p.stats_cstride, sm[p.C + i]); }
-        if (red_b) { atomicAdd(st + 2 * p.stats_cstride, sm[2 * p.C + i]); atomicAdd(st + 3 * p.stats_cstride, sm[3 * p.C + i]); }
+        const size_t ao = (size_t)n * p.aff_nstride + i;
+        if (red_a) { atomicAdd(st, t0); atomicAdd(st + p.stats_cstride, t1 * p.invstd_a[ao]); }
+        if (red_b) { atomicAdd(st + 2 * p.stats_cstride, t2); atomicAdd(st + 3 * p.stats_cstride, t3 * p.invstd_b[ao]); }
     }
 }
 
-// backward pass 2
-template <typename T>
-__global__ void __launch_bounds__(256) affine_act_bwd_apply_kernel(const AffArgs p) {
+// backward pass 2:  da = sa*g + Pa*a + Qa  with  Pa = -sa*inv*c2, Qa = -sa*c1 + sa*inv*c2*mean  (batch-stat norm),
+// Pa = Qa = 0 for a constant affine; same for b with gb = g*actb'(ub).
+template <typename T, bool HAS_B, int ACT, int ACTB>
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kernel(const AffArgs p) {
+    constexpr int U = HAS_B ? 1 : 2;
+    const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     if (!L.active) return;
     const int n = blockIdx.y;
@@ -196,74 +233,78 @@ __global__ void __launch_bounds__(256) affine_act_bwd_apply_kernel(const AffArgs
     const long long pix0 = (long long)n * p.HW;
     const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
     const size_t aoff = (size_t)n * p.aff_nstride + c;
-    const bool has_b = p.b.ptr != nullptr;
 
-    float sa[8], ma[8], ia[8], k1a[8], k2a[8], sb[8], tb[8], mb[8], ib[8], k1b[8], k2b[8];
+    float sa[8], ta[8], Pa[8], Qa[8], sb[8], tb[8], Pb[8], Qb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        sa[i] = 1.f; ma[i] = 0.f; ia[i] = 0.f; k1a[i] = 0.f; k2a[i] = 0.f;
-        sb[i] = 1.f; tb[i] = 0.f; mb[i] = 0.f; ib[i] = 0.f; k1b[i] = 0.f; k2b[i] = 0.f;
+    for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; Pa[i] = 0.f; Qa[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; Pb[i] = 0.f; Qb[i] = 0.f; }
+    if (p.mode_a != SEMB_AFF_NONE) { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
+    if (p.mode_a == SEMB_AFF_BATCH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float k = sa[i] * p.invstd_a[aoff + i] * p.c2_a[aoff + i];
+            Pa[i] = -k;
+            Qa[i] = fmaf(k, p.mean_a[aoff + i], -sa[i] * p.c1_a[aoff + i]);
+        }
     }
-    if (p.mode_a != SEMB_AFF_NONE)
+    if (HAS_B && p.mode_b != SEMB_AFF_NONE) { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
+    if (HAS_B && p.mode_b == SEMB_AFF_BATCH) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sa[i] = p.scale_a[aoff + i];
-    if (p.mode_a == SEMB_AFF_BATCH)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ma[i] = p.mean_a[aoff + i]; ia[i] = p.invstd_a[aoff + i]; k1a[i] = p.c1_a[aoff + i]; k2a[i] = p.c2_a[aoff + i]; }
-    if (has_b && p.mode_b != SEMB_AFF_NONE)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sb[i] = p.scale_b[aoff + i]; tb[i] = p.shift_b[aoff + i]; }
-    if (has_b && p.mode_b == SEMB_AFF_BATCH)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { mb[i] = p.mean_b[aoff + i]; ib[i] = p.invstd_b[aoff + i]; k1b[i] = p.c1_b[aoff + i]; k2b[i] = p.c2_b[aoff + i]; }
+        for (int i = 0; i < 8; ++i) {
+            const float k = sb[i] * p.invstd_b[aoff + i] * p.c2_b[aoff + i];
+            Pb[i] = -k;
+            Qb[i] = fmaf(k, p.mean_b[aoff + i], -sb[i] * p.c1_b[aoff + i]);
+        }
+    }
+    const bool wa = p.da.ptr != nullptr, wb = HAS_B && p.db.ptr != nullptr;
 
-    for (int px = begin + L.prow; px < end; px += L.rows) {
-        float g[8], vy[8];
-        Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g);
-        if (p.act != SEMB_ACT_NONE) {
-            Vec8<T>::load(vptr<T>(p.y, pix0 + px, c), vy);
+    for (int base = begin + L.prow; base < end; base += L.rows * U) {
+        float g[U][8], va[U][8], vb[U][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] *= act_bwd_from_y(vy[i], p.act);
+        for (int u = 0; u < U; ++u) {
+            const int px = base + u * L.rows;
+            if (px < end) {
+                Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g[u]);
+                Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va[u]);
+                if (HAS_B) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb[u]);
+            }
         }
-        if (p.da.ptr) {
-            float d[8];
-            if (p.mode_a == SEMB_AFF_BATCH) {
-                float va[8];
-                Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) d[i] = sa[i] * (g[i] - k1a[i] - (va[i] - ma[i]) * ia[i] * k2a[i]);
-            } else {
+        for (int u = 0; u < U; ++u) {
+            const int px = base + u * L.rows;
+            if (px < end) {
+                float da[8], db[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) d[i] = sa[i] * g[i];
+                for (int i = 0; i < 8; ++i) {
+                    float ub = 0.f, t = fmaf(va[u][i], sa[i], ta[i]);
+                    if (HAS_B) { ub = fmaf(vb[u][i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                    const float gg = g[u][i] * act_bwd_from_u(t, act);
+                    da[i] = fmaf(sa[i], gg, fmaf(Pa[i], va[u][i], Qa[i]));
+                    if (HAS_B) {
+                        const float gb = gg * act_bwd_from_u(ub, actb);
+                        db[i] = fmaf(sb[i], gb, fmaf(Pb[i], vb[u][i], Qb[i]));
+                    }
+                }
+                if (wa) {
+                    T* o = vptr_mut<T>(p.da, pix0 + px, c);
+                    if (p.acc_a) {
+                        float old[8];
+                        Vec8<T>::load(o, old);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) da[i] += old[i];
+                    }
+                    Vec8<T>::store(o, da);
+                }
+                if (wb) {
+                    T* o = vptr_mut<T>(p.db, pix0 + px, c);
+                    if (p.acc_b) {
+                        float old[8];
+                        Vec8<T>::load(o, old);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) db[i] += old[i];
+                    }
+                    Vec8<T>::store(o, db);
+                }
             }
-            T* o = vptr_mut<T>(p.da, pix0 + px, c);
-            if (p.acc_a) {
-                float old[8];
-                Vec8<T>::load(o, old);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) d[i] += old[i];
-            }
-            Vec8<T>::store(o, d);
-        }
-        if (has_b && p.db.ptr) {
-            float d[8], vb[8];
-            const bool need_b = p.mode_b == SEMB_AFF_BATCH || p.actb != SEMB_ACT_NONE;
-            if (need_b) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float gb = g[i];
-                if (p.actb != SEMB_ACT_NONE) gb *= act_bwd_from_y(act_fwd(fmaf(vb[i], sb[i], tb[i]), p.actb), p.actb);
-                if (p.mode_b == SEMB_AFF_BATCH) d[i] = sb[i] * (gb - k1b[i] - (vb[i] - mb[i]) * ib[i] * k2b[i]);
-                else d[i] = sb[i] * gb;
-            }
-            T* o = vptr_mut<T>(p.db, pix0 + px, c);
-            if (p.acc_b) {
-                float old[8];
-                Vec8<T>::load(o, old);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) d[i] += old[i];
-            }
-            Vec8<T>::store(o, d);
         }
     }
 }
@@ -299,7 +340,7 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const AffArgs p) {
 
 static int pick_ppb(int HW, int N, int C) {
     const int rows = 256 / (C / 8);
-    long long target_blocks = 148LL * 8;
+    long long target_blocks = 148LL * 12;
     int ppb = (int)cdivl((long long)HW * N, target_blocks);
     int min_ppb = rows * 4;
     if (ppb < min_ppb) ppb = min_ppb;
@@ -399,6 +440,31 @@ extern "C" int semb_norm_bwd_finalize(const float* sums, int32_t which, int32_t 
     return check_launch("norm_bwd_finalize");
 }
 
+
+// (activation, second-operand activation) combinations compiled statically; anything else takes the runtime path
+#define SEMB_AFF_DISPATCH(KERNEL, T, HASB, grid, smem, st, p)                                                       \
+    do {                                                                                                            \
+        if ((p).act == SEMB_ACT_NONE && (!(HASB) || (p).actb == SEMB_ACT_NONE))                                     \
+            KERNEL<T, HASB, SEMB_ACT_NONE, SEMB_ACT_NONE><<<grid, 256, smem, st>>>(p);                              \
+        else if ((p).act == SEMB_ACT_RELU && (!(HASB) || (p).actb == SEMB_ACT_NONE))                                \
+            KERNEL<T, HASB, SEMB_ACT_RELU, SEMB_ACT_NONE><<<grid, 256, smem, st>>>(p);                              \
+        else if ((p).act == SEMB_ACT_RELU && (p).actb == SEMB_ACT_RELU)                                             \
+            KERNEL<T, HASB, SEMB_ACT_RELU, SEMB_ACT_RELU><<<grid, 256, smem, st>>>(p);                              \
+        else                                                                                                        \
+            KERNEL<T, HASB, -1, -1><<<grid, 256, smem, st>>>(p);                                                    \
+    } while (0)
+
+#define SEMB_AFF_LAUNCH(KERNEL, dtype, has_b, grid, smem, st, p)                                                    \
+    do {                                                                                                            \
+        if ((dtype) == SEMB_BF16) {                                                                                 \
+            if (has_b) SEMB_AFF_DISPATCH(KERNEL, bf16, true, grid, smem, st, p);                                    \
+            else SEMB_AFF_DISPATCH(KERNEL, bf16, false, grid, smem, st, p);                                         \
+        } else {                                                                                                    \
+            if (has_b) SEMB_AFF_DISPATCH(KERNEL, float, true, grid, smem, st, p);                                   \
+            else SEMB_AFF_DISPATCH(KERNEL, float, false, grid, smem, st, p);                                        \
+        }                                                                                                           \
+    } while (0)
+
 extern "C" int semb_affine_act_fwd(const semb_affine_desc* d, const semb_tensor* a, const float* scale_a,
                                    const float* shift_a, const semb_tensor* b, const float* scale_b, const float* shift_b,
                                    const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
@@ -418,39 +484,41 @@ extern "C" int semb_affine_act_fwd(const semb_affine_desc* d, const semb_tensor*
     p.ppb = pick_ppb(d->HW, d->N, d->C);
     dim3 grid(cdiv(d->HW, p.ppb), d->N);
     const size_t smem = stats ? (size_t)(256 / (d->C / 8)) * 2 * d->C * sizeof(float) : 0;
-    if (d->dtype == SEMB_BF16) affine_act_fwd_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(p);
-    else affine_act_fwd_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(p);
+    cudaStream_t st = as_stream(stream);
+    SEMB_AFF_LAUNCH(affine_act_fwd_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_fwd");
 }
 
-extern "C" int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
-                                          const semb_tensor* a, const semb_tensor* b, const float* mean_a,
-                                          const float* invstd_a, const float* scale_b, const float* shift_b,
-                                          const float* mean_b, const float* invstd_b, float* sums,
+extern "C" int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* a,
+                                          const semb_tensor* b, const float* scale_a, const float* shift_a,
+                                          const float* mean_a, const float* invstd_a, const float* scale_b,
+                                          const float* shift_b, const float* mean_b, const float* invstd_b, float* sums,
                                           int32_t sums_nstride, int32_t sums_cstride, void* stream) {
     int rc = check_aff(d);
     if (rc) return rc;
-    SEMB_REQUIRE(view_ok(dy) && view_ok(a) && (!b || view_ok(b)) && (d->act == SEMB_ACT_NONE || view_ok(y)), SEMB_EALIGN,
-                 "affine bwd reduce: bad tensor view");
+    SEMB_REQUIRE(view_ok(dy) && view_ok(a) && (!b || view_ok(b)), SEMB_EALIGN, "affine bwd reduce: bad tensor view");
     SEMB_REQUIRE(sums, SEMB_ESHAPE, "affine bwd reduce: null sums");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_NONE || (scale_a && shift_a), SEMB_ESHAPE, "affine bwd reduce: missing scale/shift a");
     SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (mean_a && invstd_a), SEMB_ESHAPE, "affine bwd reduce: missing mean/invstd a");
+    SEMB_REQUIRE(!b || d->mode_b == SEMB_AFF_NONE || (scale_b && shift_b), SEMB_ESHAPE, "affine bwd reduce: missing scale/shift b");
     SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (mean_b && invstd_b), SEMB_ESHAPE, "affine bwd reduce: missing mean/invstd b");
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
-    p.a = mkview(a); p.b = mkview(b); p.y = mkview(y); p.dy = mkview(dy);
-    p.mean_a = mean_a; p.invstd_a = invstd_a; p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
+    p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy);
+    p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
+    p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
     p.stats = sums; p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
     p.ppb = pick_ppb(d->HW, d->N, d->C);
     dim3 grid(cdiv(d->HW, p.ppb), d->N);
-    const size_t smem = 4 * d->C * sizeof(float);
-    if (d->dtype == SEMB_BF16) affine_act_bwd_reduce_kernel<bf16><<<grid, 256, smem, as_stream(stream)>>>(p);
-    else affine_act_bwd_reduce_kernel<float><<<grid, 256, smem, as_stream(stream)>>>(p);
+    const size_t smem = (size_t)(256 / (d->C / 8)) * 4 * d->C * sizeof(float);
+    cudaStream_t st = as_stream(stream);
+    SEMB_AFF_LAUNCH(affine_act_bwd_reduce_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_bwd_reduce");
 }
 
-extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
-                                         const semb_tensor* a, const semb_tensor* b, const float* scale_a,
+extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* a,
+                                         const semb_tensor* b, const float* scale_a, const float* shift_a,
                                          const float* mean_a, const float* invstd_a, const float* c1_a, const float* c2_a,
                                          const float* scale_b, const float* shift_b, const float* mean_b,
                                          const float* invstd_b, const float* c1_b, const float* c2_b,
@@ -458,23 +526,25 @@ extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_t
                                          void* stream) {
     int rc = check_aff(d);
     if (rc) return rc;
-    SEMB_REQUIRE(view_ok(dy) && (d->act == SEMB_ACT_NONE || view_ok(y)), SEMB_EALIGN, "affine bwd apply: bad dy/y view");
-    SEMB_REQUIRE((!da || view_ok(da)) && (!db || view_ok(db)) && (!b || view_ok(b)), SEMB_EALIGN, "affine bwd apply: bad view");
-    SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (view_ok(a) && scale_a && mean_a && invstd_a && c1_a && c2_a), SEMB_ESHAPE,
+    SEMB_REQUIRE(view_ok(dy) && view_ok(a) && (!b || view_ok(b)), SEMB_EALIGN, "affine bwd apply: bad dy/a/b view");
+    SEMB_REQUIRE((!da || view_ok(da)) && (!db || view_ok(db)), SEMB_EALIGN, "affine bwd apply: bad gradient view");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_NONE || (scale_a && shift_a), SEMB_ESHAPE, "affine bwd apply: missing scale/shift a");
+    SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (mean_a && invstd_a && c1_a && c2_a), SEMB_ESHAPE,
                  "affine bwd apply: missing batch-norm terms for a");
-    SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (scale_b && shift_b && mean_b && invstd_b && c1_b && c2_b), SEMB_ESHAPE,
+    SEMB_REQUIRE(!b || d->mode_b == SEMB_AFF_NONE || (scale_b && shift_b), SEMB_ESHAPE, "affine bwd apply: missing scale/shift b");
+    SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (mean_b && invstd_b && c1_b && c2_b), SEMB_ESHAPE,
                  "affine bwd apply: missing batch-norm terms for b");
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
-    p.a = mkview(a); p.b = mkview(b); p.y = mkview(y); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
-    p.scale_a = scale_a; p.mean_a = mean_a; p.invstd_a = invstd_a; p.c1_a = c1_a; p.c2_a = c2_a;
+    p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
+    p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a; p.c1_a = c1_a; p.c2_a = c2_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b; p.c1_b = c1_b; p.c2_b = c2_b;
     p.acc_a = acc_a; p.acc_b = acc_b;
     p.ppb = pick_ppb(d->HW, d->N, d->C);
     dim3 grid(cdiv(d->HW, p.ppb), d->N);
-    if (d->dtype == SEMB_BF16) affine_act_bwd_apply_kernel<bf16><<<grid, 256, 0, as_stream(stream)>>>(p);
-    else affine_act_bwd_apply_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(p);
+    cudaStream_t st = as_stream(stream);
+    SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, 0, st, p);
     return check_launch("affine_act_bwd_apply");
 }
 

@@ -390,8 +390,12 @@ class ConvOp(Op):
         e = self.eng
         dbias = e.gptr(self.bias) if self.bias else None
         if not self.transposed:
-            L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w), dbias,
-                                            e.stream))
+            if self.use_tc and dbias is None:
+                L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w),
+                                                   e.stream))
+            else:
+                L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w), dbias,
+                                                e.stream))
             if self.x.requires_grad:
                 if self.use_tc and self.pk_bwd is not None:
                     L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_d), C.byref(self.y.g), self.pk_bwd["buf"].data_ptr(), None,
@@ -512,9 +516,10 @@ class AffineOp(Op):
             cs = owner.C
             ns = 0 if owner.groups == 1 else 4 * owner.C
             L.check(e.lib.semb_affine_act_bwd_reduce(
-                C.byref(d), C.byref(self.y.g), C.byref(self.y.t), C.byref(self.a.t), bt,
-                self._p(na, "mean", ca), self._p(na, "invstd", ca), self._p(nb, "scale", 0), self._p(nb, "shift", 0),
-                self._p(nb, "mean", 0), self._p(nb, "invstd", 0), sums, ns, cs, e.stream))
+                C.byref(d), C.byref(self.y.g), C.byref(self.a.t), bt,
+                self._p(na, "scale", ca), self._p(na, "shift", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca),
+                self._p(nb, "scale", 0), self._p(nb, "shift", 0), self._p(nb, "mean", 0), self._p(nb, "invstd", 0),
+                sums, ns, cs, e.stream))
             if red_a:
                 dg = e.gptr(na.gamma) + 4 * ca if na.gamma else None
                 db = e.gptr(na.beta) + 4 * ca
@@ -532,8 +537,9 @@ class AffineOp(Op):
         if da is None and dbv is None:
             return
         L.check(e.lib.semb_affine_act_bwd_apply(
-            C.byref(d), C.byref(self.y.g), C.byref(self.y.t), C.byref(self.a.t), bt,
-            self._p(na, "scale", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca), self._p(na, "c1", ca), self._p(na, "c2", ca),
+            C.byref(d), C.byref(self.y.g), C.byref(self.a.t), bt,
+            self._p(na, "scale", ca), self._p(na, "shift", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca),
+            self._p(na, "c1", ca), self._p(na, "c2", ca),
             self._p(nb, "scale", 0), self._p(nb, "shift", 0), self._p(nb, "mean", 0), self._p(nb, "invstd", 0),
             self._p(nb, "c1", 0), self._p(nb, "c2", 0), da, self.acc_a, dbv, self.acc_b, e.stream))
 

@@ -131,7 +131,7 @@ def run_reference(args):
 def profile_ops(inst, weighting, peaks, size, batch):
     """One eager fwd+bwd with CUDA events around every engine op; returns the per-op table and the dominant conv."""
     import sem_b200  # noqa: F401
-    from sem_b200.engine import ConvOp
+    from sem_b200.engine import ConvOp, AffineOp
     e = inst.eng
     recs = []
 
@@ -163,6 +163,12 @@ def profile_ops(inst, weighting, peaks, size, batch):
             row.update({"geom": f"{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.R} s{g.stride}{' T' if op.transposed else ''}",
                         "flops": flops_fwd * (1 if label == "fwd" else 2),
                         "bytes": (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz * (1 if label == "fwd" else 2)})
+        if isinstance(op, AffineOp):
+            esz = 2 if e.dtype_name == "bf16" else 4
+            hb = 1 if op.b is not None else 0
+            elems = op.n * op.hw * op.a.C
+            nt = (2 + hb) if label == "fwd" else (2 + hb) + (3 + 2 * hb)      # reduce reads dy,a[,b]; apply reads the same, writes da[,db]
+            row.update({"geom": f"C={op.a.C} hw={op.hw} two_operands={bool(hb)}", "bytes": elems * esz * nt})
         rows.append(row)
     return rows
 

@@ -123,6 +123,11 @@ int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void
                        const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                        int32_t accumulate, void* stream);
 
+/* Weight gradient of the same layers on tcgen05: D[co][ci] per tap, K = output pixels (split over CTAs), both
+ * operands read as MN-major UMMA operands from the NHWC channel-group planes; accumulates (+=) into the fp32
+ * HWIO gradient with coalesced reductions.  Same contract as semb_conv2d_wgrad without dbias. */
+int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* stream);
+
 /* ---- normalisation + activation (fused elementwise) --------------------------------------- */
 
 /* From moments to the affine that BatchNormalization / GroupNormalization applies.
@@ -162,15 +167,15 @@ int semb_affine_act_fwd(const semb_affine_desc* d,
                         const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                         void* stream);
 
-/* Backward of semb_affine_act_fwd, pass 1 of 2: with g = dy*act'(y), gb = g*actb'(B(b)) and
- * xhat = (x-mean)*invstd accumulates sums[0]=sum g, sums[1]=sum g*xhat_a, sums[2]=sum gb,
- * sums[3]=sum gb*xhat_b (each at k*cstride + c, plus n*nstride for per-sample mode); only operands in
- * SEMB_AFF_BATCH mode are reduced.  y is the saved forward output (needed when act != NONE). */
-int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
+/* Backward of semb_affine_act_fwd, pass 1 of 2.  The activation derivative is recomputed from the
+ * pre-activation u = A(a)+actb(B(b)) (same fp32 arithmetic as the forward), so the saved output is not re-read.
+ * With g = dy*act'(u), gb = g*actb'(B(b)) and xhat = (x-mean)*invstd accumulates sums[0]=sum g,
+ * sums[1]=sum g*xhat_a, sums[2]=sum gb, sums[3]=sum gb*xhat_b (each at k*cstride + c, plus n*nstride for
+ * per-sample mode); only operands in SEMB_AFF_BATCH mode are reduced. */
+int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_tensor* dy,
                                const semb_tensor* a, const semb_tensor* b,
-                               const float* mean_a, const float* invstd_a,
-                               const float* scale_b, const float* shift_b,
-                               const float* mean_b, const float* invstd_b,
+                               const float* scale_a, const float* shift_a, const float* mean_a, const float* invstd_a,
+                               const float* scale_b, const float* shift_b, const float* mean_b, const float* invstd_b,
                                float* sums, int32_t sums_nstride, int32_t sums_cstride, void* stream);
 
 /* C-length finalize of the BN/IN backward: for operand `which` (0=a, 1=b) turns the sums into
@@ -181,13 +186,13 @@ int semb_norm_bwd_finalize(const float* sums, int32_t which, int32_t groups, int
                            float* c1, float* c2, float* dgamma, float* dbeta, void* stream);
 
 /* pass 2 of 2: da (+)= scale_a*(g - c1_a - xhat_a*c2_a)   [SEMB_AFF_BATCH]
- *                     = scale_a*g [PLAIN] = g [NONE];  same for db.  da/db may be NULL. */
-int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* y,
+ *                     = scale_a*g [PLAIN] = g [NONE];  same for db with gb.  da/db may be NULL. */
+int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy,
                               const semb_tensor* a, const semb_tensor* b,
-                              const float* scale_a, const float* mean_a, const float* invstd_a,
+                              const float* scale_a, const float* shift_a, const float* mean_a, const float* invstd_a,
                               const float* c1_a, const float* c2_a,
-                              const float* scale_b, const float* shift_b, const float* mean_b,
-                              const float* invstd_b, const float* c1_b, const float* c2_b,
+                              const float* scale_b, const float* shift_b, const float* mean_b, const float* invstd_b,
+                              const float* c1_b, const float* c2_b,
                               const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b,
                               void* stream);
 

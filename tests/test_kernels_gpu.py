@@ -250,7 +250,8 @@ def test_norm_affine_fwd_bwd(dtype, per_sample):
     dyv = U.view(dyd)
     # the saved forward output must be the one the kernel produced
     sums = torch.zeros(groups * 4 * cp, device="cuda")
-    L.check(lib.semb_affine_act_bwd_reduce(C.byref(d), C.byref(dyv), C.byref(yv), C.byref(av), C.byref(bv),
+    L.check(lib.semb_affine_act_bwd_reduce(C.byref(d), C.byref(dyv), C.byref(av), C.byref(bv),
+                                           arrs["a"]["scale"].data_ptr(), arrs["a"]["shift"].data_ptr(),
                                            arrs["a"]["mean"].data_ptr(), arrs["a"]["invstd"].data_ptr(),
                                            arrs["b"]["scale"].data_ptr(), arrs["b"]["shift"].data_ptr(),
                                            arrs["b"]["mean"].data_ptr(), arrs["b"]["invstd"].data_ptr(),
@@ -264,8 +265,9 @@ def test_norm_affine_fwd_bwd(dtype, per_sample):
     dad, dbd = torch.zeros_like(ad), torch.zeros_like(bd)
     dav, dbv = U.view(dad), U.view(dbd)
     A, B = arrs["a"], arrs["b"]
-    L.check(lib.semb_affine_act_bwd_apply(C.byref(d), C.byref(dyv), C.byref(yv), C.byref(av), C.byref(bv),
-                                          A["scale"].data_ptr(), A["mean"].data_ptr(), A["invstd"].data_ptr(), A["c1"].data_ptr(), A["c2"].data_ptr(),
+    L.check(lib.semb_affine_act_bwd_apply(C.byref(d), C.byref(dyv), C.byref(av), C.byref(bv),
+                                          A["scale"].data_ptr(), A["shift"].data_ptr(), A["mean"].data_ptr(), A["invstd"].data_ptr(),
+                                          A["c1"].data_ptr(), A["c2"].data_ptr(),
                                           B["scale"].data_ptr(), B["shift"].data_ptr(), B["mean"].data_ptr(), B["invstd"].data_ptr(),
                                           B["c1"].data_ptr(), B["c2"].data_ptr(), C.byref(dav), 0, C.byref(dbv), 0, U.stream()))
     torch.cuda.synchronize()
@@ -498,3 +500,36 @@ def test_conv_tc_fwd_and_dgrad(case):
     L.check(lib.semb_conv2d_fwd_tc(C.byref(gd), C.byref(dyv), wpf.data_ptr(), None, C.byref(dxv), None, 0, 0, 1, U.stream()))
     torch.cuda.synchronize()
     assert U.rel_err(dxd[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_wgrad(case):
+    """tcgen05 weight gradient (MN-major operands, split-K over pixel tiles) vs autograd on bf16-rounded x, dy."""
+    n, h, w_, cin, cout, k, pad_mode = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(13)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wt = torch.randn(k, k, cin, cout, generator=g) * 0.1
+    p = (k - 1) // 2
+    wr = wt.clone().requires_grad_(True)
+    if pad_mode == "reflect":
+        y_ref = OL.conv2d(OL.reflection_pad(x, 2 * p, 2 * p), wr, None, 1, "valid")
+    else:
+        y_ref = OL.conv2d(x, wr, None, 1, "same")
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    cpi, cpo = U.pad8(cin), U.pad8(cout)
+    pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
+    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, pm, L.BF16)
+    xd = U.to_dev(x, "bf16", pitch=cpi + 8, coff=8)
+    dyd = U.to_dev(dy, "bf16", pitch=cpo + 8, coff=0)
+    dw = torch.ones((k, k, cpi, cpo), device="cuda")          # accumulates on top of existing content
+    xv, dyv = U.view(xd, 8, cpi), U.view(dyd, 0, cpo)
+    L.check(lib.semb_conv2d_wgrad_tc(C.byref(geom), C.byref(xv), C.byref(dyv), dw.data_ptr(), U.stream()))
+    torch.cuda.synchronize()
+    got = dw.cpu() - 1.0
+    assert U.rel_err(got[:, :, :cin, :cout], wr.grad) < 1e-4
+    if cpi > cin:
+        assert float(got[:, :, cin:, :].abs().max()) == 0
+    if cpo > cout:
+        assert float(got[:, :, :, cout:].abs().max()) == 0
