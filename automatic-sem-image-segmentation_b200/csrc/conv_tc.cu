@@ -276,28 +276,39 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const TcArgs a) {
 // dW[tap][ci][co] = sum_pixels x[pixel+tap][ci] * dy[pixel][co]  as  D[M=co][N=ci] += A[co][k] * B[ci][k], k = pixels.
 // Both operands are read straight from their NHWC channel-group planes as MN-MAJOR UMMA operands (the same
 // shared-memory image the forward kernel uses as K-major): 8 consecutive pixels of a row are the 8 K-rows of a
-// core matrix, LBO = next pixel row, SBO = next channel-group plane.  Each tap owns a block of TMEM columns;
-// a CTA walks many pixel tiles (split-K over pixels), accumulating in TMEM, and flushes once with coalesced
-// fp32 reductions into the HWIO gradient.
-struct WgPlan { int NCH, nchunks, tpp, tapgroups, mtiles, cols, splits; };
+// core matrix, LBO = next pixel row, SBO = next channel-group plane.  Each tap owns a block of TMEM columns.
+//
+// Persistent, warp-specialised: 4 producer warps stream (dy tile, x halo tile) pairs through a STAGES-deep
+// cp.async ring; one elected thread of a 5th warp issues the tcgen05.mma's (K = 16 pixels each) and releases
+// ring slots with tcgen05.commit; the accumulator stays in TMEM over ALL pixel tiles of the CTA (split-K over
+// pixels) and is flushed once with coalesced fp32 reductions into the HWIO gradient.
+constexpr int WG_PRODUCERS = 128;
+constexpr int WG_THREADS = WG_PRODUCERS + 32;
 
-static inline WgPlan wg_plan(int Cin, int Cout, int taps, long long total_tiles) {
+struct WgPlan { int NCH, nchunks, tpp, tapgroups, mtiles, cols, splits, stage_bytes, planes_a_max, stages, smem_bytes; };
+
+static inline WgPlan wg_plan(int Cin, int Cout, int taps, long long total_tiles, int plane_a, int plane_b) {
     WgPlan p;
     const int cin16 = (Cin + 15) / 16 * 16;
-    p.NCH = cin16 < 256 ? cin16 : 256;
+    p.NCH = cin16 < 128 ? cin16 : 128;          // keeps a stage (dy tile + x halo) below 80 KB
     p.nchunks = (cin16 + p.NCH - 1) / p.NCH;
-    // <= 128 TMEM columns per CTA so that four CTAs share an SM and hide each other's load / MMA latency
-    int tpp = 128 / p.NCH;
-    if (tpp < 1) tpp = 1;
+    int tpp = 512 / p.NCH;
     if (tpp > taps) tpp = taps;
     p.tpp = tpp;
     p.tapgroups = (taps + p.tpp - 1) / p.tpp;
     p.mtiles = (Cout + 127) / 128;
-    int c = p.tpp * p.NCH;
+    const int c = p.tpp * p.NCH;
     p.cols = c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512)));
+    p.planes_a_max = Cout >= 128 ? 16 : (Cout + 7) / 8;
+    p.stage_bytes = p.planes_a_max * plane_a + (p.NCH / 8) * plane_b;
+    // the M=128 MMA always reads 16 A planes; planes beyond Cout are garbage rows that are never flushed, but the
+    // reads must stay inside the allocation
+    const int slack = 16 * plane_a > p.stage_bytes ? 16 * plane_a - p.stage_bytes : 0;
+    p.stages = (size_t)p.stage_bytes * 3 + slack <= 200 * 1024 ? 3 : 2;
+    p.smem_bytes = p.stage_bytes * p.stages + slack;
     const int work = p.mtiles * p.tapgroups * p.nchunks;
-    const int per_sm = 512 / p.cols > 6 ? 6 : 512 / p.cols;
-    long long s = (148LL * per_sm + work - 1) / work;
+    const int per_sm = (p.cols <= 256 && p.smem_bytes <= 100 * 1024) ? 2 : 1;
+    long long s = (148LL * per_sm) / work;
     if (s > total_tiles) s = total_tiles;
     if (s < 1) s = 1;
     p.splits = (int)s;
@@ -314,12 +325,21 @@ struct WgArgs {
     int plane_a, plane_b, halo_h, halo_w;
 };
 
-template <int COLS>
-__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const WgArgs a) {
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int COLS, int WG_STAGES>
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* As = smem;                               // dy tile : [16 co-groups][128 pixels][16 B]
-    uint8_t* Bs = smem + 16 * a.plane_a;              // x halo  : [NCH/8 ci-groups][halo pixels][16 B]
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], done_bar;
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -335,80 +355,106 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const WgArgs a) {
     const int planes_a = min(16, (a.Cout - co0 + 7) / 8);
     const int planes_b = min(NCH / 8, (a.Cin - ci0 + 7) / 8);
     const int halo_pix = a.halo_h * a.halo_w;
+    const int b_off = a.p.planes_a_max * a.plane_a;                 // B planes follow the A planes inside a stage
+    const int ntiles = (a.total_tiles - (int)blockIdx.x + a.p.splits - 1) / a.p.splits;   // tiles of this CTA
 
-    if (warp == 0) tmem_alloc<COLS>(smem_u32(&tmem_slot));
-    if (tid == 0) mbar_init(smem_u32(&mbar), 1);
-    // channel-group planes that are never loaded must still be finite zeros for the N side (they feed valid rows)
-    for (int idx = tid; idx < (NCH / 8 - planes_b) * halo_pix; idx += TC_THREADS) {
-        const int k8 = planes_b + idx / halo_pix, pix = idx % halo_pix;
-        *reinterpret_cast<uint4*>(Bs + (size_t)k8 * a.plane_b + pix * 16) = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 4) tmem_alloc<COLS>(smem_u32(&tmem_slot));
+    if (tid == 0) {
+        for (int i = 0; i < WG_STAGES; ++i) { mbar_init(smem_u32(&full_bar[i]), WG_PRODUCERS); mbar_init(smem_u32(&empty_bar[i]), 1); }
+        mbar_init(smem_u32(&done_bar), 1);
     }
+    // N-side planes beyond Cin are never loaded: keep them finite (they only feed columns that are never flushed)
+    for (int st = 0; st < WG_STAGES; ++st)
+        for (int idx = tid; idx < (NCH / 8 - planes_b) * halo_pix; idx += WG_THREADS) {
+            const int k8 = planes_b + idx / halo_pix, pix = idx % halo_pix;
+            *reinterpret_cast<uint4*>(smem + (size_t)st * a.p.stage_bytes + b_off + (size_t)k8 * a.plane_b + pix * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = instr_desc(128, NCH, 1, 1);
-    uint32_t phase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < a.total_tiles; t += a.p.splits, ++it) {
-        const int n = t / (a.tiles_x * a.tiles_y);
-        const int trem = t % (a.tiles_x * a.tiles_y);
-        const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
-        // ---- A: dy tile (no halo)
-        for (int idx = tid; idx < planes_a * 128; idx += TC_THREADS) {
-            const int k8 = idx % planes_a, pix = idx / planes_a;
-            const int oy = y0 + pix / TILE_W, ox = x0 + pix % TILE_W;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (oy < a.OH && ox < a.OW)
-                v = *reinterpret_cast<const uint4*>(a.dy + ((size_t)(n * a.OH + oy) * a.OW + ox) * a.dy_pitch + a.dy_coff + co0 + k8 * 8);
-            *reinterpret_cast<uint4*>(As + (size_t)k8 * a.plane_a + pix * 16) = v;
-        }
-        // ---- B: x halo tile
-        for (int idx = tid; idx < planes_b * halo_pix; idx += TC_THREADS) {
-            const int k8 = idx % planes_b, pix = idx / planes_b;
-            const int hy = pix / a.halo_w, hx = pix % a.halo_w;
-            int iy = y0 - a.pad_t + hy, ix = x0 - a.pad_l + hx;
-            if (a.pad_mode == SEMB_PAD_REFLECT) {
-                if (iy > -a.H && iy < 2 * a.H - 1) iy = reflect_index(iy, a.H);
-                if (ix > -a.W && ix < 2 * a.W - 1) ix = reflect_index(ix, a.W);
+    const uint32_t smem_base = smem_u32(smem);
+
+    if (warp < 4) {
+        // ===================== producers =====================
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it % WG_STAGES;
+            mbar_wait(smem_u32(&empty_bar[stage]), ((it / WG_STAGES) & 1) ^ 1);
+            const int t = blockIdx.x + it * a.p.splits;
+            const int n = t / (a.tiles_x * a.tiles_y);
+            const int trem = t % (a.tiles_x * a.tiles_y);
+            const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
+            const uint32_t sbase = smem_base + stage * a.p.stage_bytes;
+            {   // A: dy tile, one pixel per producer thread, all of its channel-group planes
+                const int oy = y0 + tid / TILE_W, ox = x0 + tid % TILE_W;
+                const bool v = oy < a.OH && ox < a.OW;
+                const bf16* src = a.dy + ((size_t)(n * a.OH + (v ? oy : 0)) * a.OW + (v ? ox : 0)) * a.dy_pitch + a.dy_coff + co0;
+                const uint32_t dst = sbase + tid * 16;
+                for (int k8 = 0; k8 < planes_a; ++k8) cp_async16(dst + k8 * a.plane_a, src + k8 * 8, v);
             }
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-                v = *reinterpret_cast<const uint4*>(a.x + ((size_t)(n * a.H + iy) * a.W + ix) * a.x_pitch + a.x_coff + ci0 + k8 * 8);
-            *reinterpret_cast<uint4*>(Bs + (size_t)k8 * a.plane_b + pix * 16) = v;
+            for (int pix = tid; pix < halo_pix; pix += WG_PRODUCERS) {   // B: x halo tile
+                const int hy = pix / a.halo_w, hx = pix % a.halo_w;
+                int iy = y0 - a.pad_t + hy, ix = x0 - a.pad_l + hx;
+                if (a.pad_mode == SEMB_PAD_REFLECT) {
+                    if (iy > -a.H && iy < 2 * a.H - 1) iy = reflect_index(iy, a.H);
+                    if (ix > -a.W && ix < 2 * a.W - 1) ix = reflect_index(ix, a.W);
+                }
+                const bool v = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+                const bf16* src = a.x + ((size_t)(n * a.H + (v ? iy : 0)) * a.W + (v ? ix : 0)) * a.x_pitch + a.x_coff + ci0;
+                const uint32_t dst = sbase + b_off + pix * 16;
+                for (int k8 = 0; k8 < planes_b; ++k8) cp_async16(dst + k8 * a.plane_b, src + k8 * 8, v);
+            }
+            cp_async_commit();
+            if (it >= WG_STAGES - 1) {          // the group issued WG_STAGES-1 iterations ago has landed
+                cp_async_wait<WG_STAGES - 1>();
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&full_bar[(it - (WG_STAGES - 1)) % WG_STAGES]));
+            }
         }
+        cp_async_wait<0>();
         fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
+        for (int it = max(0, ntiles - (WG_STAGES - 1)); it < ntiles; ++it) mbar_arrive(smem_u32(&full_bar[it % WG_STAGES]));
+    } else if (lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = instr_desc(128, NCH, 1, 1);
+        const uint64_t ad0 = smem_desc(smem_base, TILE_W * 16, a.plane_a);
+        const uint64_t bd0 = smem_desc(smem_base + b_off, a.halo_w * 16, a.plane_b);
+        for (int it = 0; it < ntiles; ++it) {
+            const int stage = it % WG_STAGES;
+            mbar_wait(smem_u32(&full_bar[stage]), (it / WG_STAGES) & 1);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
+            const uint32_t soff = (uint32_t)(stage * a.p.stage_bytes) >> 4;
             for (int tl = 0; tl < ntaps; ++tl) {
                 const int tap = tap0 + tl, r = tap / a.S, s = tap % a.S;
+#pragma unroll
                 for (int ks = 0; ks < TILE_H / 2; ++ks) {       // 16 pixels (two rows of 8) per MMA
-                    const uint64_t ad = smem_desc(a_base + ks * 2 * TILE_W * 16, TILE_W * 16, a.plane_a);
-                    const uint64_t bd = smem_desc(b_base + ((2 * ks + r) * a.halo_w + s) * 16, a.halo_w * 16, a.plane_b);
+                    const uint64_t ad = ad0 + soff + ks * (2 * TILE_W);
+                    const uint64_t bd = bd0 + soff + ((2 * ks + r) * a.halo_w + s);
                     umma_bf16(tmem + tl * NCH, ad, bd, idesc, (it | ks) != 0);
                 }
             }
-            umma_commit(smem_u32(&mbar));
+            umma_commit(smem_u32(&empty_bar[stage]));
         }
-        mbar_wait(smem_u32(&mbar), phase);
-        phase ^= 1;
+        umma_commit(smem_u32(&done_bar));
     }
-    tc_fence_after();
     // ---- flush: TMEM lane = co, columns = [tap][ci]; lanes of a warp hit consecutive co -> coalesced reductions
-    if (it > 0) {
-        const int co = co0 + warp * 32 + lane;
-        for (int tl = 0; tl < ntaps; ++tl) {
-            const int tap = tap0 + tl;
-            for (int g = 0; g < NCH / 8; ++g) {
-                float v[8];
-                tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + tl * NCH + g * 8, v);
-                if (co < a.Cout) {
+    if (warp < 4) {
+        mbar_wait(smem_u32(&done_bar), 0);
+        tc_fence_after();
+        if (ntiles > 0) {
+            const int co = co0 + warp * 32 + lane;
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const int tap = tap0 + tl;
+                for (int g = 0; g < NCH / 8; ++g) {
+                    float v[8];
+                    tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + tl * NCH + g * 8, v);
+                    if (co < a.Cout) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int ci = ci0 + g * 8 + i;
-                        if (ci < a.Cin) atomicAdd(a.dw + ((size_t)tap * a.Cin + ci) * a.Cout + co, v[i]);
+                        for (int i = 0; i < 8; ++i) {
+                            const int ci = ci0 + g * 8 + i;
+                            if (ci < a.Cin) atomicAdd(a.dw + ((size_t)tap * a.Cin + ci) * a.Cout + co, v[i]);
+                        }
                     }
                 }
             }
@@ -416,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const WgArgs a) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<COLS>(tmem);
+    if (warp == 4) tmem_dealloc<COLS>(tmem);
 }
 
 static size_t tc_smem_bytes(const TcPlan& p, int taps, int plane_bytes) {
@@ -500,17 +546,22 @@ extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* 
     a.dw = dw;
     a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
     a.total_tiles = g->N * a.tiles_x * a.tiles_y;
-    a.p = wg_plan(g->Cin, g->Cout, g->R * g->S, a.total_tiles);
     a.halo_h = TILE_H + g->R - 1; a.halo_w = TILE_W + g->S - 1;
     a.plane_a = TILE_H * TILE_W * 16 + 16;
     a.plane_b = a.halo_h * a.halo_w * 16 + 16;
-    const size_t smem = (size_t)16 * a.plane_a + (size_t)(a.p.NCH / 8) * a.plane_b;
-    SEMB_REQUIRE(smem <= 200 * 1024, SEMB_EWORKSPACE, "wgrad_tc: %zu bytes of shared memory needed", smem);
+    a.p = wg_plan(g->Cin, g->Cout, g->R * g->S, a.total_tiles, a.plane_a, a.plane_b);
+    const size_t smem = (size_t)a.p.smem_bytes;
+    SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "wgrad_tc: %zu bytes of shared memory needed", smem);
     dim3 grid(a.p.splits, a.p.mtiles * a.p.tapgroups * a.p.nchunks);
     cudaError_t e = cudaSuccess;
 #define SEMB_WG_LAUNCH(COLS)                                                                                          \
-    e = cudaFuncSetAttribute(wgrad_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    if (e == cudaSuccess) wgrad_tc_kernel<COLS><<<grid, TC_THREADS, smem, as_stream(stream)>>>(a);
+    if (a.p.stages == 3) {                                                                                            \
+        e = cudaFuncSetAttribute(wgrad_tc_kernel<COLS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e == cudaSuccess) wgrad_tc_kernel<COLS, 3><<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);             \
+    } else {                                                                                                          \
+        e = cudaFuncSetAttribute(wgrad_tc_kernel<COLS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (e == cudaSuccess) wgrad_tc_kernel<COLS, 2><<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);             \
+    }
     switch (a.p.cols) {
         case 32: SEMB_WG_LAUNCH(32) break;
         case 64: SEMB_WG_LAUNCH(64) break;
