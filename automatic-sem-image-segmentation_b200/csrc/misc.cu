@@ -259,6 +259,34 @@ __global__ void cast_out_kernel(PView src, float* __restrict__ dst, int dst_C, l
     }
 }
 
+
+// ---- depth-to-space for Conv2DTranspose(2x2, stride 2) expressed as a 1x1 conv with 4*C outputs ------------------
+// dir 0: dst[n,2y+r,2x+s,c] = src[n,y,x,(2r+s)*C+c] + bias[c]        dir 1: src[n,y,x,(2r+s)*C+c] = dst[n,2y+r,2x+s,c]
+template <typename T>
+__global__ void pixel_shuffle2_kernel(PView src, PView dst, int N, int H, int W, int C8, const float* __restrict__ bias, int dir) {
+    const long long total = (long long)N * H * W * 4 * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        long long t = i / C8;
+        const int q = (int)(t % 4); t /= 4;
+        const int x = (int)(t % W), y = (int)((t / W) % H), n = (int)(t / ((long long)W * H));
+        const size_t sp = ((size_t)n * H + y) * W + x;
+        const size_t dp = ((size_t)n * 2 * H + 2 * y + (q >> 1)) * (2 * W) + 2 * x + (q & 1);
+        float v[8];
+        if (dir == 0) {
+            Vec8<T>::load(at<T>(src, sp, q * C8 * 8 + c), v);
+            if (bias) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += bias[c + k];
+            }
+            Vec8<T>::store(at<T>(dst, dp, c), v);
+        } else {
+            Vec8<T>::load(at<T>(dst, dp, c), v);
+            Vec8<T>::store(at<T>(src, sp, q * C8 * 8 + c), v);
+        }
+    }
+}
+
 static inline int grid_for(long long total, int block = 256) {
     long long b = cdivl(total, block);
     const long long cap = 148LL * 16;
@@ -364,4 +392,15 @@ extern "C" int semb_cast_out(const semb_tensor* src, float* dst, int32_t dst_C, 
     if (dtype == SEMB_BF16) cast_out_kernel<bf16><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(pv(src), dst, dst_C, n_pixels, C8);
     else cast_out_kernel<float><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(pv(src), dst, dst_C, n_pixels, C8);
     return check_launch("cast_out");
+}
+
+extern "C" int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
+                                   const float* bias, int32_t dir, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(src) && view_ok(dst) && src->C == 4 * dst->C, SEMB_ESHAPE, "pixel_shuffle2: src must have 4x the channels of dst");
+    SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && (dir == 0 || dir == 1), SEMB_ESHAPE, "pixel_shuffle2: bad geometry");
+    const int C8 = dst->C / 8;
+    const long long total = (long long)N * H * W * 4 * C8;
+    if (dtype == SEMB_BF16) pixel_shuffle2_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, C8, bias, dir);
+    else pixel_shuffle2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, C8, bias, dir);
+    return check_launch("pixel_shuffle2");
 }

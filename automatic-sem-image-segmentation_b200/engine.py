@@ -133,14 +133,19 @@ class ParamSpec:
     """One Keras variable: logical shape + how its channel axes map into the physical tensor."""
 
     def __init__(self, name: str, kind: str, logical_shape, phys_shape, axis_maps: Dict[int, np.ndarray], trainable: bool,
-                 init: str = "zeros", fans: Tuple[int, int] = (1, 1)):
+                 init: str = "zeros", fans: Tuple[int, int] = (1, 1), to_phys_fn=None, to_logical_fn=None):
         self.name, self.kind = name, kind
         self.logical_shape, self.phys_shape = tuple(logical_shape), tuple(phys_shape)
         self.axis_maps, self.trainable, self.init, self.fans = axis_maps, trainable, init, fans
+        self.to_phys_fn, self.to_logical_fn = to_phys_fn, to_logical_fn
 
     def to_phys(self, arr: np.ndarray) -> np.ndarray:
         arr = np.asarray(arr, dtype=np.float32)
         assert tuple(arr.shape) == self.logical_shape, (self.name, arr.shape, self.logical_shape)
+        if self.to_phys_fn is not None:
+            out = np.asarray(self.to_phys_fn(arr), dtype=np.float32)
+            assert tuple(out.shape) == self.phys_shape, (self.name, out.shape, self.phys_shape)
+            return out
         out = np.zeros(self.phys_shape, dtype=np.float32)
         idx = [np.arange(s) for s in self.logical_shape]
         for ax, m in self.axis_maps.items():
@@ -149,6 +154,8 @@ class ParamSpec:
         return out
 
     def to_logical(self, phys: np.ndarray) -> np.ndarray:
+        if self.to_logical_fn is not None:
+            return np.ascontiguousarray(self.to_logical_fn(phys.reshape(self.phys_shape)))
         idx = [np.arange(s) for s in self.logical_shape]
         for ax, m in self.axis_maps.items():
             idx[ax] = m
@@ -586,3 +593,25 @@ class PadCropOp(Op):
         m = 3 if self.mode == "reflect" else 2
         L.check(e.lib.semb_pad_crop(C.byref(self.y.g), C.byref(self.x.g), e.N, self.hw_out[0], self.hw_out[1], self.hw_in[0],
                                     self.hw_in[1], self.top, self.left, m, e.dtype, self.acc, e.stream))
+
+
+class ShuffleOp(Op):
+    """Depth-to-space half of Conv2DTranspose(2x2, stride 2): y4 (N,H,W,4C) -> out (N,2H,2W,C) + bias."""
+
+    def __init__(self, eng: Engine, y4: View, out: View, h: int, w: int, bias: Optional[str]):
+        self.eng, self.y4, self.out, self.h, self.w, self.bias = eng, y4, out, h, w, bias
+
+    def plan_backward(self):
+        acc = plan_grad_write(self.y4)
+        assert acc == 0
+
+    def fwd(self, training: bool):
+        e = self.eng
+        L.check(e.lib.semb_pixel_shuffle2(C.byref(self.y4.t), C.byref(self.out.t), e.N, self.h, self.w,
+                                          e.params.ptr(self.bias) if self.bias else None, 0, e.dtype, e.stream))
+
+    def bwd(self):
+        e = self.eng
+        L.check(e.lib.semb_pixel_shuffle2(C.byref(self.y4.g), C.byref(self.out.g), e.N, self.h, self.w, None, 1, e.dtype, e.stream))
+        if self.bias:
+            L.check(e.lib.semb_channel_sum(C.byref(self.out.g), e.N, 4 * self.h * self.w, e.gptr(self.bias), e.dtype, e.stream))

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import _lib as L
-from .engine import (AffineOp, Buf, ConvOp, Engine, Layout, NormOp, PadCropOp, ParamSpec, PoolOp, View, pad8)
+from .engine import (AffineOp, Buf, ConvOp, Engine, Layout, NormOp, PadCropOp, ParamSpec, PoolOp, ShuffleOp, View, pad8)
 
 BN_MOMENTUM = 0.99
 BN_EPS = 1e-3
@@ -221,14 +221,37 @@ class UNetBuilder:
         lay = Layout.simple(filters)
         base = f"conv2d_transpose_{self.nct}"
         wname, bname = base + "/kernel", base + "/bias"
-        self._add(ParamSpec(wname, "convT_kernel", (2, 2, filters, x.layout.logical), (2, 2, lay.phys, x.layout.phys),
-                            {2: lay.index_map(), 3: x.layout.index_map()}, True, "glorot",
-                            (4 * filters, 4 * x.layout.logical)))
+        # The Keras kernel (kh,kw,Cout,Cin) is stored as the HWIO kernel of a 1x1 conv with 4*Cout outputs, one block
+        # of Cout per kernel position: phys[0,0,ci,(2r+s)*Cout_p+co] = keras[r,s,co,ci].  The transposed conv is then
+        # that 1x1 conv (tensor cores) followed by a depth-to-space pass that writes into the skip-concat buffer.
+        cin_l, cin_p, co_p = x.layout.logical, x.layout.phys, lay.phys
+        imap, omap = x.layout.index_map(), lay.index_map()
+
+        def to_phys(arr, cin_p=cin_p, co_p=co_p, imap=imap, omap=omap):
+            out = np.zeros((1, 1, cin_p, 4 * co_p), dtype=np.float32)
+            for r in range(2):
+                for s_ in range(2):
+                    blk = out[0, 0, :, (2 * r + s_) * co_p:(2 * r + s_ + 1) * co_p]
+                    blk[np.ix_(imap, omap)] = arr[r, s_].T            # (Cout,Cin) -> (Cin,Cout)
+            return out
+
+        def to_logical(phys, co_p=co_p, imap=imap, omap=omap, filters=filters, cin_l=cin_l):
+            out = np.zeros((2, 2, filters, cin_l), dtype=np.float32)
+            for r in range(2):
+                for s_ in range(2):
+                    blk = phys[0, 0, :, (2 * r + s_) * co_p:(2 * r + s_ + 1) * co_p]
+                    out[r, s_] = blk[np.ix_(imap, omap)].T
+            return out
+
+        self._add(ParamSpec(wname, "convT_kernel", (2, 2, filters, cin_l), (1, 1, cin_p, 4 * co_p), {}, True, "glorot",
+                            (4 * filters, 4 * cin_l), to_phys_fn=to_phys, to_logical_fn=to_logical))
         self._add(ParamSpec(bname, "convT_bias", (filters,), (lay.phys,), {0: lay.index_map()}, True, "zeros"))
         kct = self.kg.layer(base, [x.klayer], [wname, bname])
         kcat = self.kg.layer("concatenate", [kct, skip.klayer])
         up_view = skip_buf.view(0, lay.phys)
-        e.add_op(ConvOp(e, x.view, up_view, (x.h, x.w), (2 * x.h, 2 * x.w), wname, bname, 2, 2, (0, 0), L.PAD_ZERO, True))
+        y4 = e.new_buf(x.h, x.w, 4 * co_p, name + "_y4")
+        e.add_op(ConvOp(e, x.view, y4.view(), (x.h, x.w), (x.h, x.w), wname, None, 1, 1, (0, 0), L.PAD_ZERO, False))
+        e.add_op(ShuffleOp(e, y4.view(), up_view, x.h, x.w, bname))
         return T(skip_buf.view(), 2 * x.h, 2 * x.w, Layout.concat(lay, skip.layout), kcat)
 
     def _build(self, in_channels: int):

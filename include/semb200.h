@@ -217,6 +217,13 @@ int semb_pad_crop(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t
                   int32_t OH, int32_t OW, int32_t top, int32_t left, int32_t mode, int32_t dtype,
                   int32_t accumulate, void* stream);
 
+/* Conv2DTranspose(2x2, stride 2) (UNet_Segmentation.py:542-551) is computed as a 1x1 conv with 4*C outputs
+ * (one block of C per kernel position) followed by this depth-to-space pass:
+ * dir 0: dst[n,2y+r,2x+s,c] = src[n,y,x,(2r+s)*C+c] + bias[c]  (bias may be NULL);  dir 1: the inverse gather (its gradient).
+ * (H,W) is the size of src; dst is (2H,2W) and may be a channel slice of the skip-concat buffer. */
+int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
+                        const float* bias, int32_t dir, int32_t dtype, void* stream);
+
 /* ---- losses ------------------------------------------------------------------------------ */
 
 /* weighted_bce (UNet_Segmentation.py:379-384) + the 'mae' and 'acc' metrics (:395) + d(loss)/d(p).
