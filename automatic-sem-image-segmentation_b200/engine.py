@@ -91,6 +91,7 @@ class Buf:
         self.data = torch.zeros((n, h, w, pitch), dtype=eng.tdtype, device=eng.device)
         self._grad = None
         self.grad_cover: List[Tuple[int, int]] = []  # channel intervals already written in this backward plan
+        self.force_acc = False   # gradient buffer shared between engines: always accumulate, the owner zeroes it
 
     def grad_tensor(self) -> torch.Tensor:
         if self._grad is None:
@@ -166,7 +167,7 @@ class Engine:
     """Owns buffers, parameters, scratch and the op list of ONE network instance."""
 
     def __init__(self, n: int, dtype: str = "bf16", device: Optional[torch.device] = None, dry: bool = False,
-                 use_tc: bool = True):
+                 use_tc: bool = True, share: Optional["Engine"] = None):
         # dry=True builds the op list / parameter maps on the CPU for host-logic tests; nothing can execute.
         self.dry = dry
         if not dry:
@@ -192,6 +193,13 @@ class Engine:
         self.tc_enabled = bool(use_tc) and dtype == "bf16"
         self.tc_packs: List[dict] = []
         self._pack_dirty = True
+        # weight sharing between towers of the same network (CycleGAN applies each generator three times per step):
+        # a sharing engine has its own buffers / ops / scratch but uses the root's parameters, gradients and packs
+        self.share = share
+        if share is not None:
+            assert share.finalized and share.dtype == self.dtype
+            self.params, self.state, self.specs, self.spec_order = share.params, share.state, share.specs, share.spec_order
+            self.tc_packs = share.tc_packs
 
     # ---- construction ------------------------------------------------------------------
     def new_buf(self, h: int, w: int, pitch: int, name: str, requires_grad: bool = True, n: Optional[int] = None) -> Buf:
@@ -200,6 +208,9 @@ class Engine:
         return b
 
     def add_param(self, spec: ParamSpec):
+        if self.share is not None:
+            assert spec.name in self.specs and self.specs[spec.name].phys_shape == spec.phys_shape, spec.name
+            return
         self.specs[spec.name] = spec
         self.spec_order.append(spec.name)
         store = self.params if spec.trainable else self.state
@@ -210,6 +221,15 @@ class Engine:
         return op
 
     def finalize(self):
+        if self.share is not None:
+            for s in (self.zeroed, self.scratch):
+                s.alloc(self.device)
+            r = self.share
+            self.grads, self.adam_m, self.adam_v, self.adam_state, self.lr = r.grads, r.adam_m, r.adam_v, r.adam_state, r.lr
+            for op in reversed(self.ops):
+                op.plan_backward()
+            self.finalized = True
+            return
         for s in (self.params, self.state, self.zeroed, self.scratch):
             s.alloc(self.device)
         self.grads = torch.zeros_like(self.params.t)
@@ -228,12 +248,22 @@ class Engine:
         self.finalized = True
 
     def tc_pack(self, w: str, R: int, S: int, cin: int, cout: int, flip: int) -> dict:
+        for pk in self.tc_packs:
+            if pk["w"] == w and pk["flip"] == flip:
+                return pk
         pk = {"w": w, "R": R, "S": S, "Cin": cin, "Cout": cout, "flip": flip, "buf": None}
         self.tc_packs.append(pk)
+        root = self.share or self
+        if root.finalized:      # a tower added after the root was finalised needs a pack the root never used
+            nbytes = int(self.lib.semb_pack_weights_tc(None, R, S, cin, cout, flip, None, None))
+            pk["buf"] = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device=self.device)
+            root._pack_dirty = True
         return pk
 
     def repack(self):
         """fp32 master weights -> packed bf16 UMMA images (after set_weights / Adam)."""
+        if self.share is not None:
+            return self.share.repack()
         if not self.dry:
             st = self.stream
             for pk in self.tc_packs:
@@ -287,14 +317,15 @@ class Engine:
     def zero_step(self, zero_grads: bool):
         st = self.stream
         L.check(self.lib.semb_fill_f32(self.zeroed.t.data_ptr(), self.zeroed.t.numel(), 0.0, st))
-        if zero_grads:
+        if zero_grads and self.share is None:
             L.check(self.lib.semb_fill_f32(self.grads.data_ptr(), self.grads.numel(), 0.0, st))
 
     def forward(self, training: bool):
         if self.dry:
             raise L.SembError("dry engine: kernels need an sm_100a device, there is no CPU execution path")
-        if self._pack_dirty and self.tc_packs:
-            self.repack()
+        root = self.share or self
+        if root._pack_dirty and root.tc_packs:
+            root.repack()
         for op in self.ops:
             op.fwd(training)
 
@@ -312,6 +343,8 @@ class Engine:
 
 def plan_grad_write(view: View) -> int:
     """Returns the accumulate flag for a gradient write into `view` at this point of the backward plan."""
+    if view.buf.force_acc:
+        return 1
     lo, hi = view.coff, view.coff + view.C
     cover = view.buf.grad_cover
     inside = any(a <= lo and hi <= b for a, b in cover)
@@ -362,14 +395,26 @@ class ConvOp(Op):
         self.stats = stats  # (zeroed-store name, offset, nstride, cstride)
         self.acc_x = 0
         self.use_tc = (eng.tc_enabled and not transposed and stride == 1 and k in (1, 3))
+        self.pad_buf = None
+        if pad_mode == L.PAD_REFLECT and x.requires_grad and not transposed:
+            # the data gradient of a reflect-padded conv is taken on the padded domain and folded back
+            hp = max(h, (oh - 1) * stride + k)
+            wp = max(wd, (ow - 1) * stride + k)
+            self.pad_buf = eng.new_buf(hp, wp, x.C, f"{w}_dxpad", n=n)
+            self.pad_hw = (hp, wp)
+            self.geom_p = L.ConvGeom(n, hp, wp, oh, ow, cin, cout, k, k, stride, 0, 0, L.PAD_ZERO, eng.dtype)
         if self.use_tc:
             self.pk_fwd = eng.tc_pack(w, k, k, cin, cout, 0)
             self.pk_bwd = None
-            if x.requires_grad and pad_mode == L.PAD_ZERO:
+            if x.requires_grad:
                 self.pk_bwd = eng.tc_pack(w, k, k, cin, cout, 1)
                 # stride-1 data gradient = conv of dy with the mirrored, transposed kernel, pad k-1-pad
-                self.geom_d = L.ConvGeom(n, oh, ow, h, wd, cout, cin, k, k, 1, k - 1 - pad_tl[0], k - 1 - pad_tl[1],
-                                         L.PAD_ZERO, eng.dtype)
+                if self.pad_buf is None:
+                    self.geom_d = L.ConvGeom(n, oh, ow, h, wd, cout, cin, k, k, 1, k - 1 - pad_tl[0], k - 1 - pad_tl[1],
+                                             L.PAD_ZERO, eng.dtype)
+                else:
+                    self.geom_d = L.ConvGeom(n, oh, ow, self.pad_hw[0], self.pad_hw[1], cout, cin, k, k, 1, k - 1, k - 1,
+                                             L.PAD_ZERO, eng.dtype)
 
     def plan_backward(self):
         if self.x.requires_grad:
@@ -404,12 +449,18 @@ class ConvOp(Op):
                 L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w), dbias,
                                                 e.stream))
             if self.x.requires_grad:
+                dst = self.x.g if self.pad_buf is None else self.pad_buf.view().t
+                acc = self.acc_x if self.pad_buf is None else 0
                 if self.use_tc and self.pk_bwd is not None:
                     L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_d), C.byref(self.y.g), self.pk_bwd["buf"].data_ptr(), None,
-                                                     C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
+                                                     C.byref(dst), None, 0, 0, acc, e.stream))
                 else:
-                    L.check(e.lib.semb_conv2d_dgrad(C.byref(self.geom), C.byref(self.y.g), e.params.ptr(self.w), None,
-                                                    C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
+                    L.check(e.lib.semb_conv2d_dgrad(C.byref(self.geom if self.pad_buf is None else self.geom_p), C.byref(self.y.g),
+                                                    e.params.ptr(self.w), None, C.byref(dst), None, 0, 0, acc, e.stream))
+                if self.pad_buf is not None:
+                    g = self.geom
+                    L.check(e.lib.semb_pad_crop(C.byref(dst), C.byref(self.x.g), g.N, self.pad_hw[0], self.pad_hw[1], g.H, g.W,
+                                                g.pad_t, g.pad_l, 3, e.dtype, self.acc_x, e.stream))
         else:
             # d/dw of the transposed conv: wgrad of the equivalent conv with x':=d(out), dy':=in
             L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.y.g), C.byref(self.x.t), e.gptr(self.w), None,

@@ -40,7 +40,7 @@ def conv2d(x, kernel, bias=None, stride: int = 1, padding: str = "same"):
     """keras.layers.Conv2D(...)(x).  x NHWC, kernel HWIO.
     Reference call sites: UNet_Segmentation.py:421, CycleGAN.py:327,340,372,429."""
     kh, kw = kernel.shape[0], kernel.shape[1]
-    w = kernel.permute(3, 2, 0, 1)  # OIHW
+    w = kernel.permute(3, 2, 0, 1).contiguous()  # OIHW (contiguous: the fp64 CPU conv backward requires it)
     xi = _nchw(x)
     if padding == "same":
         if stride == 1:
@@ -72,7 +72,7 @@ def conv2d_transpose(x, kernel, bias=None, stride: int = 2):
     kernel (kh,kw,Cout,Cin).  UNet_Segmentation.py:542-551, CycleGAN.py:353."""
     k = kernel.shape[0]
     p, op = conv_transpose_pads(k, stride)
-    w = kernel.permute(3, 2, 0, 1)  # (Cin, Cout, kh, kw)
+    w = kernel.permute(3, 2, 0, 1).contiguous()  # (Cin, Cout, kh, kw)
     y = F.conv_transpose2d(_nchw(x), w, bias, stride=stride, padding=p, output_padding=op)
     return _nhwc(y)
 
