@@ -1,0 +1,195 @@
+"""Drop-in for Releases/Version 1.2.0/CycleGAN.py (class CycleGAN :20-317, DataLoader :454-479) on the sm_100a engine.
+
+Same attribute-style configuration and method names; `create_model()` returns `sem_b200.CycleGanModel` (networks and
+train step in hand-written CUDA).  Supported configuration = what StartProcess.py drives: no skip connection, no
+Gaussian noise in the discriminators, transposed-conv upsampling, MAE cycle / identity losses (other switches raise).
+Models are saved as `model.npz`; the per-epoch image mosaics of GANMonitor are not produced.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+from PIL import Image
+
+from . import HelperFunctions
+from .cyclegan_model import CycleGanModel, ImagePool
+
+
+class DataLoader:
+    def __init__(self, train_a, train_b, batch_size=1, use_dataloader=False, scale_for_binary_crossentropy=False, invert_images=False, **kw):
+        self.batch_size, self.train_a, self.train_b = batch_size, train_a, train_b
+        self.use_dataloader, self.scale_for_binary_crossentropy, self.invert_images = use_dataloader, scale_for_binary_crossentropy, invert_images
+
+    def __len__(self):
+        return int(min(len(self.train_a), len(self.train_b)) / float(self.batch_size))
+
+    def __getitem__(self, idx):
+        s = slice(idx * self.batch_size, (idx + 1) * self.batch_size)
+        a, b = self.train_a[s], self.train_b[s]
+        if self.use_dataloader:
+            a = CycleGAN.load_images(a, False, invert=self.invert_images)
+            b = CycleGAN.load_images(b, self.scale_for_binary_crossentropy)
+        return np.asarray(a), np.asarray(b)
+
+    def on_epoch_end(self):
+        np.random.shuffle(self.train_a)
+        np.random.shuffle(self.train_b)
+
+
+class CycleGAN:
+    def __init__(self, root_dir="./", image_shape=(384, 384, 1), allow_memory_growth=True, use_gpus_no=(0,)):
+        self.batch_size = 2
+        self.epochs = 50
+        self.learning_rate = 2e-4
+        self.use_data_loader = False
+        self.filters = 32
+        self.num_downsampling_blocks_gen = 3
+        self.num_residual_blocks_gen = 9
+        self.num_upsampling_blocks_gen = 3
+        self.num_downsampling_blocks_disc = 2
+        self.allow_memory_growth, self.use_gpus_no = allow_memory_growth, use_gpus_no
+        self.lambda_cycle_a = self.lambda_cycle_b = 10
+        self.use_binary_crossentropy = False
+        self.use_linear_decay = True
+        self.decay_epoch = int(0.75 * self.epochs)
+        self.lambda_identity_a = self.lambda_identity_b = 0.5
+        self.use_skip_connection = True
+        self.use_resize_convolution = False
+        self.label_smoothing_factor = 0.0
+        self.gaussian_noise_value = 0.15
+        self.invert_images = False
+        self.image_pool_size = 50
+        self.model = self.data = None
+        self.root_dir = root_dir
+        self.model_dir = os.path.join(root_dir, "2_CycleGAN", "Models")
+        self.image_shape = image_shape
+        self.prefix = time.strftime("%Y-%m-%d_%H-%M-%S", time.localtime())
+        self.dtype = os.environ.get("SEMB_DTYPE", "bf16")
+        # the pools are created with the batch size known HERE (2); StartProcess assigns batch_size afterwards
+        # (reference quirk) -- kept.
+        self.image_pool_a = ImagePool(batch_size=self.batch_size, pool_size=self.image_pool_size)
+        self.image_pool_b = ImagePool(batch_size=self.batch_size, pool_size=self.image_pool_size)
+        d = os.path.join(root_dir, "2_CycleGAN", "data")
+        ls = lambda s: HelperFunctions.get_image_file_paths_from_directory(os.path.join(d, s)) if os.path.isdir(os.path.join(d, s)) else []
+        self.train_a, self.test_a, self.train_b, self.test_b = ls("trainA"), ls("testA"), ls("trainB"), ls("testB")
+
+    def create_model(self) -> CycleGanModel:
+        unsupported = {"use_skip_connection": self.use_skip_connection, "use_resize_convolution": self.use_resize_convolution,
+                       "use_binary_crossentropy": self.use_binary_crossentropy, "gaussian_noise_value": self.gaussian_noise_value > 0}
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"CycleGAN options {bad} are outside the accelerated path; StartProcess.py sets them off")
+        if (self.num_downsampling_blocks_gen, self.num_upsampling_blocks_gen, self.num_downsampling_blocks_disc) != (3, 3, 2):
+            raise NotImplementedError("only the 3-down / 3-up generator and the 2-block PatchGAN are built")
+        model = CycleGanModel(image_shape=self.image_shape, batch_size=self.batch_size, filters=self.filters, dtype=self.dtype,
+                              n_res=self.num_residual_blocks_gen, lambda_cycle_a=self.lambda_cycle_a, lambda_cycle_b=self.lambda_cycle_b,
+                              lambda_identity_a=self.lambda_identity_a, lambda_identity_b=self.lambda_identity_b,
+                              image_pool_a=self.image_pool_a, image_pool_b=self.image_pool_b,
+                              label_smoothing_factor=self.label_smoothing_factor)
+        model.compile(learning_rate=self.learning_rate, beta_1=0.5)
+        return model
+
+    def generator_loss_fn(self, fake):
+        t = (1.0 - self.label_smoothing_factor) + self.label_smoothing_factor / 2
+        return float(np.mean((t - np.asarray(fake)) ** 2))
+
+    def discriminator_loss_fn(self, real, fake):
+        s = self.label_smoothing_factor
+        real_loss = float(np.mean(((1.0 - s) + s / 2 - np.asarray(real)) ** 2))
+        fake_loss = float(np.mean((s / 2 - np.asarray(fake)) ** 2))
+        return (real_loss + fake_loss) * 0.5, real_loss, fake_loss
+
+    def linear_decay(self, epoch, current_lr):
+        if epoch < self.decay_epoch:
+            return self.learning_rate
+        return self.learning_rate * (1 - (epoch - self.decay_epoch) / float(self.epochs - self.decay_epoch))
+
+    @staticmethod
+    def load_images(image_list, scale_for_binary_crossentropy=False, invert=False):
+        r = (0, 1) if scale_for_binary_crossentropy else (-1, 1)
+        images = HelperFunctions.load_and_preprocess_images(image_list, threshold_value=None, normalization_range=r, output_channels=1)
+        return images * -1.0 if invert else images
+
+    def start_training(self):
+        out_dir = os.path.join(self.model_dir, self.prefix)
+        os.makedirs(out_dir, exist_ok=True)
+        self.decay_epoch = int(0.75 * self.epochs)
+        if not self.use_data_loader:
+            self.train_a = self.load_images(self.train_a, False, invert=self.invert_images)
+            self.train_b = self.load_images(self.train_b, self.use_binary_crossentropy)
+        self.data = DataLoader(self.train_a, self.train_b, self.batch_size, self.use_data_loader, self.use_binary_crossentropy, self.invert_images)
+        self.model = self.create_model()
+        log = os.path.join(out_dir, "training_log.csv")
+        for epoch in range(self.epochs):
+            # NOTE: in the reference the LearningRateScheduler only touches the unused base optimizer of CycleGanModel,
+            # not the four Adam instances; the four learning rates therefore stay constant.
+            agg = {}
+            for i in range(len(self.data)):
+                for k, v in self.model.train_step(self.data[i]).items():
+                    agg[k] = agg.get(k, 0.0) + v
+            logs = {k: v / max(len(self.data), 1) for k, v in agg.items()}
+            new = not os.path.exists(log)
+            with open(log, "a") as fh:
+                if new:
+                    fh.write(";".join(["epoch"] + sorted(logs)) + "\n")
+                fh.write(";".join([str(epoch)] + [repr(logs[k]) for k in sorted(logs)]) + "\n")
+            print(f"Epoch {epoch + 1}/{self.epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()), flush=True)
+            self.save(os.path.join(out_dir, f"checkpoints_{epoch + 1:03d}.npz"))
+            self.data.on_epoch_end()
+        self.save(os.path.join(out_dir, "model.npz"))
+        return self.model
+
+    def save(self, path):
+        arrs = {}
+        for name, net in self.model.nets.items():
+            for n, w in zip(net.names, net.get_weights()):
+                arrs[f"{name}/{n}"] = w
+        np.savez(path, **arrs)
+
+    def load(self, path):
+        self.model = self.model or self.create_model()
+        with np.load(path) as z:
+            for name, net in self.model.nets.items():
+                net.set_named({n: z[f"{name}/{n}"] for n in net.names})
+        return self.model
+
+    def run_inference(self, files, output_directory, source_domain, model=None, tile_images=False, min_overlap=2,
+                      manage_overlap_mode=2, use_gpu=False):
+        images = HelperFunctions.load_and_preprocess_images(files, normalization_range=(-1, 1))
+        names = HelperFunctions.get_image_file_paths_from_directory(files)
+        which = "gen_a" if "a" in source_domain.lower() else "gen_b"
+        os.makedirs(output_directory, exist_ok=True)
+        weights_from = model if isinstance(model, str) else None
+        if self.model is None and weights_from is None:
+            newest = sorted(os.listdir(self.model_dir))[-1]
+            weights_from = os.path.join(self.model_dir, newest, "model.npz")
+        cache = {}
+        for i in range(images.shape[0]):
+            img = images[i]
+            if which == "gen_a" and self.invert_images:
+                img = img * -1
+            th, tw = (self.image_shape[0], self.image_shape[1]) if tile_images else (img.shape[0], img.shape[1])
+            tiles = HelperFunctions.tile_image(img, tw, th, min_overlap=min_overlap) if tile_images else img[None]
+            key = (len(tiles), th, tw)
+            if key not in cache:          # generators are fully convolutional: re-instantiate at this size, same weights
+                saved_shape, saved_bs, saved_model = self.image_shape, self.batch_size, self.model
+                self.image_shape, self.batch_size, self.model = (th, tw, 1), len(tiles), None
+                m = self.create_model()
+                if weights_from is not None:
+                    self.model = m
+                    self.load(weights_from)
+                elif saved_model is not None:
+                    for name, net in m.nets.items():
+                        net.set_weights(saved_model.nets[name].get_weights())
+                cache[key] = m
+                self.image_shape, self.batch_size, self.model = saved_shape, saved_bs, saved_model
+            pred = cache[key].generate(which, tiles)
+            out = (HelperFunctions.stitch_image(pred, img.shape[1], img.shape[0], min_overlap=min_overlap,
+                                                manage_overlap_mode=manage_overlap_mode) if tile_images else pred[0])[:, :, 0].copy()
+            if which == "gen_b" and self.invert_images:
+                out *= -1
+            out -= np.min(out)
+            out /= np.max(out)
+            Image.fromarray((out * 255).astype(np.uint8)).save(os.path.join(output_directory, os.path.split(names[i])[-1]))

@@ -1,0 +1,145 @@
+"""Host-side helpers with the reference's names and argument meaning (Releases/Version 1.2.0/HelperFunctions.py).
+
+Only what the conv-stack hot path touches is mirrored: image loading / normalisation (:290-329), the overlapping
+tile grid and its inverse (:17-141) and a threshold-only `segment`.  The classical post-processing chain (watershed,
+Li filter, particle measurements) is outside the hot path and is not reproduced here.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+from PIL import Image
+
+IMAGE_EXTENSIONS = (".tif", ".tiff", ".png", ".bmp", ".jpg", ".jpeg", ".gif")
+
+
+def get_image_file_paths_from_directory(directory):
+    return [os.path.join(directory, f) for f in os.listdir(directory) if f.endswith(IMAGE_EXTENSIONS)]
+
+
+def load_and_preprocess_images(input_dir_or_filelist, threshold_value=None, normalization_range=(-1, 1), output_channels=1,
+                               contrast_optimization_range=None):
+    """HelperFunctions.py:296-329: optional percentile clipping, min-max to [0,1], optional threshold, affine to range."""
+    if isinstance(input_dir_or_filelist, (str, os.PathLike)):
+        files = (get_image_file_paths_from_directory(input_dir_or_filelist) if os.path.isdir(input_dir_or_filelist)
+                 else [input_dir_or_filelist])
+    else:
+        files = list(input_dir_or_filelist)
+    out = []
+    for f in files:
+        img = np.array(Image.open(f), dtype="float32")
+        assert 2 <= img.ndim <= 3 and output_channels in (1, 3), "Invalid Image format"
+        if img.ndim == 3 and output_channels == 1:
+            img = np.average(img, -1)
+        if img.ndim == 2:
+            img = img[:, :, None]
+        r = contrast_optimization_range
+        if r is not None and r[0] > 0 and r[1] < 100:
+            lo, hi = np.percentile(img, r[0]), np.percentile(img, r[1])
+            img = np.clip(img, lo, hi)
+        if normalization_range is not None:
+            img = img - img.min()
+            img = img / img.max()
+            if threshold_value is not None:
+                img = (img > threshold_value).astype("float32")
+            img = normalization_range[0] + (normalization_range[1] - normalization_range[0]) * img
+        out.append(img)
+    return np.array(out, dtype="float32")
+
+
+def _grid(size: int, tile: int, min_overlap: int):
+    """number of tiles and their offsets along one axis (HelperFunctions.py:21-47)"""
+    n = math.ceil(size / tile)
+    if n > 1 and (tile - size % tile) % tile <= min_overlap:
+        n += 1
+    if n == 1:
+        return 1, [0]
+    step = tile - (tile * n - size) / (n - 1)
+    return n, [math.ceil(i * step) for i in range(n)]
+
+
+def tile_image(img, tile_size_w, tile_size_h, min_overlap=2, normalization_range=None, normalize_tiles_individually=True):
+    """Overlapping tiles, x-major order (outer loop over columns) like the reference; a tile reaching past the image
+    edge is zero filled."""
+    h, w = img.shape[0], img.shape[1]
+    nx, xs = _grid(w, tile_size_w, min_overlap)
+    ny, ys = _grid(h, tile_size_h, min_overlap)
+    tiles = np.zeros((nx * ny, tile_size_h, tile_size_w, 1), dtype="float32")
+    k = 0
+    for ox in xs:
+        for oy in ys:
+            patch = img[oy:min(oy + tile_size_h, h), ox:min(ox + tile_size_w, w), :]
+            tiles[k, :patch.shape[0], :patch.shape[1], :] = patch
+            k += 1
+    if normalization_range is not None:
+        lo, hi = normalization_range
+        if normalize_tiles_individually:
+            for t in tiles:
+                t -= t.min()
+                t /= t.max()
+                t *= (hi - lo)
+                t += lo
+        else:
+            tiles -= img.min()
+            tiles /= img.max()
+            tiles = lo + (hi - lo) * tiles
+    return tiles
+
+
+def stitch_image(img, image_size_w, image_size_h, min_overlap=2, manage_overlap_mode=2, return_8_bit_image=False):
+    """Inverse of tile_image; manage_overlap_mode 0 = maximum, 1 = average, 2 = crop half of the overlap from each tile."""
+    th, tw, c = img.shape[1], img.shape[2], img.shape[-1]
+    nx, xs = _grid(image_size_w, tw, min_overlap)
+    ny, ys = _grid(image_size_h, th, min_overlap)
+    out = np.zeros((image_size_h, image_size_w, c), dtype="float32")
+    count = np.zeros_like(out, dtype="uint8")
+    ovx = (tw * nx - image_size_w) // (2 * (nx - 1)) if nx > 1 else 0
+    ovy = (th * ny - image_size_h) // (2 * (ny - 1)) if ny > 1 else 0
+    k = 0
+    for i, ox in enumerate(xs):
+        for j, oy in enumerate(ys):
+            y1, x1 = min(oy + th, image_size_h), min(ox + tw, image_size_w)
+            if manage_overlap_mode == 0:
+                out[oy:y1, ox:x1] = np.maximum(img[k, :y1 - oy, :x1 - ox], out[oy:y1, ox:x1])
+            elif manage_overlap_mode == 1:
+                out[oy:y1, ox:x1] += img[k, :y1 - oy, :x1 - ox]
+                count[oy:y1, ox:x1] += 1
+            else:
+                cl = 0 if i == 0 else ovx
+                cr = 0 if i == nx - 1 else ovx
+                ct = 0 if j == 0 else ovy
+                cb = 0 if j == ny - 1 else ovy
+                yb, xb = min(oy + th - cb, image_size_h), min(ox + tw - cr, image_size_w)
+                out[oy + ct:yb, ox + cl:xb] = img[k, ct:ct + (yb - oy - ct), cl:cl + (xb - ox - cl)]
+            k += 1
+    if manage_overlap_mode == 1:
+        out = out / count
+    out = np.asarray(out, dtype="float32")
+    if return_8_bit_image:
+        out = np.asarray(out * 255, dtype="uint8")
+    return out
+
+
+def threshold_otsu(image_u8: np.ndarray) -> float:
+    """Otsu's threshold on an 8-bit image (skimage.filters.threshold_otsu semantics: bin centres, maximise between-class variance)."""
+    hist = np.bincount(image_u8.ravel(), minlength=256).astype(np.float64)
+    centers = np.arange(256, dtype=np.float64)
+    w1 = np.cumsum(hist)
+    w2 = np.cumsum(hist[::-1])[::-1]
+    m1 = np.cumsum(hist * centers) / np.maximum(w1, 1e-300)
+    m2 = (np.cumsum((hist * centers)[::-1]) / np.maximum(w2[::-1], 1e-300))[::-1]
+    var = w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2
+    return float(centers[int(np.argmax(var))])
+
+
+def segment(image, threshold=-1, watershed_lines=True, min_distance=9, use_four_connectivity=True):
+    """Threshold half of HelperFunctions.segment: Otsu when threshold < 0 (reference :144-185).  The watershed split
+    is classical CPU post-processing outside the hot path: masks are returned unsplit."""
+    if image.dtype == bool:
+        mask = image
+    else:
+        t = threshold_otsu(image) if threshold < 0 else threshold * 255.0
+        mask = image > t
+    return np.asarray(mask, dtype="uint8") * 255

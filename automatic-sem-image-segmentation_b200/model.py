@@ -201,8 +201,10 @@ class UNetModel:
         self.process_group = process_group
         self.world_size = dist.get_world_size(process_group)
         self.rank = dist.get_rank(process_group)
-        dist.broadcast(self._current.eng.params.t, src=0, group=process_group)
-        dist.broadcast(self._current.eng.state.t, src=0, group=process_group)
+        from . import dp
+        dp.broadcast_(self._current.eng.params.t, 0, process_group)
+        dp.broadcast_(self._current.eng.state.t, 0, process_group)
+        self._current.eng._pack_dirty = True
 
     def _step_device(self, inst: _Instance):
         """fwd + loss + bwd (+ all-reduce) + Adam on the device; inputs already in inst.x_dev / y_dev."""
@@ -246,8 +248,8 @@ class UNetModel:
             e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
 
     def _allreduce(self, e: Engine):
-        import torch.distributed as dist
-        dist.all_reduce(e.grads, op=dist.ReduceOp.SUM, group=self.process_group)
+        from . import dp
+        dp.allreduce_sum_(e.grads, self.process_group)
 
     def train_step(self, x, y) -> Dict[str, float]:
         """One TorchTrainer.train_step with HOST inputs: H2D, fwd, loss, bwd, Adam, D2H of the metrics."""

@@ -1,0 +1,110 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol, channel layouts,
+parameter packing, Keras weight ordering, tiling / stitching, the no-CPU-fallback guarantee."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import sem_b200
+from sem_b200 import _lib as L
+from sem_b200.engine import Engine, Layout, ParamSpec
+from sem_b200.nets import KerasGraph, UNetBuilder
+from sem_b200 import HelperFunctions as HF
+from oracle import unet as OU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_symbol_of_the_header():
+    hdr = open(os.path.join(ROOT, "include", "semb200.h")).read()
+    declared = set(re.findall(r"\b(semb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(L.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/semb200.h but not exported"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    assert L.load().semb_version() == 100
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(L.SembError):
+        sem_b200.UNetModel((32, 32, 1))
+    e = Engine(1, "f32", dry=True)
+    UNetBuilder(e, 32, 32, 16)
+    e.finalize()
+    with pytest.raises(L.SembError):
+        e.forward(False)
+    src = "".join(open(os.path.join(ROOT, "automatic-sem-image-segmentation_b200", f)).read()
+                  for f in os.listdir(os.path.join(ROOT, "automatic-sem-image-segmentation_b200")) if f.endswith(".py"))
+    assert "import oracle" not in src and "from oracle" not in src      # the product never touches the checker
+
+
+def test_layout_and_param_packing_roundtrip():
+    lay = Layout.concat(Layout.simple(8), Layout.simple(17), Layout.simple(26))
+    assert (lay.logical, lay.phys) == (51, 64)
+    assert lay.index_map().tolist() == list(range(8)) + list(range(8, 25)) + list(range(32, 58))
+    spec = ParamSpec("w", "conv_kernel", (3, 3, 51, 5), (3, 3, 64, 8), {2: lay.index_map(), 3: np.arange(5)}, True)
+    w = np.random.default_rng(0).standard_normal((3, 3, 51, 5)).astype(np.float32)
+    p = spec.to_phys(w)
+    assert p.shape == (3, 3, 64, 8) and p[:, :, 25:32].any() == False and p[..., 5:].any() == False
+    assert np.array_equal(spec.to_logical(p), w)
+
+
+def test_unet_builder_matches_oracle_spec_and_packs_conv_transpose():
+    e = Engine(1, "bf16", dry=True)
+    b = UNetBuilder(e, 48, 32, 16)
+    e.finalize()
+    spec = OU.UNetSpec(16)
+    assert b.creation_names == spec.names()
+    p0 = spec.init_params(0)
+    for n in spec.names():
+        e.set_param(n, p0[n].numpy())
+        assert np.array_equal(e.get_param(n), p0[n].numpy()), n
+    # Conv2DTranspose kernel (2,2,Cout,Cin) is stored as a 1x1 kernel with 4*Cout outputs
+    k = p0["conv2d_transpose_1/kernel"].numpy()
+    phys = e.params.get("conv2d_transpose_1/kernel").numpy().reshape(e.specs["conv2d_transpose_1/kernel"].phys_shape)
+    assert phys.shape == (1, 1, 432, 512)
+    assert phys[0, 0, 3, 2 * 128 + 7] == k[1, 0, 7, 3]
+    names = b.keras_weight_names()
+    assert sorted(names) == sorted(spec.names()) and len(set(names)) == 348
+
+
+def test_keras_layer_order_rule():
+    """depth-sorted (deepest first), ties broken by pre-order DFS from the output over the call-order inputs [K3.5]."""
+    g = KerasGraph()
+    i = g.layer("input", [])
+    a = g.layer("a", [i], ["a/w"])          # long branch: a -> b
+    b = g.layer("b", [a], ["b/w"])
+    c = g.layer("c", [i], ["c/w"])          # short branch
+    o = g.layer("add", [c, b])              # call order: short branch first
+    assert [g.names[k] for k in g.layer_order(o)] == ["input", "a", "c", "b", "add"]
+    assert g.weight_names(o) == ["a/w", "c/w", "b/w"]
+
+
+@pytest.mark.parametrize("h,w,th,tw", [(712, 1024, 256, 256), (712, 1024, 384, 384), (768, 1024, 256, 256), (100, 90, 128, 128)])
+def test_tile_and_stitch_roundtrip(h, w, th, tw):
+    rng = np.random.default_rng(0)
+    img = rng.random((h, w, 1)).astype(np.float32)
+    tiles = HF.tile_image(img, tw, th, min_overlap=2)
+    if (h, w, th) == (712, 1024, 256):
+        assert tiles.shape[0] == 15          # 5 x 3
+    if (h, w, th) == (712, 1024, 384):
+        assert tiles.shape[0] == 6
+    if (h, w, th) == (768, 1024, 256):
+        assert tiles.shape[0] == 20
+    for mode in (0, 1, 2):
+        back = HF.stitch_image(tiles, w, h, min_overlap=2, manage_overlap_mode=mode)
+        assert np.allclose(back, img, atol=1e-6), mode
+
+
+def test_otsu_threshold_separates_bimodal():
+    rng = np.random.default_rng(0)
+    img = np.concatenate([rng.normal(60, 8, 5000), rng.normal(190, 10, 3000)]).clip(0, 255).astype(np.uint8)
+    t = HF.threshold_otsu(img)
+    assert 80 < t < 170
+    assert HF.segment(img.reshape(100, 80), threshold=-1).dtype == np.uint8
