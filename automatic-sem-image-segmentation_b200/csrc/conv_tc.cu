@@ -70,7 +70,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // bounded spin: a descriptor bug must trap, not hang the GPU box
+    // Plain try_wait spin (measured: a suspend-time hint or a __nanosleep back-off make the hand-offs slower and the
+    // kernels are hand-off-latency bound).  Bounded: a descriptor bug must trap, not hang the GPU box.
     const long long t0 = clock64();
     uint32_t done = 0;
     while (!done) {
@@ -81,6 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (!done && clock64() - t0 > 4000000000LL) __trap();
     }
+}
+// warp-collective wait: one lane polls, the warp re-converges on it
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -126,6 +132,30 @@ __device__ __forceinline__ uint32_t instr_desc(int M, int N, int a_mn_major, int
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// asynchronous arrive: fires when all cp.async issued so far by this thread have landed (no wait in the producer)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- forward / data-gradient conv: persistent, warp-specialised -----------------------------------------------
+//   warps 0-3  epilogue   : drain TMEM (lane = output pixel), bias, moments, bf16 store at the channel offset
+//   warp  4    MMA issuer : one elected thread, tcgen05.mma per (tap, 16-channel step), tcgen05.commit
+//   warps 5-8  producers  : cp.async the halo tile of the next (tile, channel-chunk) into a ring of stages
+// The accumulator is double-buffered in TMEM (2 x NC columns) so the epilogue of tile i overlaps the MMAs of tile
+// i+1 and the loads of tile i+2.  When all input channels fit one chunk the packed weights are loaded ONCE per CTA.
+constexpr int FW_THREADS = 288;
+constexpr int FW_PRODUCER0 = 160;      // first producer thread
+
 struct TcArgs {
     int N, H, W, OH, OW, Cin, Cout, R, S, pad_t, pad_l, pad_mode;
     const bf16* x; int x_pitch, x_coff;
@@ -133,143 +163,196 @@ struct TcArgs {
     const bf16* wp; const float* bias;
     double* stats; int stats_nstride, stats_cstride;
     int accumulate;
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y, total_tiles;
     TcPlan p;
     int plane_bytes, halo_h, halo_w;
+    int stages, b_resident, a_bytes, b_bytes, stage_bytes;
 };
 
-template <int COLS>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const TcArgs a) {
+template <int COLS, int STAGES>
+__global__ void __launch_bounds__(FW_THREADS) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const int taps = a.R * a.S;
-    const int KC = a.p.KC, NC = a.p.NC;
-    uint8_t* As = smem;                                              // [KC/8][plane]
-    uint8_t* Bs = smem + (KC / 8) * a.plane_bytes;                   // [tap][KC/8][NC][16 B]
-    float* part = reinterpret_cast<float*>(Bs + (size_t)taps * KC * NC * 2);   // [2][4][NC] epilogue partials
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], b_full;
     __shared__ uint32_t tmem_slot;
-
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x;
-    const int n = tile / (a.tiles_x * a.tiles_y);
-    const int trem = tile % (a.tiles_x * a.tiles_y);
-    const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
+    const int taps = a.R * a.S;
+    const int KC = a.p.KC, NC = a.p.NC, kchunks = a.p.kchunks;
     const int nchunk = blockIdx.y;
     const int halo_pix = a.halo_h * a.halo_w;
+    // smem: [resident B (optional)] [STAGES x (A chunk [+ B chunk])] [moment partials 4 x 2 x NC floats]
+    uint8_t* ring = smem + (a.b_resident ? a.b_bytes : 0);
+    float* part = reinterpret_cast<float*>(ring + (size_t)STAGES * a.stage_bytes);
+    const int ntiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == 0) tmem_alloc<COLS>(smem_u32(&tmem_slot));
-    if (tid == 0) mbar_init(smem_u32(&mbar), 1);
+    if (warp == 4) tmem_alloc<COLS>(smem_u32(&tmem_slot));
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&full_bar[i]), 128); mbar_init(smem_u32(&empty_bar[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
+        mbar_init(smem_u32(&b_full), 128);
+    }
+    for (int i = tid; i < 8 * NC; i += FW_THREADS) part[i] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    const uint32_t idesc = instr_desc(128, NC, 0, 0);
-    uint32_t phase = 0;
+    const uint32_t ring_u32 = smem_u32(ring);
 
-    for (int kc = 0; kc < a.p.kchunks; ++kc) {
-        const int cvalid = min(KC, a.Cin - kc * KC);                // multiple of 8
-        const int ksteps = (cvalid + 15) / 16;
-        const int planes = 2 * ksteps;
-        // ---- A: halo tile of this channel chunk -> channel-group planes
-        for (int idx = tid; idx < planes * halo_pix; idx += TC_THREADS) {
-            const int k8 = idx % planes, pix = idx / planes;
-            const int hy = pix / a.halo_w, hx = pix % a.halo_w;
-            int iy = y0 - a.pad_t + hy, ix = x0 - a.pad_l + hx;
-            if (a.pad_mode == SEMB_PAD_REFLECT) {
-                // positions that only feed out-of-range output pixels may fall outside the reflectable band
-                if (iy > -a.H && iy < 2 * a.H - 1) iy = reflect_index(iy, a.H);
-                if (ix > -a.W && ix < 2 * a.W - 1) ix = reflect_index(ix, a.W);
+    if (warp >= 5) {
+        // ============================== producers ==============================
+        const int ptid = tid - FW_PRODUCER0;
+        if (a.b_resident) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.wp + (size_t)nchunk * kchunks * taps * KC * NC);
+            const uint32_t dst = smem_u32(smem);
+            for (int idx = ptid; idx < a.b_bytes / 16; idx += 128) cp_async16(dst + idx * 16, src + idx, true);
+            cp_async_commit();
+            cp_async_wait<0>();
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&b_full));
+        }
+        const int nitems = ntiles * kchunks;
+        for (int item = 0; item < nitems; ++item) {
+            const int stage = item % STAGES;
+            mbar_wait_warp(smem_u32(&empty_bar[stage]), ((item / STAGES) & 1) ^ 1);
+            const int ti = item / kchunks, kc = item - ti * kchunks;
+            const int t = blockIdx.x + ti * gridDim.x;
+            const int n = t / (a.tiles_x * a.tiles_y);
+            const int trem = t % (a.tiles_x * a.tiles_y);
+            const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
+            const int c0 = kc * KC;
+            const int planes = 2 * ((min(KC, a.Cin - c0) + 15) / 16);
+            const uint32_t sbase = ring_u32 + stage * a.stage_bytes;
+            for (int pix = ptid; pix < halo_pix; pix += 128) {
+                const int hy = pix / a.halo_w, hx = pix % a.halo_w;
+                int iy = y0 - a.pad_t + hy, ix = x0 - a.pad_l + hx;
+                if (a.pad_mode == SEMB_PAD_REFLECT) {
+                    if (iy > -a.H && iy < 2 * a.H - 1) iy = reflect_index(iy, a.H);
+                    if (ix > -a.W && ix < 2 * a.W - 1) ix = reflect_index(ix, a.W);
+                }
+                const bool v = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+                const bf16* src = a.x + ((size_t)(n * a.H + (v ? iy : 0)) * a.W + (v ? ix : 0)) * a.x_pitch + a.x_coff + c0;
+                const uint32_t dst = sbase + pix * 16;
+                for (int k8 = 0; k8 < planes; ++k8) cp_async16(dst + k8 * a.plane_bytes, src + k8 * 8, v && (c0 + k8 * 8 < a.Cin));
             }
-            const int ch = kc * KC + k8 * 8;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W && ch < a.Cin)
-                v = *reinterpret_cast<const uint4*>(a.x + ((size_t)(n * a.H + iy) * a.W + ix) * a.x_pitch + a.x_coff + ch);
-            *reinterpret_cast<uint4*>(As + (size_t)k8 * a.plane_bytes + pix * 16) = v;
+            if (!a.b_resident) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.wp + ((size_t)nchunk * kchunks + kc) * taps * KC * NC);
+                const uint32_t dst = sbase + a.a_bytes;
+                for (int idx = ptid; idx < a.b_bytes / 16; idx += 128) cp_async16(dst + idx * 16, src + idx, true);
+            }
+            cp_async_arrive_noinc(smem_u32(&full_bar[stage]));
         }
-        // ---- B: packed weights of (nchunk, kc): one contiguous block
-        {
-            const uint4* src = reinterpret_cast<const uint4*>(a.wp + ((size_t)nchunk * a.p.kchunks + kc) * taps * KC * NC);
-            uint4* dstp = reinterpret_cast<uint4*>(Bs);
-            const int n16 = taps * KC * NC / 8;
-            for (int idx = tid; idx < n16; idx += TC_THREADS) dstp[idx] = src[idx];
+        cp_async_wait<0>();
+    } else if (warp == 4) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(128, NC, 0, 0);
+            const uint64_t ad0 = smem_desc(ring_u32, a.plane_bytes, a.halo_w * 16);
+            const uint64_t bd0 = smem_desc(a.b_resident ? smem_u32(smem) : ring_u32 + a.a_bytes, NC * 16, 128);
+            if (a.b_resident) mbar_wait(smem_u32(&b_full), 0);
+            int item = 0;
+            for (int ti = 0; ti < ntiles; ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(smem_u32(&acc_empty[buf]), ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < kchunks; ++kc, ++item) {
+                    const int stage = item % STAGES;
+                    mbar_wait(smem_u32(&full_bar[stage]), (item / STAGES) & 1);
+                    fence_proxy_async();          // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+                    tc_fence_after();
+                    const int ksteps = (min(KC, a.Cin - kc * KC) + 15) / 16;
+                    const uint32_t soff = (uint32_t)(stage * a.stage_bytes) >> 4;
+                    const uint32_t pl = (uint32_t)a.plane_bytes >> 4;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        const int r = tap / a.S, s = tap % a.S;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t ad = ad0 + soff + 2 * ks * pl + (r * a.halo_w + s);
+                            const uint64_t bd = bd0 + (a.b_resident ? 0u : soff) + (uint32_t)((tap * (KC / 8) + 2 * ks) * NC);
+                            umma_bf16(tmem + buf * NC, ad, bd, idesc, (kc | tap | ks) != 0);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));
+                }
+                umma_commit(smem_u32(&acc_full[buf]));
+            }
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
+    } else {
+        // ============================== epilogue ==============================
+        const int c_begin = nchunk * NC;
+        int cur_n = -1;
+        auto flush = [&](int n) {
+            // 128 epilogue threads: combine the four warps' partial moments in a fixed order, one fp64 atomic per channel
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = tid; i < NC; i += 128) {
+                const int c = c_begin + i;
+                if (c < a.Cout) {
+                    const float t1 = ((part[i] + part[NC + i]) + part[2 * NC + i]) + part[3 * NC + i];
+                    const float t2 = ((part[4 * NC + i] + part[5 * NC + i]) + part[6 * NC + i]) + part[7 * NC + i];
+                    double* st = a.stats + (size_t)n * a.stats_nstride + c;
+                    atomicAdd(st, (double)t1);
+                    atomicAdd(st + a.stats_cstride, (double)t2);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = tid; i < 8 * NC; i += 128) part[i] = 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        for (int ti = 0; ti < ntiles; ++ti) {
+            const int buf = ti & 1;
+            const int t = blockIdx.x + ti * gridDim.x;
+            const int n = t / (a.tiles_x * a.tiles_y);
+            const int trem = t % (a.tiles_x * a.tiles_y);
+            const int y0 = (trem / a.tiles_x) * TILE_H, x0 = (trem % a.tiles_x) * TILE_W;
+            if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && n != cur_n) flush(cur_n);
+            cur_n = n;
+            mbar_wait_warp(smem_u32(&acc_full[buf]), (ti >> 1) & 1);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(As), b_base = smem_u32(Bs);
-            for (int tap = 0; tap < taps; ++tap) {
-                const int r = tap / a.S, s = tap % a.S;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint64_t ad = smem_desc(a_base + (2 * ks) * a.plane_bytes + (r * a.halo_w + s) * 16, a.plane_bytes, a.halo_w * 16);
-                    const uint64_t bd = smem_desc(b_base + (tap * (KC / 8) + 2 * ks) * NC * 16, NC * 16, 128);
-                    umma_bf16(tmem, ad, bd, idesc, (kc | tap | ks) != 0);
+            const int m = warp * 32 + lane;
+            const int oy = y0 + m / TILE_W, ox = x0 + m % TILE_W;
+            const bool pvalid = oy < a.OH && ox < a.OW;
+            bf16* yp = a.y + ((size_t)(n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
+            for (int g = 0; g < NC / 8; ++g) {
+                const int c = c_begin + g * 8;
+                float v[8];
+                tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + buf * NC + g * 8, v);
+                const bool cvalid = c < a.Cout;
+                if (a.bias && cvalid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
+                }
+                if (a.stats) {
+                    float s1[8], s2[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { s1[i] = pvalid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+                            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+                        }
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { part[warp * NC + g * 8 + i] += s1[i]; part[(4 + warp) * NC + g * 8 + i] += s2[i]; }
+                    }
+                }
+                if (pvalid && cvalid) {
+                    if (a.accumulate) {
+                        float o[8];
+                        Vec8<bf16>::load(yp + c, o);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += o[i];
+                    }
+                    Vec8<bf16>::store(yp + c, v);
                 }
             }
-            umma_commit(smem_u32(&mbar));
+            tc_fence_before();
+            mbar_arrive(smem_u32(&acc_empty[buf]));
         }
-        mbar_wait(smem_u32(&mbar), phase);
-        phase ^= 1;
-    }
-    tc_fence_after();
-
-    // ---- epilogue: TMEM lane = output pixel, columns = output channels
-    const int m = warp * 32 + lane;
-    const int oy = y0 + m / TILE_W, ox = x0 + m % TILE_W;
-    const bool pvalid = oy < a.OH && ox < a.OW;
-    bf16* yp = a.y + ((size_t)(n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
-    const int c_begin = nchunk * NC;
-    for (int g = 0; g < NC / 8; ++g) {
-        const int c = c_begin + g * 8;
-        float v[8];
-        tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + g * 8, v);     // warp-collective: before any divergence
-        const bool cvalid = c < a.Cout;
-        if (a.bias && cvalid) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
-        }
-        if (a.stats) {
-            float s1[8], s2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { s1[i] = pvalid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-                    s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-                }
-            }
-            if (lane == 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { part[warp * NC + g * 8 + i] = s1[i]; part[(4 + warp) * NC + g * 8 + i] = s2[i]; }
-            }
-        }
-        if (pvalid && cvalid) {
-            if (a.accumulate) {
-                float o[8];
-                Vec8<bf16>::load(yp + c, o);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += o[i];
-            }
-            Vec8<bf16>::store(yp + c, v);
-        }
+        if (a.stats && cur_n >= 0) flush(a.stats_nstride != 0 ? cur_n : 0);
     }
     tc_fence_before();
     __syncthreads();
-    if (a.stats) {
-        for (int i = tid; i < NC; i += TC_THREADS) {
-            const int c = c_begin + i;
-            if (c < a.Cout) {
-                const float t1 = ((part[i] + part[NC + i]) + part[2 * NC + i]) + part[3 * NC + i];
-                const float t2 = ((part[4 * NC + i] + part[5 * NC + i]) + part[6 * NC + i]) + part[7 * NC + i];
-                double* st = a.stats + (size_t)n * a.stats_nstride + c;
-                atomicAdd(st, (double)t1);
-                atomicAdd(st + a.stats_cstride, (double)t2);
-            }
-        }
-    }
-    if (warp == 0) tmem_dealloc<COLS>(tmem);
+    if (warp == 4) tmem_dealloc<COLS>(tmem);
 }
 
 // ---- weight gradient on the tensor cores ------------------------------------------------------------------
@@ -325,16 +408,6 @@ struct WgArgs {
     int plane_a, plane_b, halo_h, halo_w;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 template <int COLS, int WG_STAGES>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
@@ -380,7 +453,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
         // ===================== producers =====================
         for (int it = 0; it < ntiles; ++it) {
             const int stage = it % WG_STAGES;
-            mbar_wait(smem_u32(&empty_bar[stage]), ((it / WG_STAGES) & 1) ^ 1);
+            mbar_wait_warp(smem_u32(&empty_bar[stage]), ((it / WG_STAGES) & 1) ^ 1);
             const int t = blockIdx.x + it * a.p.splits;
             const int n = t / (a.tiles_x * a.tiles_y);
             const int trem = t % (a.tiles_x * a.tiles_y);
@@ -405,16 +478,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
                 const uint32_t dst = sbase + b_off + pix * 16;
                 for (int k8 = 0; k8 < planes_b; ++k8) cp_async16(dst + k8 * a.plane_b, src + k8 * 8, v);
             }
-            cp_async_commit();
-            if (it >= WG_STAGES - 1) {          // the group issued WG_STAGES-1 iterations ago has landed
-                cp_async_wait<WG_STAGES - 1>();
-                fence_proxy_async();
-                mbar_arrive(smem_u32(&full_bar[(it - (WG_STAGES - 1)) % WG_STAGES]));
-            }
+            cp_async_arrive_noinc(smem_u32(&full_bar[stage]));
         }
         cp_async_wait<0>();
-        fence_proxy_async();
-        for (int it = max(0, ntiles - (WG_STAGES - 1)); it < ntiles; ++it) mbar_arrive(smem_u32(&full_bar[it % WG_STAGES]));
     } else if (lane == 0) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = instr_desc(128, NCH, 1, 1);
@@ -423,6 +489,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
         for (int it = 0; it < ntiles; ++it) {
             const int stage = it % WG_STAGES;
             mbar_wait(smem_u32(&full_bar[stage]), (it / WG_STAGES) & 1);
+            fence_proxy_async();
             tc_fence_after();
             const uint32_t soff = (uint32_t)(stage * a.p.stage_bytes) >> 4;
             for (int tl = 0; tl < ntaps; ++tl) {
@@ -440,7 +507,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
     }
     // ---- flush: TMEM lane = co, columns = [tap][ci]; lanes of a warp hit consecutive co -> coalesced reductions
     if (warp < 4) {
-        mbar_wait(smem_u32(&done_bar), 0);
+        mbar_wait_warp(smem_u32(&done_bar), 0);
         tc_fence_after();
         if (ntiles > 0) {
             const int co = co0 + warp * 32 + lane;
@@ -463,10 +530,6 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
     tc_fence_before();
     __syncthreads();
     if (warp == 4) tmem_dealloc<COLS>(tmem);
-}
-
-static size_t tc_smem_bytes(const TcPlan& p, int taps, int plane_bytes) {
-    return (size_t)(p.KC / 8) * plane_bytes + (size_t)taps * p.KC * p.NC * 2 + (size_t)8 * p.NC * sizeof(float);
 }
 
 }  // namespace semb
@@ -510,23 +573,42 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     a.stats = reinterpret_cast<double*>(stats); a.stats_nstride = stats_nstride; a.stats_cstride = stats_cstride;
     a.accumulate = accumulate;
     a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
+    a.total_tiles = g->N * a.tiles_x * a.tiles_y;
     a.p = tc_plan(g->Cin, g->Cout, g->R * g->S);
     a.halo_h = TILE_H + g->R - 1; a.halo_w = TILE_W + g->S - 1;
     a.plane_bytes = a.halo_h * a.halo_w * 16 + 16;          // +16: consecutive planes start in different banks
-    const size_t smem = tc_smem_bytes(a.p, g->R * g->S, a.plane_bytes);
-    SEMB_REQUIRE(smem <= 200 * 1024, SEMB_EWORKSPACE, "conv_tc: %zu bytes of shared memory needed", smem);
-    dim3 grid(g->N * a.tiles_x * a.tiles_y, a.p.nchunks);
+    const int taps = g->R * g->S;
+    a.a_bytes = (a.p.KC / 8) * a.plane_bytes;
+    a.b_bytes = taps * a.p.KC * a.p.NC * 2;
+    a.b_resident = a.p.kchunks == 1;
+    a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
+    const size_t fixed = (a.b_resident ? a.b_bytes : 0) + (size_t)8 * a.p.NC * sizeof(float);
+    a.stages = ((size_t)3 * a.stage_bytes + fixed <= 100 * 1024 || (size_t)3 * a.stage_bytes + fixed <= 200 * 1024) ? 3 : 2;
+    const size_t smem = (size_t)a.stages * a.stage_bytes + fixed;
+    SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tc: %zu bytes of shared memory needed", smem);
+    const int cols = 2 * a.p.NC <= 32 ? 32 : (2 * a.p.NC <= 64 ? 64 : (2 * a.p.NC <= 128 ? 128 : (2 * a.p.NC <= 256 ? 256 : 512)));
+    int per_sm = 512 / cols;                                  // TMEM columns
+    if ((size_t)per_sm * (smem + 2048) > 220 * 1024) per_sm = (int)(220 * 1024 / (smem + 2048));   // shared memory
+    if (per_sm > 6) per_sm = 6;                               // 288 threads per CTA
+    if (per_sm < 1) per_sm = 1;
+    int gx = 148 * per_sm;
+    if (gx > a.total_tiles) gx = a.total_tiles;
+    dim3 grid(gx, a.p.nchunks);
     cudaError_t e = cudaSuccess;
-#define SEMB_TC_LAUNCH(COLS)                                                                                         \
-    e = cudaFuncSetAttribute(conv_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-    if (e == cudaSuccess) conv_tc_kernel<COLS><<<grid, TC_THREADS, smem, as_stream(stream)>>>(a);
-    switch (a.p.tmem_cols) {
+#define SEMB_TC_LAUNCH2(COLS, ST)                                                                                     \
+    e = cudaFuncSetAttribute(conv_tc_kernel<COLS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    if (e == cudaSuccess) conv_tc_kernel<COLS, ST><<<grid, FW_THREADS, smem, as_stream(stream)>>>(a);
+#define SEMB_TC_LAUNCH(COLS)                                                                                          \
+    if (a.stages == 3) { SEMB_TC_LAUNCH2(COLS, 3) } else { SEMB_TC_LAUNCH2(COLS, 2) }
+    switch (cols) {
         case 32: SEMB_TC_LAUNCH(32) break;
         case 64: SEMB_TC_LAUNCH(64) break;
         case 128: SEMB_TC_LAUNCH(128) break;
-        default: SEMB_TC_LAUNCH(256) break;
+        case 256: SEMB_TC_LAUNCH(256) break;
+        default: SEMB_TC_LAUNCH(512) break;
     }
 #undef SEMB_TC_LAUNCH
+#undef SEMB_TC_LAUNCH2
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
     return check_launch("conv_tc");
 }
