@@ -147,6 +147,24 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+
+// Sum 16 values across the 32 lanes of a warp.  Each round exchanges half of the remaining values with the partner
+// lane (offset 16, 8, 4, 2) and keeps the other half; a last round (offset 1) adds the two partial totals.  Result:
+// w[0] of lane l holds the warp total of value index (l >> 1) & 15 (same value in lanes l and l^1).  Fixed order.
+__device__ __forceinline__ void warp_reduce16(float (&w)[16], int lane) {
+#pragma unroll
+    for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? w[i] : w[i + h];
+            const float keep = up ? w[i + h] : w[i];
+            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
+}
+
 // ---- forward / data-gradient conv: persistent, warp-specialised -----------------------------------------------
 //   warps 0-3  epilogue   : drain TMEM (lane = output pixel), bias, moments, bf16 store at the channel offset
 //   warp  4    MMA issuer : one elected thread, tcgen05.mma per (tap, 16-channel step), tcgen05.commit
@@ -319,20 +337,15 @@ __global__ void __launch_bounds__(FW_THREADS) conv_tc_kernel(const TcArgs a) {
                     for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
                 }
                 if (a.stats) {
-                    float s1[8], s2[8];
+                    // 16 per-pixel values (8 sums, 8 squares) -> warp totals with a halving butterfly: 8+4+2+1+1 = 16
+                    // shuffles instead of 80; even lane l ends up with the total of value (l >> 1).
+                    float w[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { s1[i] = pvalid ? v[i] : 0.f; s2[i] = s1[i] * s1[i]; }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
-                            s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
-                        }
-                    }
-                    if (lane == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { part[warp * NC + g * 8 + i] += s1[i]; part[(4 + warp) * NC + g * 8 + i] += s2[i]; }
+                    for (int i = 0; i < 8; ++i) { w[i] = pvalid ? v[i] : 0.f; w[8 + i] = w[i] * w[i]; }
+                    warp_reduce16(w, lane);
+                    if ((lane & 1) == 0) {
+                        const int idx = lane >> 1;                       // 0..7 sums, 8..15 squares
+                        part[((idx >> 3) * 4 + warp) * NC + g * 8 + (idx & 7)] += w[0];
                     }
                 }
                 if (pvalid && cvalid) {
@@ -583,7 +596,7 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     a.b_resident = a.p.kchunks == 1;
     a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
     const size_t fixed = (a.b_resident ? a.b_bytes : 0) + (size_t)8 * a.p.NC * sizeof(float);
-    a.stages = ((size_t)3 * a.stage_bytes + fixed <= 100 * 1024 || (size_t)3 * a.stage_bytes + fixed <= 200 * 1024) ? 3 : 2;
+    a.stages = (size_t)4 * a.stage_bytes + fixed <= 64 * 1024 ? 4 : ((size_t)3 * a.stage_bytes + fixed <= 200 * 1024 ? 3 : 2);
     const size_t smem = (size_t)a.stages * a.stage_bytes + fixed;
     SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tc: %zu bytes of shared memory needed", smem);
     const int cols = 2 * a.p.NC <= 32 ? 32 : (2 * a.p.NC <= 64 ? 64 : (2 * a.p.NC <= 128 ? 128 : (2 * a.p.NC <= 256 ? 256 : 512)));
@@ -599,7 +612,7 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     e = cudaFuncSetAttribute(conv_tc_kernel<COLS, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
     if (e == cudaSuccess) conv_tc_kernel<COLS, ST><<<grid, FW_THREADS, smem, as_stream(stream)>>>(a);
 #define SEMB_TC_LAUNCH(COLS)                                                                                          \
-    if (a.stages == 3) { SEMB_TC_LAUNCH2(COLS, 3) } else { SEMB_TC_LAUNCH2(COLS, 2) }
+    if (a.stages == 4) { SEMB_TC_LAUNCH2(COLS, 4) } else if (a.stages == 3) { SEMB_TC_LAUNCH2(COLS, 3) } else { SEMB_TC_LAUNCH2(COLS, 2) }
     switch (cols) {
         case 32: SEMB_TC_LAUNCH(32) break;
         case 64: SEMB_TC_LAUNCH(64) break;
