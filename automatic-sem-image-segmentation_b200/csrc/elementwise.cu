@@ -54,6 +54,55 @@ __device__ __forceinline__ float act_bwd_from_u(float u, int act) {
     }
 }
 
+// Raw (unconverted) 8-channel loads: all loads of an iteration are issued before any value is unpacked, and a bf16
+// vector waits in 4 registers instead of 8.
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+    uint4 r;
+    __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) { a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+};
+
+// Block-level column sums of per-thread-row partials sm[rows][ncol] with all 256 threads: G = 256/ncol row groups are
+// summed in parallel into sm2[G][ncol], then `emit(col, total)` is called once per column.  Fixed order: deterministic.
+template <typename F>
+__device__ __forceinline__ void block_colsum(const float* sm, float* sm2, int rows, int ncol, F emit) {
+    int G = 256 / ncol;                 // sm2 holds G * ncol <= 256 floats
+    if (G > rows) G = rows;
+    __syncthreads();
+    if (G <= 1) {
+        for (int col = threadIdx.x; col < ncol; col += 256) {
+            float t = 0.f;
+            for (int r = 0; r < rows; ++r) t += sm[r * ncol + col];
+            emit(col, t);
+        }
+        return;
+    }
+    for (int idx = threadIdx.x; idx < ncol * G; idx += 256) {
+        const int col = idx % ncol, gi = idx / ncol;
+        float t = 0.f;
+        for (int r = gi; r < rows; r += G) t += sm[r * ncol + col];
+        sm2[idx] = t;
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < ncol; col += 256) {
+        float t = 0.f;
+        for (int gi = 0; gi < G; ++gi) t += sm2[gi * ncol + col];
+        emit(col, t);
+    }
+}
+
 template <int K>
 __device__ __forceinline__ void ld_params(const float* p, size_t off, float (&v)[8]) {
 #pragma unroll
@@ -62,9 +111,9 @@ __device__ __forceinline__ void ld_params(const float* p, size_t off, float (&v)
 
 // y = act(a*sa+ta [+ actb(b*sb+tb)]), optional fp64 moments of y.  U pixels per thread are loaded before any is used.
 template <typename T, bool HAS_B, int ACT, int ACTB>
-__global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_fwd_kernel(const AffArgs p) {
-    extern __shared__ float sm[];  // [rows][2][C] when moments are requested
-    constexpr int U = 2;
+__global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p) {
+    extern __shared__ float sm[];  // [rows][2][C] + [<=256] when moments are requested
+    constexpr int U = HAS_B ? 2 : 4;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     const int n = blockIdx.y;
@@ -86,24 +135,26 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_fwd_kernel(cons
 
     if (L.active) {
         for (int base = begin + L.prow; base < end; base += L.rows * U) {
-            float va[U][8], vb[U][8];
+            Raw8<T> ra[U], rb[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int px = base + u * L.rows;
                 if (px < end) {
-                    Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va[u]);
-                    if (HAS_B) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb[u]);
+                    ra[u].load(vptr<T>(p.a, pix0 + px, c));
+                    if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int px = base + u * L.rows;
                 if (px < end) {
-                    float vy[8];
+                    float va[8], vb[8], vy[8];
+                    ra[u].unpack(va);
+                    if (HAS_B) rb[u].unpack(vb);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float t = fmaf(va[u][i], sa[i], ta[i]);
-                        if (HAS_B) t += act_fwd(fmaf(vb[u][i], sb[i], tb[i]), actb);
+                        float t = fmaf(va[i], sa[i], ta[i]);
+                        if (HAS_B) t += act_fwd(fmaf(vb[i], sb[i], tb[i]), actb);
                         vy[i] = act_fwd(t, act);
                         s1[i] += vy[i];
                         s2[i] += vy[i] * vy[i];
@@ -122,14 +173,11 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_fwd_kernel(cons
                 sm[(L.prow * 2 + 1) * p.C + c + i] = s2[i];
             }
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < p.C; i += 256) {
-            float t1 = 0.f, t2 = 0.f;
-            for (int r = 0; r < L.rows; ++r) { t1 += sm[(r * 2) * p.C + i]; t2 += sm[(r * 2 + 1) * p.C + i]; }
-            double* st = p.dstats + (size_t)n * p.stats_nstride + i;
-            atomicAdd(st, (double)t1);
-            atomicAdd(st + p.stats_cstride, (double)t2);
-        }
+        float* sm2 = sm + L.rows * 2 * p.C;
+        block_colsum(sm, sm2, L.rows, 2 * p.C, [&](int col, float t) {
+            const int k = col / p.C, i = col - k * p.C;
+            atomicAdd(p.dstats + (size_t)n * p.stats_nstride + (size_t)k * p.stats_cstride + i, (double)t);
+        });
     }
 }
 
@@ -138,8 +186,8 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_fwd_kernel(cons
 // output y is never re-read.
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kernel(const AffArgs p) {
-    extern __shared__ float sm[];  // [rows][4][C]
-    constexpr int U = HAS_B ? 1 : 2;
+    extern __shared__ float sm[];  // [rows][4][C] + [<=256]
+    constexpr int U = 2;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     const int n = blockIdx.y;
@@ -164,67 +212,71 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kern
 
     if (L.active) {
         for (int base = begin + L.prow; base < end; base += L.rows * U) {
-            float g[U][8], va[U][8], vb[U][8];
+            Raw8<T> rg[U], ra[U], rb[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int px = base + u * L.rows;
                 if (px < end) {
-                    Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g[u]);
-                    Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va[u]);
-                    if (HAS_B) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb[u]);
+                    rg[u].load(vptr<T>(p.dy, pix0 + px, c));
+                    ra[u].load(vptr<T>(p.a, pix0 + px, c));
+                    if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int px = base + u * L.rows;
                 if (px < end) {
+                    float g[8], va[8], vb[8];
+                    rg[u].unpack(g);
+                    ra[u].unpack(va);
+                    if (HAS_B) rb[u].unpack(vb);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float ub = 0.f, t = fmaf(va[u][i], sa[i], ta[i]);
-                        if (HAS_B) { ub = fmaf(vb[u][i], sb[i], tb[i]); t += act_fwd(ub, actb); }
-                        const float gg = g[u][i] * act_bwd_from_u(t, act);
+                        float ub = 0.f, t = fmaf(va[i], sa[i], ta[i]);
+                        if (HAS_B) { ub = fmaf(vb[i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                        const float gg = g[i] * act_bwd_from_u(t, act);
                         q0[i] += gg;
-                        q1[i] += gg * (va[u][i] - ma[i]);
+                        q1[i] += gg * (va[i] - ma[i]);
                         if (HAS_B) {
                             const float gb = gg * act_bwd_from_u(ub, actb);
                             q2[i] += gb;
-                            q3[i] += gb * (vb[u][i] - mb[i]);
+                            q3[i] += gb * (vb[i] - mb[i]);
                         }
                     }
                 }
             }
         }
     }
-    // block combine without shared-memory atomics (fp32 smem atomics are CAS loops: 256-way contention for small C):
-    // partials [rows][4][C], then one thread per channel adds the rows in a fixed order
+    // block combine without shared-memory atomics: partials [rows][4][C], then fixed-order column sums by all threads
+    constexpr int K = HAS_B ? 4 : 2;
     if (L.active) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            sm[(L.prow * 4 + 0) * p.C + c + i] = q0[i];
-            sm[(L.prow * 4 + 1) * p.C + c + i] = q1[i];
-            sm[(L.prow * 4 + 2) * p.C + c + i] = q2[i];
-            sm[(L.prow * 4 + 3) * p.C + c + i] = q3[i];
+            sm[(L.prow * K + 0) * p.C + c + i] = q0[i];
+            sm[(L.prow * K + 1) * p.C + c + i] = q1[i];
+            if (HAS_B) {
+                sm[(L.prow * K + 2) * p.C + c + i] = q2[i];
+                sm[(L.prow * K + 3) * p.C + c + i] = q3[i];
+            }
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < p.C; i += 256) {
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        for (int r = 0; r < L.rows; ++r) {
-            t0 += sm[(r * 4 + 0) * p.C + i]; t1 += sm[(r * 4 + 1) * p.C + i];
-            t2 += sm[(r * 4 + 2) * p.C + i]; t3 += sm[(r * 4 + 3) * p.C + i];
-        }
+    float* sm2 = sm + L.rows * K * p.C;
+    block_colsum(sm, sm2, L.rows, K * p.C, [&](int col, float t) {
+        const int k = col / p.C, i = col - k * p.C;
         float* st = p.stats + (size_t)n * p.stats_nstride + i;
         const size_t ao = (size_t)n * p.aff_nstride + i;
-        if (red_a) { atomicAdd(st, t0); atomicAdd(st + p.stats_cstride, t1 * p.invstd_a[ao]); }
-        if (red_b) { atomicAdd(st + 2 * p.stats_cstride, t2); atomicAdd(st + 3 * p.stats_cstride, t3 * p.invstd_b[ao]); }
-    }
+        if (k == 0 && red_a) atomicAdd(st, t);
+        if (k == 1 && red_a) atomicAdd(st + p.stats_cstride, t * p.invstd_a[ao]);
+        if (k == 2 && red_b) atomicAdd(st + 2 * p.stats_cstride, t);
+        if (k == 3 && red_b) atomicAdd(st + 3 * p.stats_cstride, t * p.invstd_b[ao]);
+    });
 }
 
 // backward pass 2:  da = sa*g + Pa*a + Qa  with  Pa = -sa*inv*c2, Qa = -sa*c1 + sa*inv*c2*mean  (batch-stat norm),
 // Pa = Qa = 0 for a constant affine; same for b with gb = g*actb'(ub).
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kernel(const AffArgs p) {
-    constexpr int U = HAS_B ? 1 : 2;
+    constexpr int U = 2;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     if (!L.active) return;
@@ -258,30 +310,33 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
     const bool wa = p.da.ptr != nullptr, wb = HAS_B && p.db.ptr != nullptr;
 
     for (int base = begin + L.prow; base < end; base += L.rows * U) {
-        float g[U][8], va[U][8], vb[U][8];
+        Raw8<T> rg[U], ra[U], rb[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int px = base + u * L.rows;
             if (px < end) {
-                Vec8<T>::load(vptr<T>(p.dy, pix0 + px, c), g[u]);
-                Vec8<T>::load(vptr<T>(p.a, pix0 + px, c), va[u]);
-                if (HAS_B) Vec8<T>::load(vptr<T>(p.b, pix0 + px, c), vb[u]);
+                rg[u].load(vptr<T>(p.dy, pix0 + px, c));
+                ra[u].load(vptr<T>(p.a, pix0 + px, c));
+                if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int px = base + u * L.rows;
             if (px < end) {
-                float da[8], db[8];
+                float g[8], va[8], vb[8], da[8], db[8];
+                rg[u].unpack(g);
+                ra[u].unpack(va);
+                if (HAS_B) rb[u].unpack(vb);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float ub = 0.f, t = fmaf(va[u][i], sa[i], ta[i]);
-                    if (HAS_B) { ub = fmaf(vb[u][i], sb[i], tb[i]); t += act_fwd(ub, actb); }
-                    const float gg = g[u][i] * act_bwd_from_u(t, act);
-                    da[i] = fmaf(sa[i], gg, fmaf(Pa[i], va[u][i], Qa[i]));
+                    float ub = 0.f, t = fmaf(va[i], sa[i], ta[i]);
+                    if (HAS_B) { ub = fmaf(vb[i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                    const float gg = g[i] * act_bwd_from_u(t, act);
+                    da[i] = fmaf(sa[i], gg, fmaf(Pa[i], va[i], Qa[i]));
                     if (HAS_B) {
                         const float gb = gg * act_bwd_from_u(ub, actb);
-                        db[i] = fmaf(sb[i], gb, fmaf(Pb[i], vb[u][i], Qb[i]));
+                        db[i] = fmaf(sb[i], gb, fmaf(Pb[i], vb[i], Qb[i]));
                     }
                 }
                 if (wa) {
@@ -483,7 +538,7 @@ extern "C" int semb_affine_act_fwd(const semb_affine_desc* d, const semb_tensor*
     p.dstats = reinterpret_cast<double*>(stats); p.stats_nstride = stats_nstride; p.stats_cstride = stats_cstride;
     p.ppb = pick_ppb(d->HW, d->N, d->C);
     dim3 grid(cdiv(d->HW, p.ppb), d->N);
-    const size_t smem = stats ? (size_t)(256 / (d->C / 8)) * 2 * d->C * sizeof(float) : 0;
+    const size_t smem = stats ? ((size_t)(256 / (d->C / 8)) * 2 * d->C + 256) * sizeof(float) : 0;
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_fwd_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_fwd");
@@ -511,7 +566,7 @@ extern "C" int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_
     p.stats = sums; p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
     p.ppb = pick_ppb(d->HW, d->N, d->C);
     dim3 grid(cdiv(d->HW, p.ppb), d->N);
-    const size_t smem = (size_t)(256 / (d->C / 8)) * 4 * d->C * sizeof(float);
+    const size_t smem = ((size_t)(256 / (d->C / 8)) * (b ? 4 : 2) * d->C + 256) * sizeof(float);
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_bwd_reduce_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_bwd_reduce");

@@ -183,11 +183,12 @@ def test_conv_transpose(case, dtype):
 
 @pytest.mark.parametrize("dtype", DT)
 @pytest.mark.parametrize("per_sample", [False, True])
-def test_norm_affine_fwd_bwd(dtype, per_sample):
+@pytest.mark.parametrize("c", [24, 5, 120, 426])       # 3, 1, 15 and 54 channel groups: every block-reduction layout
+def test_norm_affine_fwd_bwd(dtype, per_sample, c):
     """y = relu(BN_a(a) + relu(BN_b(b))) with batch statistics (res_path unit) and the InstanceNorm variant,
     forward + both gradient passes against torch autograd on the oracle formulas."""
     lib = L.load()
-    n, h, w_, c = 3, 10, 12, 24
+    n, h, w_ = 3, 10, 12
     cp = U.pad8(c)
     g = torch.Generator().manual_seed(3)
     a = _prep(torch.randn(n, h, w_, c, generator=g) * 2 + 0.5, dtype)
