@@ -11,32 +11,12 @@
 //
 // Replaces F.conv2d / its data gradient under keras.layers.Conv2D for the stride-1 3x3 and 1x1 layers
 // (UNet_Segmentation.py:421,465-468,490-499; CycleGAN.py:327,333).
-#include "common.cuh"
+#include "tc_common.cuh"
 #include <stdlib.h>
 #include <math.h>
 
 namespace semb {
 
-constexpr int TILE_H = 16, TILE_W = 8;          // 128 output pixels = UMMA M
-constexpr int TC_THREADS = 128;
-
-struct TcPlan { int KC, NC, nchunks, kchunks, tmem_cols; };
-
-// Shared-memory budget: A planes + B taps must leave room for 2 CTAs per SM.
-static inline TcPlan tc_plan(int Cin, int Cout, int taps) {
-    TcPlan p;
-    const int c16 = (Cout + 15) / 16 * 16;
-    p.nchunks = (c16 + 255) / 256;
-    p.NC = ((c16 + p.nchunks - 1) / p.nchunks + 15) / 16 * 16;
-    const int cin16 = (Cin + 15) / 16 * 16;
-    int kc = 64;
-    while (kc > 16 && (size_t)taps * kc * p.NC * 2 + (size_t)kc * 362 > 96 * 1024) kc >>= 1;
-    if (kc > cin16) kc = cin16 <= 16 ? 16 : (cin16 <= 32 ? 32 : 64);
-    p.KC = kc;
-    p.kchunks = (Cin + kc - 1) / kc;
-    p.tmem_cols = p.NC <= 32 ? 32 : (p.NC <= 64 ? 64 : (p.NC <= 128 ? 128 : 256));
-    return p;
-}
 
 // ---- weight packing ----------------------------------------------------------------------------------
 // dst[nchunk][kchunk][tap][KC/8][NC][8] (bf16)  <-  w[r][s][ci][co] (fp32 HWIO), zero padded.
@@ -64,112 +44,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int R, int S, i
     }
 }
 
-// ---- PTX wrappers ----------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    // Plain try_wait spin (measured: a suspend-time hint or a __nanosleep back-off make the hand-offs slower and the
-    // kernels are hand-off-latency bound).  Bounded: a descriptor bug must trap, not hang the GPU box.
-    const long long t0 = clock64();
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-// warp-collective wait: one lane polls, the warp re-converges on it
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-    __syncwarp();
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-template <int COLS>
-__device__ __forceinline__ void tmem_alloc(uint32_t slot) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3 at bit 17, M>>4 at bit 24
-__device__ __forceinline__ uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-    const int sz = valid ? 16 : 0;      // src-size 0 -> the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// asynchronous arrive: fires when all cp.async issued so far by this thread have landed (no wait in the producer)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// Sum 16 values across the 32 lanes of a warp.  Each round exchanges half of the remaining values with the partner
-// lane (offset 16, 8, 4, 2) and keeps the other half; a last round (offset 1) adds the two partial totals.  Result:
-// w[0] of lane l holds the warp total of value index (l >> 1) & 15 (same value in lanes l and l^1).  Fixed order.
-__device__ __forceinline__ void warp_reduce16(float (&w)[16], int lane) {
-#pragma unroll
-    for (int h = 8, o = 16; h >= 1; h >>= 1, o >>= 1) {
-        const bool up = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < h; ++i) {
-            const float send = up ? w[i] : w[i + h];
-            const float keep = up ? w[i + h] : w[i];
-            w[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    w[0] += __shfl_xor_sync(0xffffffffu, w[0], 1);
-}
 
 // ---- forward / data-gradient conv: persistent, warp-specialised -----------------------------------------------
 //   warps 0-3  epilogue   : drain TMEM (lane = output pixel), bias, moments, bf16 store at the channel offset
@@ -180,55 +54,8 @@ __device__ __forceinline__ void warp_reduce16(float (&w)[16], int lane) {
 constexpr int FW_THREADS = 288;
 constexpr int FW_PRODUCER0 = 160;      // first producer thread
 
-struct TcArgs {
-    int N, H, W, OH, OW, Cin, Cout, R, S, pad_t, pad_l, pad_mode;
-    const bf16* x; int x_pitch, x_coff;
-    bf16* y; int y_pitch, y_coff;
-    const bf16* wp; const float* bias;
-    double* stats; int stats_nstride, stats_cstride;
-    int accumulate;
-    int tiles_x, tiles_y, total_tiles;
-    TcPlan p;
-    int plane_bytes, halo_h, halo_w;
-    int stages, b_resident, a_bytes, b_bytes, stage_bytes;
-};
-
-// Walks the tiles t = first + i*stride of an (N, tiles_y, tiles_x) grid without integer divisions in the loop.
-struct TileIter {
-    int n, ty, tx, dn, dty, dtx, tiles_x, tiles_y;
-    __device__ __forceinline__ TileIter(int first, int stride, int tiles_x_, int tiles_y_) : tiles_x(tiles_x_), tiles_y(tiles_y_) {
-        const int tpi = tiles_x * tiles_y;
-        n = first / tpi;
-        int rem = first - n * tpi;
-        ty = rem / tiles_x;
-        tx = rem - ty * tiles_x;
-        dn = stride / tpi;
-        rem = stride - dn * tpi;
-        dty = rem / tiles_x;
-        dtx = rem - dty * tiles_x;
-    }
-    __device__ __forceinline__ void next() {
-        tx += dtx; ty += dty; n += dn;
-        if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
-        if (ty >= tiles_y) { ty -= tiles_y; ++n; }
-    }
-};
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// NCT > 0: all output channels fit NCT (16 or 32) accumulator columns -- the HBM-bound high-resolution layers.  Their
-// epilogue keeps the per-channel moments of a thread's pixel in REGISTERS across all tiles of the CTA and reduces across
-// lanes once per CTA (or per sample), instead of 16 shuffles per 8 channels per tile.  NCT == 0: generic path.
-template <int COLS, int STAGES, int NCT>
+// KR: kernel size (1 or 3), compile-time so that the MMA issue loop unrolls into straight-line code.
+template <int COLS, int STAGES, int NCT, int KR>
 __global__ void __launch_bounds__(FW_THREADS, NCT == 32 ? 2 : 3) conv_tc_kernel(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], b_full;
@@ -302,7 +129,7 @@ __global__ void __launch_bounds__(FW_THREADS, NCT == 32 ? 2 : 3) conv_tc_kernel(
                 const uint32_t sbase = ring_u32 + stage * a.stage_bytes;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    if (own[j]) {
+                    if (own[j] && !(a.dbg & 1)) {
                         const uint32_t dst = sbase + (ptid + 128 * j) * 16;
                         const bf16* s = src[j] + c0;
                         for (int k8 = 0; k8 < planes; ++k8) cp_async16(dst + k8 * a.plane_bytes, s + k8 * 8, v[j] && k8 < real);
@@ -319,12 +146,18 @@ __global__ void __launch_bounds__(FW_THREADS, NCT == 32 ? 2 : 3) conv_tc_kernel(
         }
         cp_async_wait<0>();
     } else if (warp == 4) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
+        // ============================== MMA issuer (whole warp converged, elect.sync per instruction) ===============
+        {
+            // The single issuing thread is the critical path of a tile (ncu, round 1: ~50 instructions per MMA with
+            // run-time tap loops): taps and K steps are unrolled, the descriptors differ only in their low words.
+            constexpr int HALO_W = TILE_W + KR - 1;
             const uint32_t idesc = instr_desc(128, NC, 0, 0);
-            const uint64_t ad0 = smem_desc(ring_u32, a.plane_bytes, a.halo_w * 16);
+            const uint64_t ad0 = smem_desc(ring_u32, a.plane_bytes, HALO_W * 16);
             const uint64_t bd0 = smem_desc(a.b_resident ? smem_u32(smem) : ring_u32 + a.a_bytes, NC * 16, 128);
-            const uint32_t pl = (uint32_t)a.plane_bytes >> 4;
+            const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
+            const uint32_t pl2 = 2 * ((uint32_t)a.plane_bytes >> 4);  // 16-byte units per K step of the A planes
+            const uint32_t nc2 = 2 * (uint32_t)NC;                    // ... of the weight image
             const uint32_t stage16 = (uint32_t)a.stage_bytes >> 4;
             const uint32_t btap = (uint32_t)(KC / 8) * NC;            // 16-byte units between taps of the weight image
             if (a.b_resident) mbar_wait(smem_u32(&b_full), 0);
@@ -341,23 +174,22 @@ __global__ void __launch_bounds__(FW_THREADS, NCT == 32 ? 2 : 3) conv_tc_kernel(
                     tc_fence_after();
                     const int ksteps = (min(KC, a.Cin - kc * KC) + 15) / 16;
                     const uint32_t soff = (uint32_t)stage * stage16;
-                    const uint64_t ad_s = ad0 + soff;
-                    const uint64_t bd_s = bd0 + (a.b_resident ? 0u : soff);
-                    uint32_t acc = kc != 0;
-                    uint32_t boff = 0;
-                    for (int r = 0; r < a.R; ++r) {
-                        for (int s = 0; s < a.S; ++s, boff += btap) {
-                            const uint32_t aoff = (uint32_t)(r * a.halo_w + s);
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                umma_bf16(dcol, ad_s + (aoff + 2 * ks * pl), bd_s + (boff + (uint32_t)(2 * ks * NC)), idesc, acc);
-                                acc = 1;
-                            }
+                    const uint32_t a_lo = a_lo0 + soff;
+                    const uint32_t b_lo = b_lo0 + (a.b_resident ? 0u : soff);
+#pragma unroll
+                    for (int tap = 0; tap < KR * KR; ++tap) {
+                        const uint32_t at = a_lo + (uint32_t)((tap / KR) * HALO_W + (tap % KR));
+                        const uint32_t bt = b_lo + (uint32_t)tap * btap;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {            // KC <= 64: at most four K steps per chunk
+                            if (ks < ksteps && !(a.dbg & 2))
+                                umma_bf16_elect(dcol, at + ks * pl2, a_hi, bt + ks * nc2, b_hi, idesc, (tap | ks) != 0 ? 1u : (uint32_t)(kc != 0));
                         }
                     }
-                    umma_commit(smem_u32(&empty_bar[stage]));
+                    umma_commit_elect(smem_u32(&empty_bar[stage]));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(&acc_full[buf]));
+                umma_commit_elect(smem_u32(&acc_full[buf]));
             }
         }
     } else {
@@ -431,11 +263,11 @@ __global__ void __launch_bounds__(FW_THREADS, NCT == 32 ? 2 : 3) conv_tc_kernel(
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
                         }
-                        if (a.stats && pvalid) {
+                        if (a.stats && pvalid && !(a.dbg & 8)) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) { s1[c + i] += v[i]; s2[c + i] = fmaf(v[i], v[i], s2[c + i]); }
                         }
-                        if (pvalid && cvalid) {
+                        if (pvalid && cvalid && !(a.dbg & 4)) {
                             if (a.accumulate) {
                                 float o[8];
                                 Vec8<bf16>::load(yp + c, o);
@@ -628,11 +460,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
             cp_async_arrive_noinc(smem_u32(&full_bar[stage]));
         }
         cp_async_wait<0>();
-    } else if (lane == 0) {
-        // ===================== MMA issuer =====================
+    } else {
+        // ===================== MMA issuer (whole warp converged, elect.sync per instruction) =====================
         const uint32_t idesc = instr_desc(128, NCH, 1, 1);
         const uint64_t ad0 = smem_desc(smem_base, TILE_W * 16, a.plane_a);
         const uint64_t bd0 = smem_desc(smem_base + b_off, a.halo_w * 16, a.plane_b);
+        const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
         for (int it = 0; it < ntiles; ++it) {
             const int stage = it % WG_STAGES;
             mbar_wait(smem_u32(&full_bar[stage]), (it / WG_STAGES) & 1);
@@ -643,14 +477,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
                 const int tap = tap0 + tl, r = tap / a.S, s = tap % a.S;
 #pragma unroll
                 for (int ks = 0; ks < TILE_H / 2; ++ks) {       // 16 pixels (two rows of 8) per MMA
-                    const uint64_t ad = ad0 + soff + ks * (2 * TILE_W);
-                    const uint64_t bd = bd0 + soff + ((2 * ks + r) * a.halo_w + s);
-                    umma_bf16(tmem + tl * NCH, ad, bd, idesc, (it | ks) != 0);
+                    umma_bf16_elect(tmem + tl * NCH, a_lo0 + soff + ks * (2 * TILE_W), a_hi,
+                                    b_lo0 + soff + ((2 * ks + r) * a.halo_w + s), b_hi, idesc, (it | ks) != 0);
                 }
             }
-            umma_commit(smem_u32(&empty_bar[stage]));
+            umma_commit_elect(smem_u32(&empty_bar[stage]));
         }
-        umma_commit(smem_u32(&done_bar));
+        umma_commit_elect(smem_u32(&done_bar));
     }
     // ---- flush: TMEM lane = co, columns = [tap][ci]; lanes of a warp hit consecutive co -> coalesced reductions
     if (warp < 4) {
@@ -762,11 +595,13 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_stacked_kernel(const WsAr
             if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
         cp_async_wait<0>();
-    } else if (lane == 0) {
-        // ===================== MMA issuer =====================
+    } else {
+        // ===================== MMA issuer (whole warp converged, elect.sync per instruction) =====================
         const uint32_t idesc = instr_desc(128, NB, 1, 1);
         const uint64_t ad0 = smem_desc(smem_base, TILE_W * 16, WS_PLANE_A);
         const uint64_t bd0 = smem_desc(smem_base + a.a_bytes, TILE_W * 16, WS_PLANE_B);
+        const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
         const uint32_t stage16 = (uint32_t)a.stage_bytes >> 4;
         int stage = 0;
         uint32_t phase = 0;
@@ -779,14 +614,14 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_stacked_kernel(const WsAr
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
                 for (int ks = 0; ks < TILE_H / 2; ++ks) {           // 16 pixels (two rows of 8) per MMA
-                    umma_bf16(tmem + r * NB, ad0 + (soff + (uint32_t)(2 * ks + r) * TILE_W), bd0 + (soff + (uint32_t)(2 * ks) * TILE_W),
-                              idesc, (i | ks) != 0);
+                    umma_bf16_elect(tmem + r * NB, a_lo0 + soff + (uint32_t)(2 * ks + r) * TILE_W, a_hi,
+                                    b_lo0 + soff + (uint32_t)(2 * ks) * TILE_W, b_hi, idesc, (i | ks) != 0);
                 }
             }
-            umma_commit(smem_u32(&empty_bar[stage]));
+            umma_commit_elect(smem_u32(&empty_bar[stage]));
             if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&done_bar));
+        umma_commit_elect(smem_u32(&done_bar));
     }
     // ---- flush: TMEM lane = (s * p + k8) * 8 + c, columns = [r][co]; a thread owns one (s, ci) row of the gradient
     if (warp < 4) {
@@ -848,6 +683,9 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     SEMB_REQUIRE(view_ok(x) && view_ok(y) && x->C == g->Cin && y->C == g->Cout, SEMB_EALIGN, "conv_tc: bad tensor views");
     SEMB_REQUIRE(g->N > 0 && g->OH > 0 && g->OW > 0 && g->pad_t >= 0 && g->pad_l >= 0 && g->pad_t < g->R + TILE_H && g->pad_l < g->S + TILE_W,
                  SEMB_ESHAPE, "conv_tc: bad geometry");
+    // zero padding is the TMA's out-of-bounds fill: conv_tma.cu; reflect padding keeps the cp.async producers below
+    if (g->pad_mode == SEMB_PAD_ZERO && !getenv("SEMB_TC_NO_TMA"))
+        return conv_tma_launch(g, x, w_packed, bias, y, stats, stats_nstride, stats_cstride, accumulate, stream);
     TcArgs a{};
     a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
     a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
@@ -874,16 +712,20 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     int per_sm = 512 / cols;                                  // TMEM columns
     if ((size_t)per_sm * (smem + 2048) > 220 * 1024) per_sm = (int)(220 * 1024 / (smem + 2048));   // shared memory
     if (per_sm > 3) per_sm = 3;                               // registers: 288 threads x <= 72
+    if (const char* env = getenv("SEMB_TC_DEBUG")) a.dbg = atoi(env);
+    if (const char* env = getenv("SEMB_TC_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
     if (a.p.NC == 32 && per_sm > 2) per_sm = 2;
     if (per_sm < 1) per_sm = 1;
     int gx = 148 * per_sm;
     if (gx > a.total_tiles) gx = a.total_tiles;
     dim3 grid(gx, a.p.nchunks);
     cudaError_t e = cudaSuccess;
-#define SEMB_TC_LAUNCH2(COLS, ST, NCT)                                                                                \
-    e = cudaFuncSetAttribute(conv_tc_kernel<COLS, ST, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    if (e == cudaSuccess) conv_tc_kernel<COLS, ST, NCT><<<grid, FW_THREADS, smem, as_stream(stream)>>>(a);
-#define SEMB_TC_LAUNCH(COLS, NCT)                                                                                     \
+#define SEMB_TC_LAUNCH3(COLS, ST, NCT, KR)                                                                                \
+    e = cudaFuncSetAttribute(conv_tc_kernel<COLS, ST, NCT, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    if (e == cudaSuccess) conv_tc_kernel<COLS, ST, NCT, KR><<<grid, FW_THREADS, smem, as_stream(stream)>>>(a);
+#define SEMB_TC_LAUNCH2(COLS, ST, NCT)                                                                                    \
+    if (g->R == 3) { SEMB_TC_LAUNCH3(COLS, ST, NCT, 3) } else { SEMB_TC_LAUNCH3(COLS, ST, NCT, 1) }
+#define SEMB_TC_LAUNCH(COLS, NCT)                                                                                         \
     if (a.stages == 4) { SEMB_TC_LAUNCH2(COLS, 4, NCT) } else if (a.stages == 3) { SEMB_TC_LAUNCH2(COLS, 3, NCT) } else { SEMB_TC_LAUNCH2(COLS, 2, NCT) }
     switch (cols) {
         case 32: SEMB_TC_LAUNCH(32, 16) break;       // NC == 16
@@ -894,6 +736,7 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     }
 #undef SEMB_TC_LAUNCH
 #undef SEMB_TC_LAUNCH2
+#undef SEMB_TC_LAUNCH3
     if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
     return check_launch("conv_tc");
 }

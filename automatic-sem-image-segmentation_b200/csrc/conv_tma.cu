@@ -1,0 +1,401 @@
+// Zero-padded stride-1 3x3 / 1x1 convolution (forward and data gradient) on tcgen05 with TMA-staged halo tiles.
+//
+// Same implicit GEMM as conv_tc.cu (M = 16x8 output pixels, N = Cout, K = taps x Cin, halo tile staged once as
+// channel-group planes, taps = shifted UMMA descriptors), but the planes are written by the TMA unit: one elected
+// thread issues ONE cp.async.bulk.tensor per 8-channel plane -- a 4-D box {8 channels, halo_w, halo_h, 1} of the NHWC
+// tensor, whose dense shared-memory image [halo_h][halo_w][8] IS the no-swizzle K-major core-matrix layout -- and
+// the zero padding is the tensor map's out-of-bounds fill.  Round-1 ablation (scripts/ablate_conv.sh) showed the
+// cp.async version to be bound by the per-pixel address arithmetic of its 128 producer threads and by its single
+// epilogue warpgroup (~77 us for a 256x256x32 batch with loads, MMAs and stores all switched off), not by HBM.
+//
+//   warps 0-3  epilogue group 0 : accumulator buffer 0 (even tiles of the CTA)
+//   warps 4-7  epilogue group 1 : accumulator buffer 1 (odd tiles)
+//   warp  8    MMA issuer (one thread)
+//   warp  9    TMA producer (one thread)
+//
+// Replaces F.conv2d / its data gradient under keras.layers.Conv2D (UNet_Segmentation.py:421,465-468,490-499).
+#include "tc_common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace semb {
+
+constexpr int TM_THREADS = 320;
+constexpr int TM_MAX_STAGES = 6;
+
+struct TmArgs {
+    TcArgs t;
+    int plane_pitch;      // bytes between channel-group planes of a stage (multiple of 128)
+    int plane_box;        // bytes the TMA writes per plane (halo_h * halo_w * 16)
+    int nstages;
+};
+
+// all three are called by a CONVERGED warp; elect.sync picks the lane that issues (see umma_bf16_elect)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n\t}"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                 "@e cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int COLS, int NCT, int KR>
+__global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs args, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TM_MAX_STAGES], empty_bar[TM_MAX_STAGES], acc_full[2], acc_empty[2], b_full;
+    __shared__ uint32_t tmem_slot;
+    const TcArgs& a = args.t;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KC = a.p.KC, NC = NCT > 0 ? NCT : a.p.NC, kchunks = a.p.kchunks;
+    const int nchunk = blockIdx.y;
+    const int nstages = args.nstages;
+    constexpr int HALO_W = TILE_W + KR - 1;
+    // smem (128-byte aligned): [resident B (optional)] [nstages x (A planes [+ B chunk])] [moment partials 2 x 8 x NC floats]
+    const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t ring_u32 = smem_base + (a.b_resident ? a.b_bytes : 0);
+    float* part_all = reinterpret_cast<float*>(smem + (a.b_resident ? a.b_bytes : 0) + (size_t)nstages * a.stage_bytes);
+    const int ntiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 8) tmem_alloc<COLS>(smem_u32(&tmem_slot));
+    if (tid == 0) {
+        for (int i = 0; i < nstages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
+        mbar_init(smem_u32(&b_full), 1);
+    }
+    // Planes beyond Cin (Cin % 16 == 8) are never written by the TMA: they must hold finite values (their weights are 0).
+    {
+        const int n16 = (nstages * a.stage_bytes) >> 4;
+        uint4* ring = reinterpret_cast<uint4*>(smem + (a.b_resident ? a.b_bytes : 0));
+        for (int i = tid; i < n16; i += TM_THREADS) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int i = tid; i < 16 * NC; i += TM_THREADS) part_all[i] = 0.f;
+    fence_proxy_async();            // generic-proxy zero fill -> later async-proxy (TMA / tensor core) accesses
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 9) {
+        // ============================== TMA producer (whole warp converged) ==============================
+        {
+            if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+            __syncwarp();
+            const int taps = KR * KR;
+            if (a.b_resident) {
+                mbar_expect_tx(smem_u32(&b_full), (uint32_t)a.b_bytes);
+                bulk_load(smem_base, a.wp + (size_t)nchunk * kchunks * taps * KC * NC, (uint32_t)a.b_bytes, smem_u32(&b_full));
+            }
+            TileIter it(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
+            int stage = 0;
+            uint32_t phase = 1;
+            for (int ti = 0; ti < ntiles; ++ti, it.next()) {
+                const int y0 = it.ty * TILE_H - a.pad_t, x0 = it.tx * TILE_W - a.pad_l;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase);
+                    const int c0 = kc * KC;
+                    const int real = min(KC, a.Cin - c0) >> 3;             // planes that exist in the tensor
+                    const uint32_t sbase = ring_u32 + stage * a.stage_bytes;
+                    const uint32_t bar = smem_u32(&full_bar[stage]);
+                    mbar_expect_tx(bar, (uint32_t)(real * args.plane_box + (a.b_resident ? 0 : a.b_bytes)));
+                    if (!(a.dbg & 1)) {
+                        for (int k8 = 0; k8 < real; ++k8)
+                            tma_load_4d(sbase + k8 * args.plane_pitch, &xmap, a.x_coff + c0 + k8 * 8, x0, y0, it.n, bar);
+                    } else {
+                        // ablation: complete the transaction count without moving data
+                        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+                                     "@e mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n\t}" ::"r"(bar), "r"((uint32_t)(real * args.plane_box)) : "memory");
+                    }
+                    if (!a.b_resident)
+                        bulk_load(sbase + a.a_bytes, a.wp + ((size_t)nchunk * kchunks + kc) * taps * KC * NC, (uint32_t)a.b_bytes, bar);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ============================== MMA issuer (whole warp converged, elect.sync per instruction) ===============
+        {
+            const uint32_t idesc = instr_desc(128, NC, 0, 0);
+            const uint64_t ad0 = smem_desc(ring_u32, args.plane_pitch, HALO_W * 16);
+            const uint64_t bd0 = smem_desc(a.b_resident ? smem_base : ring_u32 + a.a_bytes, NC * 16, 128);
+            const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
+            const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
+            const uint32_t pl2 = 2 * ((uint32_t)args.plane_pitch >> 4);
+            const uint32_t nc2 = 2 * (uint32_t)NC;
+            const uint32_t stage16 = (uint32_t)a.stage_bytes >> 4;
+            const uint32_t btap = (uint32_t)(KC / 8) * NC;
+            if (a.b_resident) mbar_wait(smem_u32(&b_full), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ti = 0; ti < ntiles; ++ti) {
+                const int buf = ti & 1;
+                mbar_wait(smem_u32(&acc_empty[buf]), ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t dcol = tmem + buf * NC;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const int ksteps = (min(KC, a.Cin - kc * KC) + 15) / 16;
+                    const uint32_t soff = (uint32_t)stage * stage16;
+                    const uint32_t a_lo = a_lo0 + soff;
+                    const uint32_t b_lo = b_lo0 + (a.b_resident ? 0u : soff);
+#pragma unroll
+                    for (int tap = 0; tap < KR * KR; ++tap) {
+                        const uint32_t at = a_lo + (uint32_t)((tap / KR) * HALO_W + (tap % KR));
+                        const uint32_t bt = b_lo + (uint32_t)tap * btap;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {            // KC <= 64: at most four K steps per chunk
+                            if (ks < ksteps && !(a.dbg & 2))
+                                umma_bf16_elect(dcol, at + ks * pl2, a_hi, bt + ks * nc2, b_hi, idesc, (tap | ks) != 0 ? 1u : (uint32_t)(kc != 0));
+                        }
+                    }
+                    umma_commit_elect(smem_u32(&empty_bar[stage]));
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_elect(smem_u32(&acc_full[buf]));
+            }
+        }
+    } else {
+        // ============================== epilogue (two groups, one accumulator buffer each) ==============================
+        const int grp = warp >> 2;                        // 0 or 1 = accumulator buffer
+        const int wq = warp & 3;                          // TMEM lane quarter this warp may read
+        const int etid = tid & 127;
+        float* part = part_all + grp * 8 * NC;
+        const int c_begin = nchunk * NC;
+        int cur_n = -1;
+        auto combine = [&](int n) {
+            // the group's 128 threads: combine the four warps' partial moments in a fixed order, one fp64 atomic per channel
+            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            for (int i = etid; i < NC; i += 128) {
+                const int c = c_begin + i;
+                if (c < a.Cout) {
+                    const float t1 = ((part[i] + part[NC + i]) + part[2 * NC + i]) + part[3 * NC + i];
+                    const float t2 = ((part[4 * NC + i] + part[5 * NC + i]) + part[6 * NC + i]) + part[7 * NC + i];
+                    double* st = a.stats + (size_t)n * a.stats_nstride + c;
+                    atomicAdd(st, (double)t1);
+                    atomicAdd(st + a.stats_cstride, (double)t2);
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+            for (int i = etid; i < 8 * NC; i += 128) part[i] = 0.f;
+            asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+        };
+        const int m = wq * 32 + lane;
+        const int my = m / TILE_W, mx = m % TILE_W;
+        const uint32_t acc_addr = tmem + ((uint32_t)(wq * 32) << 16) + grp * NC;
+        const uint32_t full_u32 = smem_u32(&acc_full[grp]), empty_u32 = smem_u32(&acc_empty[grp]);
+        TileIter it(blockIdx.x + grp * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
+        if constexpr (NCT > 0) {
+            float s1[NCT], s2[NCT];
+#pragma unroll
+            for (int i = 0; i < NCT; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+            auto flush_regs = [&](int n) {
+#pragma unroll
+                for (int q = 0; q < NCT / 16; ++q) {
+                    float w[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = s1[q * 16 + i];
+                    warp_reduce16(w, lane);
+                    if ((lane & 1) == 0) part[wq * NC + q * 16 + (lane >> 1)] = w[0];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) w[i] = s2[q * 16 + i];
+                    warp_reduce16(w, lane);
+                    if ((lane & 1) == 0) part[(4 + wq) * NC + q * 16 + (lane >> 1)] = w[0];
+                }
+#pragma unroll
+                for (int i = 0; i < NCT; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+                combine(n);
+            };
+            for (int ti = grp, k = 0; ti < ntiles; ti += 2, ++k, it.next()) {
+                if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) flush_regs(cur_n);
+                cur_n = it.n;
+                const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
+                const bool pvalid = oy < a.OH && ox < a.OW;
+                bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
+                mbar_wait_warp(full_u32, k & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int h = 0; h < NCT / 16; ++h) {
+                    float v16[16];
+                    tmem_ld16(acc_addr + h * 16, v16);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int c = h * 16 + half * 8;
+                        const bool cvalid = c < a.Cout;
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = v16[half * 8 + i];
+                        if (a.bias && cvalid) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
+                        }
+                        if (a.stats && pvalid && !(a.dbg & 8)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { s1[c + i] += v[i]; s2[c + i] = fmaf(v[i], v[i], s2[c + i]); }
+                        }
+                        if (pvalid && cvalid && !(a.dbg & 4)) {
+                            if (a.accumulate) {
+                                float o[8];
+                                Vec8<bf16>::load(yp + c, o);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] += o[i];
+                            }
+                            Vec8<bf16>::store(yp + c, v);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(empty_u32);
+            }
+            if (a.stats && cur_n >= 0) flush_regs(a.stats_nstride != 0 ? cur_n : 0);
+        } else {
+            for (int ti = grp, k = 0; ti < ntiles; ti += 2, ++k, it.next()) {
+                if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) combine(cur_n);
+                cur_n = it.n;
+                const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
+                const bool pvalid = oy < a.OH && ox < a.OW;
+                bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
+                mbar_wait_warp(full_u32, k & 1);
+                tc_fence_after();
+                for (int g = 0; g < NC / 8; ++g) {
+                    const int c = c_begin + g * 8;
+                    float v[8];
+                    tmem_ld8(acc_addr + g * 8, v);
+                    const bool cvalid = c < a.Cout;
+                    if (a.bias && cvalid) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
+                    }
+                    if (a.stats) {
+                        float w[16];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { w[i] = pvalid ? v[i] : 0.f; w[8 + i] = w[i] * w[i]; }
+                        warp_reduce16(w, lane);
+                        if ((lane & 1) == 0) {
+                            const int idx = lane >> 1;                       // 0..7 sums, 8..15 squares
+                            part[((idx >> 3) * 4 + wq) * NC + g * 8 + (idx & 7)] += w[0];
+                        }
+                    }
+                    if (pvalid && cvalid && !(a.dbg & 4)) {
+                        if (a.accumulate) {
+                            float o[8];
+                            Vec8<bf16>::load(yp + c, o);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += o[i];
+                        }
+                        Vec8<bf16>::store(yp + c, v);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(empty_u32);
+            }
+            if (a.stats && cur_n >= 0) combine(a.stats_nstride != 0 ? cur_n : 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc<COLS>(tmem);
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Called by semb_conv2d_fwd_tc (conv_tc.cu) after argument validation, for SEMB_PAD_ZERO geometries.
+int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream) {
+    TmArgs A{};
+    TcArgs& a = A.t;
+    a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
+    a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
+    a.x = reinterpret_cast<const bf16*>(x->ptr); a.x_pitch = x->pitch; a.x_coff = x->coff;
+    a.y = reinterpret_cast<bf16*>(y->ptr); a.y_pitch = y->pitch; a.y_coff = y->coff;
+    a.wp = reinterpret_cast<const bf16*>(w_packed); a.bias = bias;
+    a.stats = reinterpret_cast<double*>(stats); a.stats_nstride = stats_nstride; a.stats_cstride = stats_cstride;
+    a.accumulate = accumulate;
+    a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
+    a.total_tiles = g->N * a.tiles_x * a.tiles_y;
+    a.p = tc_plan(g->Cin, g->Cout, g->R * g->S);
+    a.halo_h = TILE_H + g->R - 1; a.halo_w = TILE_W + g->S - 1;
+    A.plane_box = a.halo_h * a.halo_w * 16;
+    A.plane_pitch = (A.plane_box + 127) / 128 * 128;
+    a.plane_bytes = A.plane_pitch;
+    const int taps = g->R * g->S;
+    a.a_bytes = (a.p.KC / 8) * A.plane_pitch;
+    a.b_bytes = taps * a.p.KC * a.p.NC * 2;
+    a.b_resident = a.p.kchunks == 1;
+    a.stage_bytes = a.a_bytes + (a.b_resident ? 0 : a.b_bytes);
+    const size_t fixed = (a.b_resident ? a.b_bytes : 0) + (size_t)16 * a.p.NC * sizeof(float) + 128;
+    // ring depth: enough bytes in flight per SM for HBM (>= ~48 KB with two CTAs), within half of the shared memory
+    int nst = 2;
+    while (nst < TM_MAX_STAGES && (size_t)(nst + 1) * a.stage_bytes + fixed <= 100 * 1024 && (size_t)nst * a.stage_bytes < 48 * 1024) ++nst;
+    while (nst > 2 && (size_t)nst * a.stage_bytes + fixed > 220 * 1024) --nst;
+    if (const char* env = getenv("SEMB_TMA_STAGES")) { const int v = atoi(env); if (v >= 2 && v <= TM_MAX_STAGES) nst = v; }
+    A.nstages = nst;
+    a.stages = nst;
+    const size_t smem = (size_t)nst * a.stage_bytes + fixed;
+    SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tma: %zu bytes of shared memory needed", smem);
+    const int cols = 2 * a.p.NC <= 32 ? 32 : (2 * a.p.NC <= 64 ? 64 : (2 * a.p.NC <= 128 ? 128 : (2 * a.p.NC <= 256 ? 256 : 512)));
+    int per_sm = 512 / cols;                                  // TMEM columns
+    if ((size_t)per_sm * (smem + 2048) > 220 * 1024) per_sm = (int)(220 * 1024 / (smem + 2048));   // shared memory
+    if (per_sm > 2) per_sm = 2;                               // registers: 320 threads x <= 102
+    if (const char* env = getenv("SEMB_TC_DEBUG")) a.dbg = atoi(env);
+    if (const char* env = getenv("SEMB_TC_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
+    if (per_sm < 1) per_sm = 1;
+    int gx = 148 * per_sm;
+    if (gx > a.total_tiles) gx = a.total_tiles;
+    dim3 grid(gx, a.p.nchunks);
+
+    EncodeTiledFn enc = encode_tiled();
+    SEMB_REQUIRE(enc != nullptr, SEMB_ECUDA, "conv_tma: cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap xmap;
+    const cuuint64_t dims[4] = {(cuuint64_t)x->pitch, (cuuint64_t)g->W, (cuuint64_t)g->H, (cuuint64_t)g->N};
+    const cuuint64_t strides[3] = {(cuuint64_t)x->pitch * 2, (cuuint64_t)g->W * x->pitch * 2, (cuuint64_t)g->H * g->W * x->pitch * 2};
+    const cuuint32_t box[4] = {8u, (cuuint32_t)a.halo_w, (cuuint32_t)a.halo_h, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult cr = enc(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x->ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SEMB_REQUIRE(cr == CUDA_SUCCESS, SEMB_ECUDA, "conv_tma: cuTensorMapEncodeTiled failed (%d) for pitch %d W %d H %d N %d", (int)cr,
+                 x->pitch, g->W, g->H, g->N);
+
+    cudaError_t e = cudaSuccess;
+#define SEMB_TM_LAUNCH2(COLS, NCT, KR)                                                                                   \
+    e = cudaFuncSetAttribute(conv_tma_kernel<COLS, NCT, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    if (e == cudaSuccess) conv_tma_kernel<COLS, NCT, KR><<<grid, TM_THREADS, smem, as_stream(stream)>>>(A, xmap);
+#define SEMB_TM_LAUNCH(COLS, NCT)                                                                                        \
+    if (g->R == 3) { SEMB_TM_LAUNCH2(COLS, NCT, 3) } else { SEMB_TM_LAUNCH2(COLS, NCT, 1) }
+    switch (cols) {
+        case 32: SEMB_TM_LAUNCH(32, 16) break;       // NC == 16
+        case 64: SEMB_TM_LAUNCH(64, 32) break;       // NC == 32
+        case 128: SEMB_TM_LAUNCH(128, 0) break;
+        case 256: SEMB_TM_LAUNCH(256, 0) break;
+        default: SEMB_TM_LAUNCH(512, 0) break;
+    }
+#undef SEMB_TM_LAUNCH
+#undef SEMB_TM_LAUNCH2
+    if (e != cudaSuccess) { set_error("conv_tma: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
+    return check_launch("conv_tma");
+}
+
+}  // namespace semb

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default="conv,affine")
+    ap.add_argument("--shapes", default=None, help="override the conv shapes: 'H,Cin,Cout,k;...'")
     args = ap.parse_args()
     L.require_device()
     lib = L.load()
@@ -60,7 +61,8 @@ def main():
         return max(2, min(8, int(300e6 // max(nbytes, 1)) + 1))
 
     if "conv" in args.only:
-        for (hw, cin, cout, k) in CONV_SHAPES:
+        shapes = CONV_SHAPES if not args.shapes else [tuple(int(v) for v in t.split(",")) for t in args.shapes.split(";")]
+        for (hw, cin, cout, k) in shapes:
             p = k // 2
             geom = L.ConvGeom(n, hw, hw, hw, hw, cin, cout, k, k, 1, p, p, L.PAD_ZERO, L.BF16)
             gd = L.ConvGeom(n, hw, hw, hw, hw, cout, cin, k, k, 1, k - 1 - p, k - 1 - p, L.PAD_ZERO, L.BF16)

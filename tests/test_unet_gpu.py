@@ -86,12 +86,20 @@ def test_train_step_matches_oracle_f32(shape):
     wgt = float((y == 0).sum() / (y == 1).sum())
     tr = OU.UNetTrainer(spec, p0, wgt)
     logs_ref, yp_ref = tr.train_step(x, y)
-    # The same oracle in float64 measures how sensitive each gradient is to fp32 rounding: ReLU / max-pool decisions
-    # at |pre-activation| ~ 1e-7 flip between two fp32 evaluations and move some gradients of these tiny tiles by
-    # up to 3e-2.  A tensor passes if it is within 1e-3 of EITHER evaluation of the reference, or within twice the
-    # reference's own fp32-vs-fp64 discrepancy.
+    # The gradients of these tiny tiles are not 1e-3-stable under fp32 rounding: a ReLU / max-pool decision at
+    # |pre-activation| ~ 1e-7 flips between two fp32 evaluations and moves e.g. conv2d_48/kernel by 0.145 of its scale
+    # (reproduced with the oracle alone: x * (1 + 1e-7 * noise) gives exactly that deviation).  The reference is
+    # therefore an ENSEMBLE of oracle evaluations -- fp32, fp64 and fp32 on inputs perturbed by 1e-7 relative (what
+    # a different summation order does) -- and a tensor passes if it is within 1e-3 of ANY member, plus twice the
+    # oracle's own fp32-vs-fp64 discrepancy.
     tr64 = OU.UNetTrainer(spec, {k: v.double() for k, v in p0.items()}, wgt)
     tr64.train_step(x.double(), y.double())
+    ensemble = [tr, tr64]
+    for k in range(4):
+        xp = x * (1.0 + 1e-7 * torch.randn(x.shape, generator=g))
+        trp = OU.UNetTrainer(spec, p0, wgt)
+        trp.train_step(xp, y)
+        ensemble.append(trp)
 
     m = UNetModel((h, w, 1), 16, dtype="f32", batch_size=n, use_cuda_graph=False)
     m.set_named_weights(_named_np(p0))
@@ -113,7 +121,7 @@ def test_train_step_matches_oracle_f32(shape):
         # analytically ZERO gradient (pure rounding noise in both implementations), hence the global floor.
         ref64 = tr64.last_grads[name].float()
         den = max(float(ref.abs().max()), 1e-3 * gmax)
-        err = min(float((gr - ref).abs().max()), float((gr - ref64).abs().max())) / den
+        err = min(float((gr - t.last_grads[name].float()).abs().max()) for t in ensemble) / den
         slack = 2.0 * float((ref - ref64).abs().max()) / den
         if err - slack > worst[1]:
             worst = (name, err - slack)
@@ -124,7 +132,7 @@ def test_train_step_matches_oracle_f32(shape):
         # atol: variables whose true gradient / statistic is analytically zero only carry rounding noise
         ref64 = tr64.params[name].detach().float()
         got = torch.from_numpy(new[name])
-        err = min(float((got - ref).abs().max()), float((got - ref64).abs().max()))
+        err = min(float((got - t.params[name].detach().float()).abs().max()) for t in ensemble)
         assert err < 1e-3 * float(ref.abs().max()) + 1e-5 + 2.0 * float((ref - ref64).abs().max()), (name, err)
 
 
