@@ -8,10 +8,11 @@
 // cp.async version to be bound by the per-pixel address arithmetic of its 128 producer threads and by its single
 // epilogue warpgroup (~77 us for a 256x256x32 batch with loads, MMAs and stores all switched off), not by HBM.
 //
-//   warps 0-3  epilogue group 0 : accumulator buffer 0 (even tiles of the CTA)
-//   warps 4-7  epilogue group 1 : accumulator buffer 1 (odd tiles)
-//   warp  8    MMA issuer (one thread)
-//   warp  9    TMA producer (one thread)
+//   warps 0-3  epilogue group 0 : even tiles of the CTA
+//   warps 4-7  epilogue group 1 : odd tiles
+//   warps 8-9  MMA issuers      : even / odd tiles (ncu, round 1: ONE issuing warp needs ~280 instructions = 2100 cycles
+//                                 per 3x3 tile and never waits -- it, not HBM or the tensor pipe, paced the kernel)
+//   warp  10   TMA producer
 //
 // Replaces F.conv2d / its data gradient under keras.layers.Conv2D (UNet_Segmentation.py:421,465-468,490-499).
 #include "tc_common.cuh"
@@ -20,11 +21,16 @@
 
 namespace semb {
 
-constexpr int TM_THREADS = 320;
+constexpr int TM_THREADS = 352;
 constexpr int TM_MAX_STAGES = 6;
+
+constexpr int TM_MAX_ACC = 4;
 
 struct TmArgs {
     TcArgs t;
+    int tmem_cols;
+    int nmma;             // MMA issuer warps in use: 2 (ring split in halves) when the ring has >= 4 stages, else 1
+    int nacc;             // accumulator buffers in TMEM (2 or 4): the MMA -> epilogue -> MMA hand-off takes ~2-4k cycles
     int plane_pitch;      // bytes between channel-group planes of a stage (multiple of 128)
     int plane_box;        // bytes the TMA writes per plane (halo_h * halo_w * 16)
     int nstages;
@@ -47,16 +53,27 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int COLS, int NCT, int KR>
+__device__ __forceinline__ void tmem_alloc_rt(uint32_t slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// NCT: compile-time channel count of the register-moment epilogue (16 / 32, 0 = generic).  KR: kernel size.
+// KS: K steps per chunk when all input channels fit one chunk (1..4, straight-line MMA issue), 0 = run-time.
+template <int NCT, int KR, int KS>
 __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs args, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[TM_MAX_STAGES], empty_bar[TM_MAX_STAGES], acc_full[2], acc_empty[2], b_full;
+    __shared__ __align__(8) uint64_t full_bar[TM_MAX_STAGES], empty_bar[TM_MAX_STAGES], acc_full[TM_MAX_ACC], acc_empty[TM_MAX_ACC], b_full;
     __shared__ uint32_t tmem_slot;
     const TcArgs& a = args.t;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = a.p.KC, NC = NCT > 0 ? NCT : a.p.NC, kchunks = a.p.kchunks;
     const int nchunk = blockIdx.y;
     const int nstages = args.nstages;
+    const int nacc = args.nacc;
     constexpr int HALO_W = TILE_W + KR - 1;
     // smem (128-byte aligned): [resident B (optional)] [nstages x (A planes [+ B chunk])] [moment partials 2 x 8 x NC floats]
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -65,10 +82,10 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     float* part_all = reinterpret_cast<float*>(smem + (a.b_resident ? a.b_bytes : 0) + (size_t)nstages * a.stage_bytes);
     const int ntiles = (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == 8) tmem_alloc<COLS>(smem_u32(&tmem_slot));
+    if (warp == 8) tmem_alloc_rt(smem_u32(&tmem_slot), (uint32_t)args.tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < nstages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
+        for (int i = 0; i < TM_MAX_ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
         mbar_init(smem_u32(&b_full), 1);
     }
     // Planes beyond Cin (Cin % 16 == 8) are never written by the TMA: they must hold finite values (their weights are 0).
@@ -84,7 +101,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    if (warp == 9) {
+    if (warp == 10) {
         // ============================== TMA producer (whole warp converged) ==============================
         {
             if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
@@ -94,13 +111,18 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                 mbar_expect_tx(smem_u32(&b_full), (uint32_t)a.b_bytes);
                 bulk_load(smem_base, a.wp + (size_t)nchunk * kchunks * taps * KC * NC, (uint32_t)a.b_bytes, smem_u32(&b_full));
             }
+            // The ring is split in two halves, one per MMA warp (tile parity): every barrier has exactly one consumer
+            // that waits on each of its phases in order (a consumer that skipped phases could not tell them apart).
             TileIter it(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
-            int stage = 0;
-            uint32_t phase = 1;
+            const int half = args.nmma == 2 ? nstages >> 1 : nstages;
+            int slot0 = 0, slot1 = 0;
+            uint32_t ph0 = 1, ph1 = 1;
             for (int ti = 0; ti < ntiles; ++ti, it.next()) {
                 const int y0 = it.ty * TILE_H - a.pad_t, x0 = it.tx * TILE_W - a.pad_l;
+                const int w = args.nmma == 2 ? (ti & 1) : 0;
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(smem_u32(&empty_bar[stage]), phase);
+                    const int stage = w ? half + slot1 : slot0;
+                    mbar_wait(smem_u32(&empty_bar[stage]), w ? ph1 : ph0);
                     const int c0 = kc * KC;
                     const int real = min(KC, a.Cin - c0) >> 3;             // planes that exist in the tensor
                     const uint32_t sbase = ring_u32 + stage * a.stage_bytes;
@@ -116,13 +138,16 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                     }
                     if (!a.b_resident)
                         bulk_load(sbase + a.a_bytes, a.wp + ((size_t)nchunk * kchunks + kc) * taps * KC * NC, (uint32_t)a.b_bytes, bar);
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    if (w) { if (++slot1 == half) { slot1 = 0; ph1 ^= 1; } }
+                    else   { if (++slot0 == half) { slot0 = 0; ph0 ^= 1; } }
                 }
             }
         }
-    } else if (warp == 8) {
-        // ============================== MMA issuer (whole warp converged, elect.sync per instruction) ===============
-        {
+    } else if (warp >= 8) {
+        // ============================== MMA issuers (two warps, alternate tiles; converged, elect.sync per instruction) ====
+        if (warp - 8 < args.nmma) {
+            const int mw = warp - 8;
+            const int nmma = args.nmma;
             const uint32_t idesc = instr_desc(128, NC, 0, 0);
             const uint64_t ad0 = smem_desc(ring_u32, args.plane_pitch, HALO_W * 16);
             const uint64_t bd0 = smem_desc(a.b_resident ? smem_base : ring_u32 + a.a_bytes, NC * 16, 128);
@@ -133,39 +158,45 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
             const uint32_t stage16 = (uint32_t)a.stage_bytes >> 4;
             const uint32_t btap = (uint32_t)(KC / 8) * NC;
             if (a.b_resident) mbar_wait(smem_u32(&b_full), 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int ti = 0; ti < ntiles; ++ti) {
-                const int buf = ti & 1;
-                mbar_wait(smem_u32(&acc_empty[buf]), ((ti >> 1) & 1) ^ 1);
+            const int half = nmma == 2 ? nstages >> 1 : nstages;
+            int slot = 0, buf = mw;
+            uint32_t phase = 0, aphase = 1;
+            for (int ti = mw; ti < ntiles; ti += nmma) {
+                mbar_wait(smem_u32(&acc_empty[buf]), aphase);
                 tc_fence_after();
                 const uint32_t dcol = tmem + buf * NC;
                 for (int kc = 0; kc < kchunks; ++kc) {
+                    const int stage = mw * half + slot;
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
-                    const int ksteps = (min(KC, a.Cin - kc * KC) + 15) / 16;
+                    const int ksteps = KS > 0 ? KS : (min(KC, a.Cin - kc * KC) + 15) / 16;
                     const uint32_t soff = (uint32_t)stage * stage16;
                     const uint32_t a_lo = a_lo0 + soff;
                     const uint32_t b_lo = b_lo0 + (a.b_resident ? 0u : soff);
+                    if (!(a.dbg & 2)) {
 #pragma unroll
-                    for (int tap = 0; tap < KR * KR; ++tap) {
-                        const uint32_t at = a_lo + (uint32_t)((tap / KR) * HALO_W + (tap % KR));
-                        const uint32_t bt = b_lo + (uint32_t)tap * btap;
+                        for (int tap = 0; tap < KR * KR; ++tap) {
+                            const uint32_t at = a_lo + (uint32_t)((tap / KR) * HALO_W + (tap % KR));
+                            const uint32_t bt = b_lo + (uint32_t)tap * btap;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {            // KC <= 64: at most four K steps per chunk
-                            if (ks < ksteps && !(a.dbg & 2))
-                                umma_bf16_elect(dcol, at + ks * pl2, a_hi, bt + ks * nc2, b_hi, idesc, (tap | ks) != 0 ? 1u : (uint32_t)(kc != 0));
+                            for (int ks = 0; ks < (KS > 0 ? KS : 4); ++ks) {      // KC <= 64: at most four K steps per chunk
+                                if (KS > 0 || ks < ksteps)
+                                    umma_bf16_elect(dcol, at + ks * pl2, a_hi, bt + ks * nc2, b_hi, idesc,
+                                                    (tap | ks) != 0 ? 1u : (uint32_t)(kc != 0));
+                            }
                         }
                     }
                     umma_commit_elect(smem_u32(&empty_bar[stage]));
-                    if (++stage == nstages) { stage = 0; phase ^= 1; }
+                    if (++slot == half) { slot = 0; phase ^= 1; }
                 }
                 umma_commit_elect(smem_u32(&acc_full[buf]));
+                buf += nmma;                                // this warp's accumulator buffers: mw, mw + nmma, ...
+                if (buf >= nacc) { buf = mw; aphase ^= 1; }
             }
         }
     } else {
-        // ============================== epilogue (two groups, one accumulator buffer each) ==============================
-        const int grp = warp >> 2;                        // 0 or 1 = accumulator buffer
+        // ============================== epilogue (two groups, alternate tiles; accumulator buffer = tile % nacc) ==============================
+        const int grp = warp >> 2;                        // 0 or 1: even / odd tiles of the CTA
         const int wq = warp & 3;                          // TMEM lane quarter this warp may read
         const int etid = tid & 127;
         float* part = part_all + grp * 8 * NC;
@@ -190,8 +221,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
         };
         const int m = wq * 32 + lane;
         const int my = m / TILE_W, mx = m % TILE_W;
-        const uint32_t acc_addr = tmem + ((uint32_t)(wq * 32) << 16) + grp * NC;
-        const uint32_t full_u32 = smem_u32(&acc_full[grp]), empty_u32 = smem_u32(&acc_empty[grp]);
+        const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+        const int nuse = nacc >> 1;                        // buffers of this group: grp, grp + 2, ...
         TileIter it(blockIdx.x + grp * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
         if constexpr (NCT > 0) {
             float s1[NCT], s2[NCT];
@@ -215,12 +246,16 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                 combine(n);
             };
             for (int ti = grp, k = 0; ti < ntiles; ti += 2, ++k, it.next()) {
+                const int buf = ti % nacc;
+                const uint32_t acc_addr = lane_addr + buf * NC;
+                const uint32_t full_u32 = smem_u32(&acc_full[buf]), empty_u32 = smem_u32(&acc_empty[buf]);
+                const uint32_t fpar = (uint32_t)(k / nuse) & 1u;
                 if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) flush_regs(cur_n);
                 cur_n = it.n;
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
-                mbar_wait_warp(full_u32, k & 1);
+                mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
 #pragma unroll
                 for (int h = 0; h < NCT / 16; ++h) {
@@ -258,12 +293,16 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
             if (a.stats && cur_n >= 0) flush_regs(a.stats_nstride != 0 ? cur_n : 0);
         } else {
             for (int ti = grp, k = 0; ti < ntiles; ti += 2, ++k, it.next()) {
+                const int buf = ti % nacc;
+                const uint32_t acc_addr = lane_addr + buf * NC;
+                const uint32_t full_u32 = smem_u32(&acc_full[buf]), empty_u32 = smem_u32(&acc_empty[buf]);
+                const uint32_t fpar = (uint32_t)(k / nuse) & 1u;
                 if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) combine(cur_n);
                 cur_n = it.n;
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
-                mbar_wait_warp(full_u32, k & 1);
+                mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
                 for (int g = 0; g < NC / 8; ++g) {
                     const int c = c_begin + g * 8;
@@ -302,7 +341,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc<COLS>(tmem);
+    if (warp == 8) tmem_dealloc_rt(tmem, (uint32_t)args.tmem_cols);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -351,14 +390,21 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     while (nst < TM_MAX_STAGES && (size_t)(nst + 1) * a.stage_bytes + fixed <= 100 * 1024 && (size_t)nst * a.stage_bytes < 48 * 1024) ++nst;
     while (nst > 2 && (size_t)nst * a.stage_bytes + fixed > 220 * 1024) --nst;
     if (const char* env = getenv("SEMB_TMA_STAGES")) { const int v = atoi(env); if (v >= 2 && v <= TM_MAX_STAGES) nst = v; }
+    A.nmma = nst >= 4 ? 2 : 1;
+    if (A.nmma == 2) nst &= ~1;             // two half-rings, one per MMA warp
     A.nstages = nst;
     a.stages = nst;
     const size_t smem = (size_t)nst * a.stage_bytes + fixed;
     SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tma: %zu bytes of shared memory needed", smem);
-    const int cols = 2 * a.p.NC <= 32 ? 32 : (2 * a.p.NC <= 64 ? 64 : (2 * a.p.NC <= 128 ? 128 : (2 * a.p.NC <= 256 ? 256 : 512)));
+    A.nacc = a.p.NC <= 64 ? 4 : 2;
+    if (const char* env = getenv("SEMB_TMA_NACC")) { const int v = atoi(env); if (v == 2 || (v == 4 && a.p.NC <= 128)) A.nacc = v; }
+    const int need = A.nacc * a.p.NC;
+    const int ks_fixed = a.p.kchunks == 1 ? (g->Cin + 15) / 16 : 0;
+    const int cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+    A.tmem_cols = cols;
     int per_sm = 512 / cols;                                  // TMEM columns
     if ((size_t)per_sm * (smem + 2048) > 220 * 1024) per_sm = (int)(220 * 1024 / (smem + 2048));   // shared memory
-    if (per_sm > 2) per_sm = 2;                               // registers: 320 threads x <= 102
+    if (per_sm > 2) per_sm = 2;                               // registers: 352 threads x <= 93
     if (const char* env = getenv("SEMB_TC_DEBUG")) a.dbg = atoi(env);
     if (const char* env = getenv("SEMB_TC_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
     if (per_sm < 1) per_sm = 1;
@@ -380,20 +426,24 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
                  x->pitch, g->W, g->H, g->N);
 
     cudaError_t e = cudaSuccess;
-#define SEMB_TM_LAUNCH2(COLS, NCT, KR)                                                                                   \
-    e = cudaFuncSetAttribute(conv_tma_kernel<COLS, NCT, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    if (e == cudaSuccess) conv_tma_kernel<COLS, NCT, KR><<<grid, TM_THREADS, smem, as_stream(stream)>>>(A, xmap);
-#define SEMB_TM_LAUNCH(COLS, NCT)                                                                                        \
-    if (g->R == 3) { SEMB_TM_LAUNCH2(COLS, NCT, 3) } else { SEMB_TM_LAUNCH2(COLS, NCT, 1) }
-    switch (cols) {
-        case 32: SEMB_TM_LAUNCH(32, 16) break;       // NC == 16
-        case 64: SEMB_TM_LAUNCH(64, 32) break;       // NC == 32
-        case 128: SEMB_TM_LAUNCH(128, 0) break;
-        case 256: SEMB_TM_LAUNCH(256, 0) break;
-        default: SEMB_TM_LAUNCH(512, 0) break;
+#define SEMB_TM_LAUNCH3(NCT, KR, KS)                                                                                     \
+    e = cudaFuncSetAttribute(conv_tma_kernel<NCT, KR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+    if (e == cudaSuccess) conv_tma_kernel<NCT, KR, KS><<<grid, TM_THREADS, smem, as_stream(stream)>>>(A, xmap);
+#define SEMB_TM_LAUNCH2(NCT, KR)                                                                                         \
+    switch (ks_fixed) {                                                                                                  \
+        case 1: SEMB_TM_LAUNCH3(NCT, KR, 1) break;                                                                       \
+        case 2: SEMB_TM_LAUNCH3(NCT, KR, 2) break;                                                                       \
+        case 3: SEMB_TM_LAUNCH3(NCT, KR, 3) break;                                                                       \
+        case 4: SEMB_TM_LAUNCH3(NCT, KR, 4) break;                                                                       \
+        default: SEMB_TM_LAUNCH3(NCT, KR, 0) break;                                                                      \
     }
+#define SEMB_TM_LAUNCH(NCT)                                                                                              \
+    if (g->R == 3) { SEMB_TM_LAUNCH2(NCT, 3) } else { SEMB_TM_LAUNCH2(NCT, 1) }
+    // NC == 32 would need 64 moment registers per thread (spills under the 92-register cap): generic epilogue
+    if (a.p.NC == 16) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
 #undef SEMB_TM_LAUNCH
 #undef SEMB_TM_LAUNCH2
+#undef SEMB_TM_LAUNCH3
     if (e != cudaSuccess) { set_error("conv_tma: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
     return check_launch("conv_tma");
 }

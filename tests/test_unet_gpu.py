@@ -149,10 +149,14 @@ def test_cuda_graph_step_equals_eager():
     outs = [outs[0], outs[2]]
     for a, b in zip(outs[0][0], outs[1][0]):
         assert abs(a["loss"] - b["loss"]) < 1e-4 * abs(a["loss"])
+    lr, nsteps = 1e-3, 3
     for k in outs[0][1]:
-        # two runs of the same implementation: backward reductions use fp32 atomics, Adam amplifies that noise
+        # two runs of the same implementation: backward reductions use fp32 atomics (order-dependent rounding).  For a
+        # parameter whose gradient is pure rounding noise (e.g. a beta in front of a batch-statistics BN: analytically
+        # zero) Adam's normalised update m/sqrt(v) is +-1 with a noise-determined sign, i.e. two runs may differ by up to
+        # 2*lr per step; everywhere else the difference is a small fraction of the weight scale.
         a, b = torch.from_numpy(outs[1][1][k]), torch.from_numpy(outs[0][1][k])
-        assert float((a - b).abs().max()) < 1e-2 * float(b.abs().max()) + 1e-4, k
+        assert float((a - b).abs().max()) < 1e-2 * float(b.abs().max()) + 2 * lr * nsteps + 1e-4, k
 
 
 def test_train_step_bf16_close_to_oracle():
