@@ -54,6 +54,9 @@ SIGNATURES = {
     "semb_conv2d_dgrad": (C.c_int, [_GP, _TP, _P, _P, _TP, _P, _I, _I, _I, _P]),
     "semb_conv2d_wgrad": (C.c_int, [_GP, _TP, _TP, _P, _P, _P]),
     "semb_pack_weights_tc": (C.c_int64, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "semb_pack_batch_job_size": (C.c_int64, []),
+    "semb_pack_batch_prepare": (C.c_int, [_I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "semb_pack_weights_tc_batch": (C.c_int, [_P, _I, _I, _P]),
     "semb_conv2d_fwd_tc": (C.c_int, [_GP, _TP, _P, _P, _TP, _P, _I, _I, _I, _P]),
     "semb_conv2d_wgrad_tc": (C.c_int, [_GP, _TP, _TP, _P, _P]),
     "semb_norm_finalize": (C.c_int, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
@@ -63,6 +66,8 @@ SIGNATURES = {
     "semb_norm_bwd_finalize": (C.c_int, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "semb_affine_act_bwd_apply": (C.c_int, [_AP, _TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                             _TP, _I, _TP, _I, _P]),
+    "semb_affine_act_bwd_fused": (C.c_int, [_AP, _TP, _TP, _TP, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _P, _P,
+                                            _P, _I, _I, _P, _TP, _I, _TP, _I, _P]),
     "semb_channel_sum": (C.c_int, [_TP, _I, _I, _P, _I, _P]),
     "semb_maxpool2x2_fwd": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _P]),
     "semb_maxpool2x2_bwd": (C.c_int, [_TP, _TP, _TP, _I, _I, _I, _I, _I, _P]),

@@ -45,6 +45,43 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int R, int S, i
 }
 
 
+// All weight images of a network in ONE launch (a train step re-packs ~120 tensors after Adam): job table in device memory.
+struct PackJob {
+    const float* w;
+    bf16* dst;
+    int R, S, Cin, Cout, flip;
+    TcPlan p;
+    long long total;
+    int block0, nblocks;
+};
+
+__global__ void pack_weights_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    int j = 0;
+    while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
+    const PackJob job = jobs[j];
+    const int taps = job.R * job.S;
+    const int K = job.flip ? job.Cout : job.Cin;
+    const int N = job.flip ? job.Cin : job.Cout;
+    const TcPlan p = job.p;
+    const long long stride = (long long)job.nblocks * blockDim.x;
+    for (long long i = (long long)(blockIdx.x - job.block0) * blockDim.x + threadIdx.x; i < job.total; i += stride) {
+        long long t = i;
+        const int ke = (int)(t % 8); t /= 8;
+        const int nl = (int)(t % p.NC); t /= p.NC;
+        const int k8 = (int)(t % (p.KC / 8)); t /= (p.KC / 8);
+        const int tap = (int)(t % taps); t /= taps;
+        const int kch = (int)(t % p.kchunks); t /= p.kchunks;
+        const int nch = (int)t;
+        const int k = kch * p.KC + k8 * 8 + ke, n = nch * p.NC + nl;
+        float v = 0.f;
+        if (k < K && n < N) {
+            if (!job.flip) v = job.w[((size_t)tap * job.Cin + k) * job.Cout + n];
+            else v = job.w[((size_t)(taps - 1 - tap) * job.Cin + n) * job.Cout + k];
+        }
+        job.dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
 // ---- forward / data-gradient conv: persistent, warp-specialised -----------------------------------------------
 //   warps 0-3  epilogue   : drain TMEM (lane = output pixel), bias, moments, bf16 store at the channel offset
 //   warp  4    MMA issuer : one elected thread, tcgen05.mma per (tap, 16-channel step), tcgen05.commit
@@ -671,6 +708,32 @@ extern "C" int64_t semb_pack_weights_tc(const float* w, int32_t R, int32_t S, in
     pack_weights_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(w, R, S, Cin, Cout, flip, p, reinterpret_cast<bf16*>(dst), total);
     const int rc = check_launch("pack_weights_tc");
     return rc ? rc : total * 2;
+}
+
+extern "C" int64_t semb_pack_batch_job_size(void) { return (int64_t)sizeof(PackJob); }
+
+extern "C" int semb_pack_batch_prepare(int32_t index, const float* w, void* dst, int32_t R, int32_t S, int32_t Cin, int32_t Cout,
+                                       int32_t flip, int32_t block0, void* host_jobs) {
+    SEMB_REQUIRE(host_jobs && w && dst && index >= 0, SEMB_ESHAPE, "pack_batch_prepare: null argument");
+    SEMB_REQUIRE(((R == 1 && S == 1) || (R == 3 && S == 3)) && Cin > 0 && Cout > 0 && Cin % 8 == 0 && Cout % 8 == 0, SEMB_ESHAPE,
+                 "pack_batch_prepare: need 1x1 or 3x3 and 8-padded channels (got %dx%d, %d->%d)", R, S, Cin, Cout);
+    PackJob& j = reinterpret_cast<PackJob*>(host_jobs)[index];
+    j.w = w; j.dst = reinterpret_cast<bf16*>(dst); j.R = R; j.S = S; j.Cin = Cin; j.Cout = Cout; j.flip = flip;
+    const int K = flip ? Cout : Cin, N = flip ? Cin : Cout;
+    j.p = tc_plan(K, N, R * S);
+    j.total = (long long)j.p.nchunks * j.p.kchunks * R * S * j.p.KC * j.p.NC;
+    long long nb = cdivl(j.total, 2048);
+    if (nb > 64) nb = 64;
+    if (nb < 1) nb = 1;
+    j.block0 = block0;
+    j.nblocks = (int)nb;
+    return block0 + (int)nb;           // first block of the next job
+}
+
+extern "C" int semb_pack_weights_tc_batch(const void* device_jobs, int32_t njobs, int32_t total_blocks, void* stream) {
+    SEMB_REQUIRE(device_jobs && njobs > 0 && total_blocks > 0, SEMB_ESHAPE, "pack_weights_tc_batch: bad arguments");
+    pack_weights_batch_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const PackJob*>(device_jobs), njobs);
+    return check_launch("pack_weights_tc_batch");
 }
 
 extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,

@@ -42,6 +42,10 @@ struct AffArgs {
     float* stats; double* dstats; int stats_nstride, stats_cstride;
     int acc_a, acc_b;
     int ppb;  // pixels per block
+    // fused backward (reduce -> grid barrier -> apply)
+    float count_a, count_b;
+    float *dgamma_a, *dbeta_a, *dgamma_b, *dbeta_b;
+    unsigned int* barrier;
 };
 
 __device__ __forceinline__ float act_bwd_from_u(float u, int act) {
@@ -364,6 +368,209 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
     }
 }
 
+// Fused backward of the normalisation + activation: pass 1 (sums), a grid-wide barrier, pass 2 (gradients) in ONE
+// cooperative launch.  Pass 2 walks each block's pixel range BACKWARDS, so that the part of dy / a / b the block read
+// last in pass 1 is re-read while it is still in the 126 MB L2 -- for the layers whose operands fit L2 the second pass
+// costs no HBM reads at all; the C-length finalize (c1, c2, dgamma, dbeta) is folded in as well (three launches -> one).
+template <typename T, bool HAS_B, int ACT, int ACTB>
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_fused_kernel(const AffArgs p) {
+    extern __shared__ float sm[];  // [rows][K][C] + [<=256]
+    constexpr int U = 2;
+    const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
+    const Lanes L(p.C);
+    const int n = blockIdx.y;
+    const int c = L.cg * 8;
+    const long long pix0 = (long long)n * p.HW;
+    const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
+    const size_t aoff = (size_t)n * p.aff_nstride + c;
+    const bool red_a = p.mode_a == SEMB_AFF_BATCH, red_b = HAS_B && p.mode_b == SEMB_AFF_BATCH;
+
+    float sa[8], ta[8], ma[8], sb[8], tb[8], mb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; ma[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; mb[i] = 0.f; }
+    if (L.active) {
+        if (p.mode_a != SEMB_AFF_NONE) { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
+        if (red_a) ld_params<0>(p.mean_a, aoff, ma);
+        if (HAS_B && p.mode_b != SEMB_AFF_NONE) { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
+        if (red_b) ld_params<0>(p.mean_b, aoff, mb);
+    }
+    // ---------------- pass 1: sums ----------------
+    {
+        float q0[8], q1[8], q2[8], q3[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { q0[i] = q1[i] = q2[i] = q3[i] = 0.f; }
+        if (L.active) {
+            for (int base = begin + L.prow; base < end; base += L.rows * U) {
+                Raw8<T> rg[U], ra[U], rb[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int px = base + u * L.rows;
+                    if (px < end) {
+                        rg[u].load(vptr<T>(p.dy, pix0 + px, c));
+                        ra[u].load(vptr<T>(p.a, pix0 + px, c));
+                        if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int px = base + u * L.rows;
+                    if (px < end) {
+                        float g[8], va[8], vb[8];
+                        rg[u].unpack(g);
+                        ra[u].unpack(va);
+                        if (HAS_B) rb[u].unpack(vb);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float ub = 0.f, t = fmaf(va[i], sa[i], ta[i]);
+                            if (HAS_B) { ub = fmaf(vb[i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                            const float gg = g[i] * act_bwd_from_u(t, act);
+                            q0[i] += gg;
+                            q1[i] += gg * (va[i] - ma[i]);
+                            if (HAS_B) {
+                                const float gb = gg * act_bwd_from_u(ub, actb);
+                                q2[i] += gb;
+                                q3[i] += gb * (vb[i] - mb[i]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        constexpr int K = HAS_B ? 4 : 2;
+        if (L.active) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sm[(L.prow * K + 0) * p.C + c + i] = q0[i];
+                sm[(L.prow * K + 1) * p.C + c + i] = q1[i];
+                if (HAS_B) {
+                    sm[(L.prow * K + 2) * p.C + c + i] = q2[i];
+                    sm[(L.prow * K + 3) * p.C + c + i] = q3[i];
+                }
+            }
+        }
+        float* sm2 = sm + L.rows * K * p.C;
+        block_colsum(sm, sm2, L.rows, K * p.C, [&](int col, float t) {
+            const int k = col / p.C, i = col - k * p.C;
+            float* st = p.stats + (size_t)n * p.stats_nstride + i;
+            const size_t ao = (size_t)n * p.aff_nstride + i;
+            if (k == 0 && red_a) atomicAdd(st, t);
+            if (k == 1 && red_a) atomicAdd(st + p.stats_cstride, t * p.invstd_a[ao]);
+            if (k == 2 && red_b) atomicAdd(st + 2 * p.stats_cstride, t);
+            if (k == 3 && red_b) atomicAdd(st + 3 * p.stats_cstride, t * p.invstd_b[ao]);
+        });
+    }
+    // ---------------- grid-wide barrier (cooperative launch: all blocks are co-resident) ----------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int expected = gridDim.x * gridDim.y;
+        atomicAdd(p.barrier, 1u);
+        while (*reinterpret_cast<volatile unsigned int*>(p.barrier) < expected) __nanosleep(64);
+        __threadfence();
+        // self-resetting: the last block to LEAVE the barrier clears both words for the next launch
+        if (atomicAdd(p.barrier + 1, 1u) == expected - 1) { p.barrier[0] = 0u; p.barrier[1] = 0u; }
+    }
+    __syncthreads();
+    // ---------------- C-length finalize: dgamma / dbeta (one block per sample row) ----------------
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < p.C; i += 256) {
+            const float* st = p.stats + (size_t)n * p.stats_nstride + i;
+            if (red_a) {
+                if (p.dbeta_a) atomicAdd(p.dbeta_a + i, __ldcg(st));
+                if (p.dgamma_a) atomicAdd(p.dgamma_a + i, __ldcg(st + p.stats_cstride));
+            }
+            if (red_b) {
+                if (p.dbeta_b) atomicAdd(p.dbeta_b + i, __ldcg(st + 2 * p.stats_cstride));
+                if (p.dgamma_b) atomicAdd(p.dgamma_b + i, __ldcg(st + 3 * p.stats_cstride));
+            }
+        }
+    }
+    if (!L.active) return;
+    // ---------------- pass 2: gradients, newest data first ----------------
+    float Pa[8], Qa[8], Pb[8], Qb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { Pa[i] = 0.f; Qa[i] = 0.f; Pb[i] = 0.f; Qb[i] = 0.f; }
+    {
+        const float* st = p.stats + (size_t)n * p.stats_nstride + c;
+        if (red_a) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float c1 = __ldcg(st + i) / p.count_a, c2 = __ldcg(st + p.stats_cstride + i) / p.count_a;
+                const float k = sa[i] * p.invstd_a[aoff + i] * c2;
+                Pa[i] = -k;
+                Qa[i] = fmaf(k, ma[i], -sa[i] * c1);
+            }
+        }
+        if (red_b) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float c1 = __ldcg(st + 2 * p.stats_cstride + i) / p.count_b, c2 = __ldcg(st + 3 * p.stats_cstride + i) / p.count_b;
+                const float k = sb[i] * p.invstd_b[aoff + i] * c2;
+                Pb[i] = -k;
+                Qb[i] = fmaf(k, mb[i], -sb[i] * c1);
+            }
+        }
+    }
+    const bool wa = p.da.ptr != nullptr, wb = HAS_B && p.db.ptr != nullptr;
+    if (!wa && !wb) return;
+    const int span = L.rows * U;
+    const int niter = (end - begin - L.prow + span - 1) / span;      // iterations of this thread in pass 1
+    for (int it = niter - 1; it >= 0; --it) {
+        const int base = begin + L.prow + it * span;
+        Raw8<T> rg[U], ra[U], rb[U];
+#pragma unroll
+        for (int u = U - 1; u >= 0; --u) {
+            const int px = base + u * L.rows;
+            if (px < end) {
+                rg[u].load(vptr<T>(p.dy, pix0 + px, c));
+                ra[u].load(vptr<T>(p.a, pix0 + px, c));
+                if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+            }
+        }
+#pragma unroll
+        for (int u = U - 1; u >= 0; --u) {
+            const int px = base + u * L.rows;
+            if (px < end) {
+                float g[8], va[8], vb[8], da[8], db[8];
+                rg[u].unpack(g);
+                ra[u].unpack(va);
+                if (HAS_B) rb[u].unpack(vb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float ub = 0.f, t = fmaf(va[i], sa[i], ta[i]);
+                    if (HAS_B) { ub = fmaf(vb[i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                    const float gg = g[i] * act_bwd_from_u(t, act);
+                    da[i] = fmaf(sa[i], gg, fmaf(Pa[i], va[i], Qa[i]));
+                    if (HAS_B) {
+                        const float gb = gg * act_bwd_from_u(ub, actb);
+                        db[i] = fmaf(sb[i], gb, fmaf(Pb[i], vb[i], Qb[i]));
+                    }
+                }
+                if (wa) {
+                    T* o = vptr_mut<T>(p.da, pix0 + px, c);
+                    if (p.acc_a) {
+                        float old[8];
+                        Vec8<T>::load(o, old);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) da[i] += old[i];
+                    }
+                    Vec8<T>::store(o, da);
+                }
+                if (wb) {
+                    T* o = vptr_mut<T>(p.db, pix0 + px, c);
+                    if (p.acc_b) {
+                        float old[8];
+                        Vec8<T>::load(o, old);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) db[i] += old[i];
+                    }
+                    Vec8<T>::store(o, db);
+                }
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const AffArgs p) {
     extern __shared__ float sm[];  // [C]
@@ -619,6 +826,86 @@ extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_t
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, 0, st, p);
     return check_launch("affine_act_bwd_apply");
+}
+
+// ---- fused backward ----------------------------------------------------------------------------------------------
+template <typename T, bool HAS_B, int ACT, int ACTB>
+static cudaError_t launch_fused(dim3 grid, size_t smem, cudaStream_t st, const AffArgs& p, int* max_blocks_per_sm) {
+    auto k = affine_act_bwd_fused_kernel<T, HAS_B, ACT, ACTB>;
+    if (max_blocks_per_sm) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, k, 256, smem);
+    }
+    void* args[] = {const_cast<AffArgs*>(&p)};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(k), grid, dim3(256), args, smem, st);
+}
+
+template <typename T, bool HAS_B>
+static cudaError_t dispatch_fused(dim3 grid, size_t smem, cudaStream_t st, const AffArgs& p, int* occ) {
+    if (p.act == SEMB_ACT_NONE && (!HAS_B || p.actb == SEMB_ACT_NONE)) return launch_fused<T, HAS_B, SEMB_ACT_NONE, SEMB_ACT_NONE>(grid, smem, st, p, occ);
+    if (p.act == SEMB_ACT_RELU && (!HAS_B || p.actb == SEMB_ACT_NONE)) return launch_fused<T, HAS_B, SEMB_ACT_RELU, SEMB_ACT_NONE>(grid, smem, st, p, occ);
+    if (p.act == SEMB_ACT_RELU && p.actb == SEMB_ACT_RELU) return launch_fused<T, HAS_B, SEMB_ACT_RELU, SEMB_ACT_RELU>(grid, smem, st, p, occ);
+    return launch_fused<T, HAS_B, -1, -1>(grid, smem, st, p, occ);
+}
+
+extern "C" int semb_affine_act_bwd_fused(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* a, const semb_tensor* b,
+                                         const float* scale_a, const float* shift_a, const float* mean_a, const float* invstd_a,
+                                         float count_a, float* dgamma_a, float* dbeta_a,
+                                         const float* scale_b, const float* shift_b, const float* mean_b, const float* invstd_b,
+                                         float count_b, float* dgamma_b, float* dbeta_b,
+                                         float* sums, int32_t sums_nstride, int32_t sums_cstride, void* barrier,
+                                         const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b, void* stream) {
+    int rc = check_aff(d);
+    if (rc) return rc;
+    SEMB_REQUIRE(view_ok(dy) && view_ok(a) && (!b || view_ok(b)), SEMB_EALIGN, "affine bwd fused: bad dy/a/b view");
+    SEMB_REQUIRE((!da || view_ok(da)) && (!db || view_ok(db)), SEMB_EALIGN, "affine bwd fused: bad gradient view");
+    SEMB_REQUIRE(sums && barrier, SEMB_ESHAPE, "affine bwd fused: null sums / barrier");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_BATCH || (b && d->mode_b == SEMB_AFF_BATCH), SEMB_ESHAPE,
+                 "affine bwd fused: no batch-statistics operand (use semb_affine_act_bwd_apply)");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_NONE || (scale_a && shift_a), SEMB_ESHAPE, "affine bwd fused: missing scale/shift a");
+    SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (mean_a && invstd_a && count_a > 0.f), SEMB_ESHAPE, "affine bwd fused: missing batch-norm terms for a");
+    SEMB_REQUIRE(!b || d->mode_b == SEMB_AFF_NONE || (scale_b && shift_b), SEMB_ESHAPE, "affine bwd fused: missing scale/shift b");
+    SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (mean_b && invstd_b && count_b > 0.f), SEMB_ESHAPE, "affine bwd fused: missing batch-norm terms for b");
+    AffArgs p{};
+    p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
+    p.aff_nstride = d->aff_nstride;
+    p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
+    p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
+    p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
+    p.count_a = count_a; p.count_b = count_b;
+    p.dgamma_a = dgamma_a; p.dbeta_a = dbeta_a; p.dgamma_b = dgamma_b; p.dbeta_b = dbeta_b;
+    p.stats = sums; p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
+    p.barrier = reinterpret_cast<unsigned int*>(barrier);
+    p.acc_a = acc_a; p.acc_b = acc_b;
+    const bool has_b = b != nullptr;
+    const size_t smem = ((size_t)(256 / (d->C / 8)) * (has_b ? 4 : 2) * d->C + 256) * sizeof(float);
+    cudaStream_t st = as_stream(stream);
+    // co-residency: the grid must fit one wave (cooperative launch)
+    int occ = 0;
+    cudaError_t e;
+    if (d->dtype == SEMB_BF16) e = has_b ? dispatch_fused<bf16, true>(dim3(), smem, st, p, &occ) : dispatch_fused<bf16, false>(dim3(), smem, st, p, &occ);
+    else e = has_b ? dispatch_fused<float, true>(dim3(), smem, st, p, &occ) : dispatch_fused<float, false>(dim3(), smem, st, p, &occ);
+    SEMB_REQUIRE(e == cudaSuccess && occ >= 1, SEMB_ECUDA, "affine bwd fused: occupancy query failed (%s)", cudaGetErrorString(e));
+    if (occ > (has_b ? 2 : 3)) occ = has_b ? 2 : 3;
+    const bool per_sample = d->aff_nstride != 0 || sums_nstride != 0;
+    dim3 grid;
+    const int rows = 256 / (p.C / 8);
+    if (!per_sample) {
+        grid = aff_grid(p, false, occ);
+    } else {
+        long long per_n = (148LL * occ) / p.N;                 // blocks per sample so that the whole grid is one wave
+        if (per_n < 1) per_n = 1;
+        int ppb = (int)cdivl(p.HW, per_n);
+        if (ppb < rows * 4) ppb = rows * 4;
+        p.ppb = cdiv(ppb, rows) * rows;
+        grid = dim3(cdiv(p.HW, p.ppb), p.N);
+    }
+    SEMB_REQUIRE((long long)grid.x * grid.y <= 148LL * occ, SEMB_EWORKSPACE,
+                 "affine bwd fused: %u x %u blocks do not fit one wave (use the two-pass kernels)", grid.x, grid.y);
+    if (d->dtype == SEMB_BF16) e = has_b ? dispatch_fused<bf16, true>(grid, smem, st, p, nullptr) : dispatch_fused<bf16, false>(grid, smem, st, p, nullptr);
+    else e = has_b ? dispatch_fused<float, true>(grid, smem, st, p, nullptr) : dispatch_fused<float, false>(grid, smem, st, p, nullptr);
+    if (e != cudaSuccess) { set_error("affine bwd fused: cooperative launch failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
+    return check_launch("affine_act_bwd_fused");
 }
 
 extern "C" int semb_channel_sum(const semb_tensor* x, int32_t N, int32_t HW, float* out, int32_t dtype, void* stream) {

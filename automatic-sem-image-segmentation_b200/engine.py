@@ -193,6 +193,15 @@ class Engine:
         self.tc_enabled = bool(use_tc) and dtype == "bf16"
         self.tc_packs: List[dict] = []
         self._pack_dirty = True
+        self._pack_table = None
+        import os as _os
+        # one cooperative launch for the BN backward (sums -> grid barrier -> gradients).  Measured on B200 (round 1): SLOWER
+        # than the two-pass kernels on every layer of the UNet (5.41 vs 4.77 ms per step; the barrier and the cooperative
+        # launch cost more than the L2 re-read saves), so it stays opt-in.
+        self.fused_affine_bwd = _os.environ.get("SEMB_FUSED_AFFINE_BWD") is not None
+        # weight gradients run on a side stream, concurrently with the data-gradient / normalisation chain (they only
+        # meet again at the optimizer); set by the model front end, off for weight-sharing towers
+        self.wgrad_stream: Optional[torch.cuda.Stream] = None
         # weight sharing between towers of the same network (CycleGAN applies each generator three times per step):
         # a sharing engine has its own buffers / ops / scratch but uses the root's parameters, gradients and packs
         self.share = share
@@ -260,17 +269,27 @@ class Engine:
             root._pack_dirty = True
         return pk
 
+    def _pack_jobs(self):
+        """Device table of pack jobs (one launch re-packs every weight image); rebuilt when a tower adds a pack."""
+        if self._pack_table is None or self._pack_table[1] != len(self.tc_packs):
+            n = len(self.tc_packs)
+            host = np.zeros(n * int(self.lib.semb_pack_batch_job_size()), dtype=np.uint8)
+            blocks = 0
+            for i, pk in enumerate(self.tc_packs):
+                blocks = int(self.lib.semb_pack_batch_prepare(i, self.params.ptr(pk["w"]), pk["buf"].data_ptr(), pk["R"], pk["S"],
+                                                               pk["Cin"], pk["Cout"], pk["flip"], blocks, host.ctypes.data))
+                if blocks < 0:
+                    L.check(blocks)
+            self._pack_table = (torch.from_numpy(host).to(self.device), n, blocks)
+        return self._pack_table
+
     def repack(self):
         """fp32 master weights -> packed bf16 UMMA images (after set_weights / Adam)."""
         if self.share is not None:
             return self.share.repack()
-        if not self.dry:
-            st = self.stream
-            for pk in self.tc_packs:
-                rc = self.lib.semb_pack_weights_tc(self.params.ptr(pk["w"]), pk["R"], pk["S"], pk["Cin"], pk["Cout"], pk["flip"],
-                                                   pk["buf"].data_ptr(), st)
-                if rc < 0:
-                    L.check(int(rc))
+        if not self.dry and self.tc_packs:
+            table, n, blocks = self._pack_jobs()
+            L.check(self.lib.semb_pack_weights_tc_batch(table.data_ptr(), n, blocks, self.stream))
         self._pack_dirty = False
 
     def gptr(self, name: str) -> int:
@@ -332,6 +351,18 @@ class Engine:
     def backward(self):
         for op in reversed(self.ops):
             op.bwd()
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.wgrad_stream)       # join before the optimizer
+
+    def on_wgrad_stream(self, fn):
+        """Runs `fn` (kernel launches that only produce weight gradients) on the side stream, after everything queued
+        so far on the current stream; the caller's stream does not wait for it (see backward())."""
+        side = self.wgrad_stream
+        if side is None:
+            return fn()
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            fn()
 
     def adam(self, beta1: float, beta2: float, eps: float, gscale: float = 1.0):
         L.check(self.lib.semb_adam_step(self.params.t.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
@@ -443,11 +474,11 @@ class ConvOp(Op):
         dbias = e.gptr(self.bias) if self.bias else None
         if not self.transposed:
             if self.use_tc and dbias is None:
-                L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w),
-                                                   e.stream))
+                e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g),
+                                                                             e.gptr(self.w), e.stream)))
             else:
-                L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g), e.gptr(self.w), dbias,
-                                                e.stream))
+                e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g),
+                                                                          e.gptr(self.w), dbias, e.stream)))
             if self.x.requires_grad:
                 dst = self.x.g if self.pad_buf is None else self.pad_buf.view().t
                 acc = self.acc_x if self.pad_buf is None else 0
@@ -528,6 +559,9 @@ class AffineOp(Op):
         self.acc_a = self.acc_b = 0
         groups = max(norm_a.groups if norm_a else 1, norm_b.groups if norm_b else 1)
         self.aff_nstride = 0 if groups == 1 else (norm_a or norm_b).C
+        # two zeroed words for the grid barrier of the fused backward kernel
+        eng._naff = getattr(eng, "_naff", 0) + 1
+        self.bar = eng.zeroed.add(f"affine_{eng._naff}/barrier", 4)
 
     def plan_backward(self):
         if self.a.requires_grad:
@@ -568,6 +602,28 @@ class AffineOp(Op):
         red_a = d.mode_a == L.AFF_BATCH
         red_b = self.b is not None and d.mode_b == L.AFF_BATCH
         # the bwd sums of this op live in norm_a's (resp. norm_b's) scratch; slot [0,1] = a-terms, [2,3] = b-terms
+        da = C.byref(self.a.g) if self.a.requires_grad else None
+        dbv = C.byref(self.b.g) if (self.b is not None and self.b.requires_grad) else None
+        if (red_a or red_b) and e.fused_affine_bwd:
+            owner = na if red_a else nb
+            sums = e.zeroed.ptr(owner.sums, ca if red_a else 0)
+            cs = owner.C
+            ns = 0 if owner.groups == 1 else 4 * owner.C
+            dga = (e.gptr(na.gamma) + 4 * ca) if (red_a and na.gamma) else None
+            dba = (e.gptr(na.beta) + 4 * ca) if red_a else None
+            dgb = e.gptr(nb.gamma) if (red_b and nb.gamma) else None
+            dbb = e.gptr(nb.beta) if red_b else None
+            rc = e.lib.semb_affine_act_bwd_fused(
+                C.byref(d), C.byref(self.y.g), C.byref(self.a.t), bt,
+                self._p(na, "scale", ca), self._p(na, "shift", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca),
+                na.count if na else 0.0, dga, dba,
+                self._p(nb, "scale", 0), self._p(nb, "shift", 0), self._p(nb, "mean", 0), self._p(nb, "invstd", 0),
+                nb.count if nb else 0.0, dgb, dbb,
+                sums, ns, cs, e.zeroed.ptr(self.bar), da, self.acc_a, dbv, self.acc_b, e.stream)
+            if rc == 0:
+                return
+            if rc != -4:            # SEMB_EWORKSPACE: grid not co-resident -> two-pass kernels below
+                L.check(rc)
         if red_a or red_b:
             owner = na if red_a else nb
             sums = e.zeroed.ptr(owner.sums, ca if red_a else 0)
@@ -590,8 +646,6 @@ class AffineOp(Op):
                 # the sums buffer is norm_a (different C stride) the b-sums still sit at 2*cs, 3*cs.
                 L.check(e.lib.semb_norm_bwd_finalize(sums, 1, nb.groups, self.a.C, cs, ns, nb.count, None, None,
                                                      self._p(nb, "c1", 0), self._p(nb, "c2", 0), dg, db, e.stream))
-        da = C.byref(self.a.g) if self.a.requires_grad else None
-        dbv = C.byref(self.b.g) if (self.b is not None and self.b.requires_grad) else None
         if da is None and dbv is None:
             return
         L.check(e.lib.semb_affine_act_bwd_apply(

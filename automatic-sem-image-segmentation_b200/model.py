@@ -37,6 +37,8 @@ class _Instance:
         e = self.eng
         self.loss_sums = e.zeroed.add("loss/sums", 4)
         e.finalize()
+        if os.environ.get("SEMB_NO_WGRAD_STREAM") is None:
+            e.wgrad_stream = torch.cuda.Stream(device=e.device)
         self.n, self.h, self.w = n, h, w
         self.x_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
         self.y_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)

@@ -134,6 +134,7 @@ def profile_ops(inst, weighting, peaks, size, batch):
     from sem_b200.engine import ConvOp, AffineOp
     e = inst.eng
     recs = []
+    side, e.wgrad_stream = e.wgrad_stream, None        # per-op events need every kernel on the timed stream
 
     def timed(label, op, fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -150,6 +151,7 @@ def profile_ops(inst, weighting, peaks, size, batch):
     for op in reversed(e.ops):
         timed("bwd", op, lambda op=op: op.bwd())
     torch.cuda.synchronize()
+    e.wgrad_stream = side
     rows = []
     for label, op, a, b in recs:
         ms = a.elapsed_time(b)

@@ -114,6 +114,15 @@ int semb_conv2d_wgrad(const semb_conv_geom* g, const semb_tensor* x, const semb_
 int64_t semb_pack_weights_tc(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout,
                              int32_t flip, void* dst, void* stream);
 
+/* One launch for all weight images of a network.  The caller keeps a HOST array of njobs opaque job records
+ * (semb_pack_batch_job_size() bytes each), fills record `index` with semb_pack_batch_prepare (which returns the first
+ * block of the next job, i.e. the running block count, or a negative SEMB_E* code), copies the array to the device once
+ * and then calls semb_pack_weights_tc_batch(device_jobs, njobs, total_blocks) after every weight update. */
+int64_t semb_pack_batch_job_size(void);
+int semb_pack_batch_prepare(int32_t index, const float* w, void* dst, int32_t R, int32_t S, int32_t Cin, int32_t Cout,
+                            int32_t flip, int32_t block0, void* host_jobs);
+int semb_pack_weights_tc_batch(const void* device_jobs, int32_t njobs, int32_t total_blocks, void* stream);
+
 /* Same contract as semb_conv2d_fwd for stride 1, R=S in {1,3}, bf16 storage: im2col-free implicit GEMM on
  * tcgen05.mma (M = 128 output pixels per CTA, N = Cout, K = taps x Cin) with the fp32 accumulator in TMEM.
  * The A operand is the NHWC halo tile staged once in shared memory; the nine taps are shifted UMMA
@@ -195,6 +204,20 @@ int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy,
                               const float* c1_b, const float* c2_b,
                               const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b,
                               void* stream);
+
+/* Both backward passes and the C-length finalize in ONE cooperative launch: pass 1 (the sums of
+ * semb_affine_act_bwd_reduce), a grid-wide barrier, dgamma += sum(g*xhat) / dbeta += sum(g) (each may be NULL), then
+ * pass 2 (semb_affine_act_bwd_apply with c1 = sum(g)/count, c2 = sum(g*xhat)/count) walking every block's pixel range
+ * backwards so that it re-reads from L2 what pass 1 read last.  At least one operand must be in SEMB_AFF_BATCH mode.
+ * `sums` (4 x cstride floats per group) and `barrier` (two 32-bit words) must be ZERO on entry; the barrier words are
+ * zero again on exit.  Returns SEMB_EWORKSPACE when the grid cannot be co-resident (fall back to the two-pass calls). */
+int semb_affine_act_bwd_fused(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* a, const semb_tensor* b,
+                              const float* scale_a, const float* shift_a, const float* mean_a, const float* invstd_a,
+                              float count_a, float* dgamma_a, float* dbeta_a,
+                              const float* scale_b, const float* shift_b, const float* mean_b, const float* invstd_b,
+                              float count_b, float* dgamma_b, float* dbeta_b,
+                              float* sums, int32_t sums_nstride, int32_t sums_cstride, void* barrier,
+                              const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b, void* stream);
 
 /* out[c] += sum over pixels of x[.,c]   (bias gradient of Conv2DTranspose / biased Conv2D) */
 int semb_channel_sum(const semb_tensor* x, int32_t N, int32_t HW, float* out, int32_t dtype, void* stream);

@@ -278,6 +278,28 @@ def test_norm_affine_fwd_bwd(dtype, per_sample, c):
     assert U.rel_err(dgam_b[:c], gb.grad) < tol
     assert U.rel_err(dbeta_a[:c], ba.grad) < tol and U.rel_err(dbeta_b[:c], bb.grad) < tol
 
+    # the fused cooperative kernel (sums -> grid barrier -> finalize -> gradients) must reproduce the three-launch path
+    sums2 = torch.zeros(groups * 4 * cp, device="cuda")
+    bar = torch.zeros(2, dtype=torch.int32, device="cuda")
+    dgam_b2, dbeta_a2, dbeta_b2 = torch.zeros(cp, device="cuda"), torch.zeros(cp, device="cuda"), torch.zeros(cp, device="cuda")
+    dad2, dbd2 = torch.ones_like(ad), torch.zeros_like(bd)          # da accumulates on top of ones
+    dav2, dbv2 = U.view(dad2), U.view(dbd2)
+    for rep in range(2):                                              # twice: the barrier words must reset themselves
+        if rep == 1:
+            sums2.zero_(); dgam_b2.zero_(); dbeta_a2.zero_(); dbeta_b2.zero_(); dad2.fill_(1.0)
+        L.check(lib.semb_affine_act_bwd_fused(
+            C.byref(d), C.byref(dyv), C.byref(av), C.byref(bv),
+            A["scale"].data_ptr(), A["shift"].data_ptr(), A["mean"].data_ptr(), A["invstd"].data_ptr(), count, None, dbeta_a2.data_ptr(),
+            B["scale"].data_ptr(), B["shift"].data_ptr(), B["mean"].data_ptr(), B["invstd"].data_ptr(), count, dgam_b2.data_ptr(),
+            dbeta_b2.data_ptr(), sums2.data_ptr(), 4 * cp if per_sample else 0, cp, bar.data_ptr(),
+            C.byref(dav2), 1, C.byref(dbv2), 0, U.stream()))
+        torch.cuda.synchronize()
+        assert int(bar.abs().max()) == 0
+        assert U.rel_err(dad2[..., :c].float() - 1.0, ar.grad) < tol
+        assert U.rel_err(dbd2[..., :c], br_.grad) < tol
+        assert U.rel_err(dgam_b2[:c], gb.grad) < tol
+        assert U.rel_err(dbeta_a2[:c], ba.grad) < tol and U.rel_err(dbeta_b2[:c], bb.grad) < tol
+
 
 def test_norm_finalize_moving_stats():
     lib = L.load()
