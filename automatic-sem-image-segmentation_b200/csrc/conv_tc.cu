@@ -811,6 +811,8 @@ extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* 
     SEMB_REQUIRE(g->stride == 1 && ((g->R == 1 && g->S == 1) || (g->R == 3 && g->S == 3)), SEMB_ESHAPE,
                  "wgrad_tc: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
     SEMB_REQUIRE(view_ok(x) && view_ok(dy) && x->C == g->Cin && dy->C == g->Cout, SEMB_EALIGN, "wgrad_tc: bad tensor views");
+    if (g->R == 3 && g->pad_mode == SEMB_PAD_ZERO && g->pad_t <= 2 && g->pad_l <= 2 && !getenv("SEMB_WGRAD_NO_TMA"))
+        return wgrad_tma_launch(g, x, dy, dw, stream);
     if (g->R == 3 && g->Cin <= 40 && g->Cout <= 128 && g->pad_t <= 2 && g->pad_l <= 2 && !getenv("SEMB_WGRAD_NO_STACK")) {
         WsArgs w{};
         w.N = g->N; w.H = g->H; w.W = g->W; w.OH = g->OH; w.OW = g->OW; w.Cin = g->Cin; w.Cout = g->Cout;

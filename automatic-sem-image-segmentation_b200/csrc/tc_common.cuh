@@ -219,4 +219,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
                     void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream);
 
+// wgrad_tma.cu: TMA-staged weight gradient of the zero-padded 3x3 layers
+int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* stream);
+
 }  // namespace semb
