@@ -36,6 +36,13 @@ class AffineDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("N", "HW", "C", "dtype", "act", "actb", "mode_a", "mode_b", "aff_nstride")]
 
 
+class NormFin(C.Structure):
+    """semb_norm_fin"""
+    _fields_ = [("stats", C.c_void_p), ("stats_nstride", C.c_int32), ("cstride", C.c_int32), ("count", C.c_float), ("eps", C.c_float),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p),
+                ("invstd", C.c_void_p), ("moving_mean", C.c_void_p), ("moving_var", C.c_void_p), ("momentum", C.c_float)]
+
+
 _P = C.c_void_p
 _I = C.c_int32
 _L = C.c_int64
@@ -66,6 +73,9 @@ SIGNATURES = {
     "semb_norm_bwd_finalize": (C.c_int, [_P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "semb_affine_act_bwd_apply": (C.c_int, [_AP, _TP, _TP, _TP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                             _TP, _I, _TP, _I, _P]),
+    "semb_affine_act_fwd_fin": (C.c_int, [_AP, _TP, C.POINTER(NormFin), _TP, C.POINTER(NormFin), _TP, _P, _I, _I, _P]),
+    "semb_affine_act_bwd_apply_sums": (C.c_int, [_AP, _TP, _TP, _TP, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _P, _P,
+                                                 _P, _I, _I, _TP, _I, _TP, _I, _P]),
     "semb_affine_act_bwd_fused": (C.c_int, [_AP, _TP, _TP, _TP, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _F, _P, _P,
                                             _P, _I, _I, _P, _TP, _I, _TP, _I, _P]),
     "semb_channel_sum": (C.c_int, [_TP, _I, _I, _P, _I, _P]),

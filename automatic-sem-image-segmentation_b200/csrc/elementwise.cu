@@ -42,7 +42,9 @@ struct AffArgs {
     float* stats; double* dstats; int stats_nstride, stats_cstride;
     int acc_a, acc_b;
     int ppb;  // pixels per block
-    // fused backward (reduce -> grid barrier -> apply)
+    // finalize of the normalisations folded into the forward kernel (stats == NULL: scale / shift are read)
+    semb_norm_fin fa, fb;
+    // fused backward (reduce -> grid barrier -> apply) and apply-from-sums
     float count_a, count_b;
     float *dgamma_a, *dbeta_a, *dgamma_b, *dbeta_b;
     unsigned int* barrier;
@@ -113,6 +115,34 @@ __device__ __forceinline__ void ld_params(const float* p, size_t off, float (&v)
     for (int i = 0; i < 8; ++i) v[i] = p[off + i];
 }
 
+// Folded semb_norm_finalize: the thread's 8 channels of group g, same arithmetic as norm_finalize_kernel.  `publish`:
+// this thread also writes scale / shift / mean / invstd (read by the backward kernels) and, for g == 0, the moving
+// statistics.
+__device__ __forceinline__ void fin_params(const semb_norm_fin& f, int g, int c, bool publish, bool moving, float (&sc)[8], float (&sh)[8]) {
+    const double* st = reinterpret_cast<const double*>(f.stats) + (size_t)g * f.stats_nstride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double dm = st[c + i] / (double)f.count;
+        const float mean = (float)dm;
+        const float var = (float)(st[f.cstride + c + i] / (double)f.count - dm * dm);
+        const float inv = rsqrtf(var + f.eps);
+        const float ga = f.gamma ? f.gamma[c + i] : 1.f;
+        sc[i] = ga * inv;
+        sh[i] = f.beta[c + i] - mean * sc[i];
+        if (publish) {
+            const size_t o = (size_t)g * f.cstride + c + i;
+            f.scale[o] = sc[i];
+            f.shift[o] = sh[i];
+            if (f.mean) f.mean[o] = mean;
+            if (f.invstd) f.invstd[o] = inv;
+            if (moving && f.moving_mean) {
+                f.moving_mean[c + i] = f.moving_mean[c + i] * f.momentum + mean * (1.f - f.momentum);
+                f.moving_var[c + i] = f.moving_var[c + i] * f.momentum + var * (1.f - f.momentum);
+            }
+        }
+    }
+}
+
 // y = act(a*sa+ta [+ actb(b*sb+tb)]), optional fp64 moments of y.  U pixels per thread are loaded before any is used.
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p) {
@@ -130,8 +160,17 @@ __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; }
     if (L.active) {
-        if (p.mode_a != SEMB_AFF_NONE) { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
-        if (HAS_B && p.mode_b != SEMB_AFF_NONE) { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
+        const int g = p.aff_nstride != 0 ? n : 0;
+        const bool publish = blockIdx.x == 0 && L.prow == 0 && (p.aff_nstride != 0 || n == 0);
+        const bool moving = publish && n == 0 && p.aff_nstride == 0;
+        if (p.mode_a != SEMB_AFF_NONE) {
+            if (p.fa.stats) fin_params(p.fa, g, c, publish, moving, sa, ta);
+            else { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
+        }
+        if (HAS_B && p.mode_b != SEMB_AFF_NONE) {
+            if (p.fb.stats) fin_params(p.fb, g, c, publish, moving, sb, tb);
+            else { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
+        }
     }
     float s1[8], s2[8];
 #pragma unroll
@@ -293,25 +332,46 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
     float sa[8], ta[8], Pa[8], Qa[8], sb[8], tb[8], Pb[8], Qb[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sa[i] = 1.f; ta[i] = 0.f; Pa[i] = 0.f; Qa[i] = 0.f; sb[i] = 1.f; tb[i] = 0.f; Pb[i] = 0.f; Qb[i] = 0.f; }
+    // c1 = sum(g)/count, c2 = sum(g*xhat)/count: from the c1/c2 arrays, or (p.stats != NULL, semb_affine_act_bwd_apply_sums)
+    // straight from the sums of pass 1, which folds semb_norm_bwd_finalize into this kernel
+    const float* st = p.stats ? p.stats + (size_t)n * p.stats_nstride + c : nullptr;
     if (p.mode_a != SEMB_AFF_NONE) { ld_params<0>(p.scale_a, aoff, sa); ld_params<0>(p.shift_a, aoff, ta); }
     if (p.mode_a == SEMB_AFF_BATCH) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float k = sa[i] * p.invstd_a[aoff + i] * p.c2_a[aoff + i];
+            const float c1 = st ? st[i] / p.count_a : p.c1_a[aoff + i];
+            const float c2 = st ? st[p.stats_cstride + i] / p.count_a : p.c2_a[aoff + i];
+            const float k = sa[i] * p.invstd_a[aoff + i] * c2;
             Pa[i] = -k;
-            Qa[i] = fmaf(k, p.mean_a[aoff + i], -sa[i] * p.c1_a[aoff + i]);
+            Qa[i] = fmaf(k, p.mean_a[aoff + i], -sa[i] * c1);
         }
     }
     if (HAS_B && p.mode_b != SEMB_AFF_NONE) { ld_params<0>(p.scale_b, aoff, sb); ld_params<0>(p.shift_b, aoff, tb); }
     if (HAS_B && p.mode_b == SEMB_AFF_BATCH) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float k = sb[i] * p.invstd_b[aoff + i] * p.c2_b[aoff + i];
+            const float c1 = st ? st[2 * p.stats_cstride + i] / p.count_b : p.c1_b[aoff + i];
+            const float c2 = st ? st[3 * p.stats_cstride + i] / p.count_b : p.c2_b[aoff + i];
+            const float k = sb[i] * p.invstd_b[aoff + i] * c2;
             Pb[i] = -k;
-            Qb[i] = fmaf(k, p.mean_b[aoff + i], -sb[i] * p.c1_b[aoff + i]);
+            Qb[i] = fmaf(k, p.mean_b[aoff + i], -sb[i] * c1);
+        }
+    }
+    if (st && blockIdx.x == 0 && L.prow == 0) {      // dgamma += sum(g*xhat), dbeta += sum(g): once per group
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (p.mode_a == SEMB_AFF_BATCH) {
+                if (p.dbeta_a) atomicAdd(p.dbeta_a + c + i, st[i]);
+                if (p.dgamma_a) atomicAdd(p.dgamma_a + c + i, st[p.stats_cstride + i]);
+            }
+            if (HAS_B && p.mode_b == SEMB_AFF_BATCH) {
+                if (p.dbeta_b) atomicAdd(p.dbeta_b + c + i, st[2 * p.stats_cstride + i]);
+                if (p.dgamma_b) atomicAdd(p.dgamma_b + c + i, st[3 * p.stats_cstride + i]);
+            }
         }
     }
     const bool wa = p.da.ptr != nullptr, wb = HAS_B && p.db.ptr != nullptr;
+    if (!wa && !wb) return;
 
     for (int base = begin + L.prow; base < end; base += L.rows * U) {
         Raw8<T> rg[U], ra[U], rb[U];
@@ -826,6 +886,65 @@ extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_t
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, 0, st, p);
     return check_launch("affine_act_bwd_apply");
+}
+
+// ---- forward with the normalisation finalize folded in -----------------------------------------------------------------
+extern "C" int semb_affine_act_fwd_fin(const semb_affine_desc* d, const semb_tensor* a, const semb_norm_fin* fin_a,
+                                       const semb_tensor* b, const semb_norm_fin* fin_b, const semb_tensor* y, void* stats,
+                                       int32_t stats_nstride, int32_t stats_cstride, void* stream) {
+    int rc = check_aff(d);
+    if (rc) return rc;
+    SEMB_REQUIRE(view_ok(a) && view_ok(y) && (!b || view_ok(b)), SEMB_EALIGN, "affine fwd fin: bad tensor view");
+    SEMB_REQUIRE(a->C == d->C && y->C == d->C && (!b || b->C == d->C), SEMB_ESHAPE, "affine fwd fin: channel mismatch");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_NONE || (fin_a && fin_a->scale && fin_a->shift && (!fin_a->stats || fin_a->beta)), SEMB_ESHAPE,
+                 "affine fwd fin: missing normalisation record for a");
+    SEMB_REQUIRE(!b || d->mode_b == SEMB_AFF_NONE || (fin_b && fin_b->scale && fin_b->shift && (!fin_b->stats || fin_b->beta)), SEMB_ESHAPE,
+                 "affine fwd fin: missing normalisation record for b");
+    AffArgs p{};
+    p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
+    p.aff_nstride = d->aff_nstride;
+    p.a = mkview(a); p.b = mkview(b); p.y = mkview(y);
+    if (fin_a) { p.fa = *fin_a; p.scale_a = fin_a->scale; p.shift_a = fin_a->shift; }
+    if (fin_b) { p.fb = *fin_b; p.scale_b = fin_b->scale; p.shift_b = fin_b->shift; }
+    p.dstats = reinterpret_cast<double*>(stats); p.stats_nstride = stats_nstride; p.stats_cstride = stats_cstride;
+    dim3 grid = aff_grid(p, d->aff_nstride != 0 || (stats && stats_nstride != 0), 3);
+    const size_t smem = stats ? ((size_t)(256 / (d->C / 8)) * 2 * d->C + 256) * sizeof(float) : 0;
+    cudaStream_t st = as_stream(stream);
+    SEMB_AFF_LAUNCH(affine_act_fwd_kernel, d->dtype, b != nullptr, grid, smem, st, p);
+    return check_launch("affine_act_fwd_fin");
+}
+
+// ---- backward pass 2 straight from the sums of pass 1 (folds semb_norm_bwd_finalize) ---------------------------------------
+extern "C" int semb_affine_act_bwd_apply_sums(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* a, const semb_tensor* b,
+                                              const float* scale_a, const float* shift_a, const float* mean_a, const float* invstd_a,
+                                              float count_a, float* dgamma_a, float* dbeta_a,
+                                              const float* scale_b, const float* shift_b, const float* mean_b, const float* invstd_b,
+                                              float count_b, float* dgamma_b, float* dbeta_b,
+                                              const float* sums, int32_t sums_nstride, int32_t sums_cstride,
+                                              const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b, void* stream) {
+    int rc = check_aff(d);
+    if (rc) return rc;
+    SEMB_REQUIRE(view_ok(dy) && view_ok(a) && (!b || view_ok(b)), SEMB_EALIGN, "affine bwd apply sums: bad dy/a/b view");
+    SEMB_REQUIRE((!da || view_ok(da)) && (!db || view_ok(db)), SEMB_EALIGN, "affine bwd apply sums: bad gradient view");
+    SEMB_REQUIRE(sums, SEMB_ESHAPE, "affine bwd apply sums: null sums");
+    SEMB_REQUIRE(d->mode_a == SEMB_AFF_NONE || (scale_a && shift_a), SEMB_ESHAPE, "affine bwd apply sums: missing scale/shift a");
+    SEMB_REQUIRE(d->mode_a != SEMB_AFF_BATCH || (mean_a && invstd_a && count_a > 0.f), SEMB_ESHAPE, "affine bwd apply sums: missing batch-norm terms for a");
+    SEMB_REQUIRE(!b || d->mode_b == SEMB_AFF_NONE || (scale_b && shift_b), SEMB_ESHAPE, "affine bwd apply sums: missing scale/shift b");
+    SEMB_REQUIRE(!b || d->mode_b != SEMB_AFF_BATCH || (mean_b && invstd_b && count_b > 0.f), SEMB_ESHAPE, "affine bwd apply sums: missing batch-norm terms for b");
+    AffArgs p{};
+    p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
+    p.aff_nstride = d->aff_nstride;
+    p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
+    p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
+    p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
+    p.count_a = count_a; p.count_b = count_b;
+    p.dgamma_a = dgamma_a; p.dbeta_a = dbeta_a; p.dgamma_b = dgamma_b; p.dbeta_b = dbeta_b;
+    p.stats = const_cast<float*>(sums); p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
+    p.acc_a = acc_a; p.acc_b = acc_b;
+    dim3 grid = aff_grid(p, d->aff_nstride != 0 || sums_nstride != 0, b ? 2 : 3);
+    cudaStream_t st = as_stream(stream);
+    SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, 0, st, p);
+    return check_launch("affine_act_bwd_apply_sums");
 }
 
 // ---- fused backward ----------------------------------------------------------------------------------------------

@@ -199,6 +199,9 @@ class Engine:
         # than the two-pass kernels on every layer of the UNet (5.41 vs 4.77 ms per step; the barrier and the cooperative
         # launch cost more than the L2 re-read saves), so it stays opt-in.
         self.fused_affine_bwd = _os.environ.get("SEMB_FUSED_AFFINE_BWD") is not None
+        # the C-length finalize kernels (scale/shift from moments; c1/c2/dgamma/dbeta from the backward sums) are folded
+        # into the affine kernels that consume them: ~170 launches of 5-6 us fewer per UNet step
+        self.fold_norm = _os.environ.get("SEMB_NO_FOLD_NORM") is None
         # weight gradients run on a side stream, concurrently with the data-gradient / normalisation chain (they only
         # meet again at the optimizer); set by the model front end, off for weight-sharing towers
         self.wgrad_stream: Optional[torch.cuda.Stream] = None
@@ -520,6 +523,7 @@ class NormOp(Op):
             eng.scratch.add(f"{name}/{k}", c * groups)
         self.nstride = 0 if groups == 1 else c
         self.stats_nstride = 0 if groups == 1 else 2 * c
+        self.consumers = 0       # AffineOps applying this norm; with exactly one the finalize is folded into its kernel
 
     def s(self, k: str) -> int:
         return self.eng.scratch.ptr(f"{self.name}/{k}")
@@ -527,8 +531,30 @@ class NormOp(Op):
     def stats_ref(self, coff: int = 0):
         return (self.stats, coff, self.stats_nstride, self.C)
 
+    def folded(self, training: bool) -> bool:
+        return self.eng.fold_norm and self.consumers == 1 and self.uses_batch_stats(training)
+
+    def fin(self, training: bool, coff: int = 0) -> L.NormFin:
+        """semb_norm_fin record for the consumer kernel (stats=NULL when the finalize is not folded)."""
+        e = self.eng
+        f = L.NormFin()
+        f.scale, f.shift = self.s("scale") + 4 * coff, self.s("shift") + 4 * coff
+        if self.folded(training):
+            f.stats = e.zeroed.ptr(self.stats, 2 * coff)
+            f.stats_nstride, f.cstride = self.stats_nstride, self.C
+            f.count, f.eps = self.count, self.eps
+            f.gamma = (e.params.ptr(self.gamma) + 4 * coff) if self.gamma else None
+            f.beta = e.params.ptr(self.beta) + 4 * coff
+            f.mean, f.invstd = self.s("mean") + 4 * coff, self.s("invstd") + 4 * coff
+            if self.moving and training:
+                f.moving_mean, f.moving_var = e.state.ptr(self.moving[0]) + 4 * coff, e.state.ptr(self.moving[1]) + 4 * coff
+            f.momentum = self.momentum
+        return f
+
     def fwd(self, training: bool):
         e = self.eng
+        if self.folded(training):
+            return          # the AffineOp that applies this norm finalizes it in its own kernel
         gamma = e.params.ptr(self.gamma) if self.gamma else None
         beta = e.params.ptr(self.beta)
         if training or self.moving is None:
@@ -560,6 +586,9 @@ class AffineOp(Op):
         groups = max(norm_a.groups if norm_a else 1, norm_b.groups if norm_b else 1)
         self.aff_nstride = 0 if groups == 1 else (norm_a or norm_b).C
         # two zeroed words for the grid barrier of the fused backward kernel
+        for nm in (norm_a, norm_b):
+            if nm is not None:
+                nm.consumers += 1
         eng._naff = getattr(eng, "_naff", 0) + 1
         self.bar = eng.zeroed.add(f"affine_{eng._naff}/barrier", 4)
 
@@ -588,6 +617,14 @@ class AffineOp(Op):
         if self.stats_out is not None and training:
             name, off, ns, cs = self.stats_out
             sp = e.zeroed.ptr(name, 2 * off)
+        if e.fold_norm:
+            fa = self.norm_a.fin(training, self.coff_a) if self.norm_a is not None else None
+            fb = self.norm_b.fin(training, 0) if (self.norm_b is not None and self.b is not None) else None
+            L.check(e.lib.semb_affine_act_fwd_fin(
+                C.byref(d), C.byref(self.a.t), C.byref(fa) if fa is not None else None,
+                C.byref(self.b.t) if self.b is not None else None, C.byref(fb) if fb is not None else None,
+                C.byref(self.y.t), sp, ns, cs, e.stream))
+            return
         L.check(e.lib.semb_affine_act_fwd(
             C.byref(d), C.byref(self.a.t), self._p(self.norm_a, "scale", self.coff_a), self._p(self.norm_a, "shift", self.coff_a),
             C.byref(self.b.t) if self.b is not None else None, self._p(self.norm_b, "scale", 0), self._p(self.norm_b, "shift", 0),
@@ -634,6 +671,19 @@ class AffineOp(Op):
                 self._p(na, "scale", ca), self._p(na, "shift", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca),
                 self._p(nb, "scale", 0), self._p(nb, "shift", 0), self._p(nb, "mean", 0), self._p(nb, "invstd", 0),
                 sums, ns, cs, e.stream))
+            if e.fold_norm:
+                # pass 2 reads the sums directly and accumulates dgamma / dbeta (semb_norm_bwd_finalize folded in)
+                dga = (e.gptr(na.gamma) + 4 * ca) if (red_a and na.gamma) else None
+                dba = (e.gptr(na.beta) + 4 * ca) if red_a else None
+                dgb = e.gptr(nb.gamma) if (red_b and nb.gamma) else None
+                dbb = e.gptr(nb.beta) if red_b else None
+                L.check(e.lib.semb_affine_act_bwd_apply_sums(
+                    C.byref(d), C.byref(self.y.g), C.byref(self.a.t), bt,
+                    self._p(na, "scale", ca), self._p(na, "shift", ca), self._p(na, "mean", ca), self._p(na, "invstd", ca),
+                    na.count if na else 0.0, dga, dba,
+                    self._p(nb, "scale", 0), self._p(nb, "shift", 0), self._p(nb, "mean", 0), self._p(nb, "invstd", 0),
+                    nb.count if nb else 0.0, dgb, dbb, sums, ns, cs, da, self.acc_a, dbv, self.acc_b, e.stream))
+                return
             if red_a:
                 dg = e.gptr(na.gamma) + 4 * ca if na.gamma else None
                 db = e.gptr(na.beta) + 4 * ca

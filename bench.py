@@ -129,12 +129,14 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------- GPU arm
 def profile_ops(inst, weighting, peaks, size, batch):
-    """One eager fwd+bwd with CUDA events around every engine op; returns the per-op table and the dominant conv."""
+    """One eager fwd+bwd with CUDA events around every engine op (weight gradients timed separately from the data
+    gradients); returns one row per (op, kernel family) with its time and ALGORITHMIC bytes / flops."""
     import sem_b200  # noqa: F401
     from sem_b200.engine import ConvOp, AffineOp
     e = inst.eng
     recs = []
     side, e.wgrad_stream = e.wgrad_stream, None        # per-op events need every kernel on the timed stream
+    wg = {}
 
     def timed(label, op, fn):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -143,36 +145,86 @@ def profile_ops(inst, weighting, peaks, size, batch):
         b.record()
         recs.append((label, op, a, b))
 
+    orig_side = e.on_wgrad_stream
+
+    def timed_wgrad(fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        wg["last"] = (a, b)
+
+    e.on_wgrad_stream = timed_wgrad
     e.zero_step(zero_grads=True)
     inst.stage_in()
     for op in e.ops:
         timed("fwd", op, lambda op=op: op.fwd(True))
     inst.loss(weighting, with_grad=True)
     for op in reversed(e.ops):
+        wg.pop("last", None)
         timed("bwd", op, lambda op=op: op.bwd())
+        if "last" in wg:
+            recs.append(("wgrad", op, *wg["last"]))
     torch.cuda.synchronize()
+    e.on_wgrad_stream = orig_side
     e.wgrad_stream = side
+    esz = 2 if e.dtype_name == "bf16" else 4
     rows = []
+    last_bwd = None
     for label, op, a, b in recs:
         ms = a.elapsed_time(b)
-        row = {"phase": label, "op": type(op).__name__, "ms": ms}
+        row = {"phase": label, "op": type(op).__name__, "ms": ms, "kernel": "other"}
         if isinstance(op, ConvOp):
             g = op.geom
-            taps = g.R * g.S
             pix = g.N * g.OH * g.OW
-            esz = 2 if e.dtype_name == "bf16" else 4
-            flops_fwd = 2.0 * pix * taps * g.Cin * g.Cout                    # physical (8-padded) channels
+            flops = 2.0 * pix * g.R * g.S * g.Cin * g.Cout                     # physical (8-padded) channels
+            nbytes = (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz             # input + output activations once
+            tc = op.use_tc and e.dtype_name == "bf16"
             row.update({"geom": f"{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.R} s{g.stride}{' T' if op.transposed else ''}",
-                        "flops": flops_fwd * (1 if label == "fwd" else 2),
-                        "bytes": (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz * (1 if label == "fwd" else 2)})
+                        "flops": flops, "bytes": nbytes})
+            if label == "fwd":
+                row["kernel"] = "conv_tma_kernel (fwd+dgrad)" if tc else "conv_simt"
+            elif label == "wgrad":
+                row["kernel"] = ("wgrad_tma_kernel" if g.R == 3 else "wgrad_tc_kernel") if tc else "wgrad_simt"
+                last_bwd["ms"] = max(last_bwd["ms"] - ms, 0.0)                  # what is left of the op is the data gradient
+            else:
+                row["kernel"] = "conv_tma_kernel (fwd+dgrad)" if tc else "conv_simt"
+                if not op.x.requires_grad:
+                    row["flops"], row["bytes"] = 0.0, 0
+                last_bwd = row
         if isinstance(op, AffineOp):
-            esz = 2 if e.dtype_name == "bf16" else 4
             hb = 1 if op.b is not None else 0
             elems = op.n * op.hw * op.a.C
-            nt = (2 + hb) if label == "fwd" else (2 + hb) + (3 + 2 * hb)      # reduce reads dy,a[,b]; apply reads the same, writes da[,db]
-            row.update({"geom": f"C={op.a.C} hw={op.hw} two_operands={bool(hb)}", "bytes": elems * esz * nt})
+            nt = (2 + hb) if label == "fwd" else (2 + hb) + (3 + 2 * hb)       # reduce reads dy,a[,b]; apply reads the same, writes da[,db]
+            row.update({"geom": f"C={op.a.C} hw={op.hw} two_operands={bool(hb)}", "bytes": elems * esz * nt,
+                        "kernel": "affine_act_fwd_kernel" if label == "fwd" else "affine_act_bwd_{reduce,apply}_kernel"})
         rows.append(row)
     return rows
+
+
+def kernel_table(rows, peaks):
+    """Per kernel family: time share of the (eager) step, achieved algorithmic GB/s and TFLOP/s, roofline bound."""
+    total = sum(r["ms"] for r in rows)
+    fam = {}
+    for r in rows:
+        f = fam.setdefault(r["kernel"], {"ms": 0.0, "bytes": 0.0, "flops": 0.0, "launch_groups": 0})
+        f["ms"] += r["ms"]
+        f["bytes"] += r.get("bytes", 0)
+        f["flops"] += r.get("flops", 0.0)
+        f["launch_groups"] += 1
+    ridge = peaks["tflops_burst"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    out = {}
+    for k, f in fam.items():
+        if f["ms"] <= 0:
+            continue
+        gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9
+        tfs = f["flops"] / (f["ms"] * 1e-3) / 1e12
+        ai = f["flops"] / f["bytes"] if f["bytes"] else 0.0
+        out[k] = {"ms": f["ms"], "share_of_step": f["ms"] / total, "algorithmic_GBps": gbs, "TFLOPs": tfs,
+                  "arithmetic_intensity_flop_per_byte": ai, "bound": "tensor" if ai >= ridge else "hbm",
+                  "frac_of_hbm_peak": gbs / peaks["hbm_gbs"], "frac_of_tensor_peak": tfs / peaks["tflops_burst"],
+                  "ops": f["launch_groups"], "bytes_per_step": f["bytes"]}
+    return out, total
 
 
 def run_ours(args):
@@ -254,29 +306,45 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- per-op profile (eager, CUDA events) -> dominant kernel roofline
+    # ---- per-op profile (eager, CUDA events on the launching stream) -> roofline of the dominant kernel
     rows = profile_ops(inst, wgt, peaks, size, batch)
-    total_ms = sum(r["ms"] for r in rows)
-    convs = [r for r in rows if "flops" in r]
-    top = max(convs, key=lambda r: r["ms"])
-    conv_ms = sum(r["ms"] for r in convs)
-    ridge = peaks["tflops_burst"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    ai = top["flops"] / top["bytes"]
-    if ai >= ridge:
-        roof = {"bound": "tensor", "achieved": top["flops"] / (top["ms"] * 1e-3) / 1e12, "peak": peaks["tflops_burst"], "unit": "TFLOP/s"}
+    table, total_ms = kernel_table(rows, peaks)
+    named = {k: v for k, v in table.items() if k != "other"}
+    top_name = max(named, key=lambda k: named[k]["ms"])
+    top = named[top_name]
+    if top["bound"] == "tensor":
+        roof = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": peaks["tflops_burst"], "unit": "TFLOP/s"}
     else:
-        roof = {"bound": "hbm", "achieved": top["bytes"] / (top["ms"] * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s"}
+        roof = {"bound": "hbm", "achieved": top["algorithmic_GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["kernel"] = top_name
+    roof["kernel_ms_per_step"] = top["ms"]
+    roof["kernel_share_of_step"] = top["share_of_step"]
+    roof["launches_per_step"] = top["ops"]
+    roof["arithmetic_intensity_flop_per_byte"] = top["arithmetic_intensity_flop_per_byte"]
+    roof["algorithmic_bytes_per_launch"] = top["bytes_per_step"] / max(top["ops"], 1)
+    roof["avg_launch_ms"] = top["ms"] / max(top["ops"], 1)
+    roof["peak_source"] = peaks["source"] + ", burst figure (kernels timed one by one)"
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/traffic.json), per launch
     roof["traffic"] = None
-    roof["kernel"] = f"{top['op']}.{top['phase']} {top['geom']}"
-    roof["kernel_ms"] = top["ms"]
-    roof["kernel_share_of_step"] = top["ms"] / total_ms
-    roof["arithmetic_intensity_flop_per_byte"] = ai
-    roof["peak_source"] = peaks["source"] + ", burst figure (kernel timed alone)"
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        ent = tj.get(top_name.split(" ")[0])
+        if ent:
+            roof["traffic"] = ent["dram_bytes_per_launch"]
+            roof["traffic_source"] = ent.get("source")
     net_tflops = value / world * FLOP_PER_TILE_FWD_BWD.get(size, 31.669e9 * (size / 256) ** 2) / 1e12
     roof["net_conv_tflops"] = net_tflops
     roof["net_frac_of_tensor_peak_sustained"] = net_tflops / peaks["tflops_sustained"]
-    roof["conv_share_of_step"] = conv_ms / total_ms
+    # the "fused 3x3 stage" of SURVEY 8d: the three chained 3x3 convs of mres6 (32x32) and mres7 (64x64), forward
+    stage = [r for r in rows if r["phase"] == "fwd" and r["op"] == "ConvOp" and " k3 " in r.get("geom", "") and
+             r["geom"].split(" ")[0] in ("32x32", "64x64") and r["flops"] > 2e10]
+    if stage:
+        sf, st = sum(r["flops"] for r in stage), sum(r["ms"] for r in stage)
+        roof["stage_3x3_mres6_mres7_fwd"] = {"TFLOPs": sf / (st * 1e-3) / 1e12, "frac_of_tensor_peak": sf / (st * 1e-3) / 1e12 / peaks["tflops_burst"],
+                                             "convs": len(stage), "ms": st}
 
     # ---- CPU baseline beside it (bounded sample)
     cpu = None
@@ -298,6 +366,7 @@ def run_ours(args):
         "gpu_launches": int(launches_per_step * args.steps),
         "launches_per_step": int(launches_per_step),
         "roofline": roof,
+        "roofline_by_kernel": table,
         "cpu_baseline": cpu,
         "clocks": clocks,
         "last_step_metrics": last,

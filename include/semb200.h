@@ -205,6 +205,35 @@ int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_tensor* dy,
                               const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b,
                               void* stream);
 
+/* semb_norm_finalize folded into its consumer: one record per normalised operand.  stats != NULL: the kernel computes
+ * scale/shift from the fp64 moments (same arithmetic as semb_norm_finalize) and one block per group also WRITES
+ * scale / shift / mean / invstd (mean / invstd may be NULL) and, for per-channel statistics, updates the moving
+ * statistics (moving_mean may be NULL).  stats == NULL: scale / shift are inputs (constant or already finalized). */
+typedef struct {
+    const void* stats;                 /* fp64 moment accumulators, or NULL                          */
+    int32_t stats_nstride, cstride;    /* strides in doubles / elements, as in semb_norm_finalize    */
+    float count, eps;
+    const float *gamma, *beta;         /* gamma may be NULL (scale=False)                            */
+    float *scale, *shift, *mean, *invstd;
+    float *moving_mean, *moving_var;
+    float momentum;
+} semb_norm_fin;
+
+/* semb_affine_act_fwd with semb_norm_finalize folded in (85 C-length launches fewer per UNet step). */
+int semb_affine_act_fwd_fin(const semb_affine_desc* d, const semb_tensor* a, const semb_norm_fin* fin_a,
+                            const semb_tensor* b, const semb_norm_fin* fin_b, const semb_tensor* y, void* stats,
+                            int32_t stats_nstride, int32_t stats_cstride, void* stream);
+
+/* semb_affine_act_bwd_apply reading c1 = sum(g)/count, c2 = sum(g*xhat)/count straight from the sums written by
+ * semb_affine_act_bwd_reduce, and accumulating dgamma / dbeta (each may be NULL): semb_norm_bwd_finalize folded in. */
+int semb_affine_act_bwd_apply_sums(const semb_affine_desc* d, const semb_tensor* dy, const semb_tensor* a, const semb_tensor* b,
+                                   const float* scale_a, const float* shift_a, const float* mean_a, const float* invstd_a,
+                                   float count_a, float* dgamma_a, float* dbeta_a,
+                                   const float* scale_b, const float* shift_b, const float* mean_b, const float* invstd_b,
+                                   float count_b, float* dgamma_b, float* dbeta_b,
+                                   const float* sums, int32_t sums_nstride, int32_t sums_cstride,
+                                   const semb_tensor* da, int32_t acc_a, const semb_tensor* db, int32_t acc_b, void* stream);
+
 /* Both backward passes and the C-length finalize in ONE cooperative launch: pass 1 (the sums of
  * semb_affine_act_bwd_reduce), a grid-wide barrier, dgamma += sum(g*xhat) / dbeta += sum(g) (each may be NULL), then
  * pass 2 (semb_affine_act_bwd_apply with c1 = sum(g)/count, c2 = sum(g*xhat)/count) walking every block's pixel range

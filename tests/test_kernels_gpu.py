@@ -278,6 +278,40 @@ def test_norm_affine_fwd_bwd(dtype, per_sample, c):
     assert U.rel_err(dgam_b[:c], gb.grad) < tol
     assert U.rel_err(dbeta_a[:c], ba.grad) < tol and U.rel_err(dbeta_b[:c], bb.grad) < tol
 
+    # folded variants: forward that finalizes the norms itself, pass 2 straight from the sums (+ dgamma / dbeta)
+    fins = {}
+    for tag, t, gam, bet in (("a", a, None, beta_a), ("b", b, gamma_b, beta_b)):
+        st = moments(t)
+        o2 = {k: torch.zeros(groups * cp, device="cuda") for k in ("scale", "shift", "mean", "invstd")}
+        gam_d = U.pad_v(gam) if gam is not None else None
+        bet_d = U.pad_v(bet)
+        keep += [st, gam_d, bet_d, o2]
+        f = L.NormFin()
+        f.stats, f.stats_nstride, f.cstride, f.count, f.eps = st.data_ptr(), nstride, cp, count, eps
+        f.gamma, f.beta = (gam_d.data_ptr() if gam_d is not None else None), bet_d.data_ptr()
+        f.scale, f.shift, f.mean, f.invstd = (o2[k].data_ptr() for k in ("scale", "shift", "mean", "invstd"))
+        fins[tag] = (f, o2)
+    yd2 = torch.zeros_like(yd)
+    yv2 = U.view(yd2)
+    L.check(lib.semb_affine_act_fwd_fin(C.byref(d), C.byref(av), C.byref(fins["a"][0]), C.byref(bv), C.byref(fins["b"][0]), C.byref(yv2),
+                                        None, 0, 0, U.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(yd2, yd)
+    for tag in ("a", "b"):
+        for k in ("scale", "shift", "mean", "invstd"):
+            assert torch.equal(fins[tag][1][k], arrs[tag][k]), (tag, k)
+    dgam_b3, dbeta_a3, dbeta_b3 = torch.zeros(cp, device="cuda"), torch.zeros(cp, device="cuda"), torch.zeros(cp, device="cuda")
+    dad3, dbd3 = torch.zeros_like(ad), torch.zeros_like(bd)
+    dav3, dbv3 = U.view(dad3), U.view(dbd3)
+    L.check(lib.semb_affine_act_bwd_apply_sums(
+        C.byref(d), C.byref(dyv), C.byref(av), C.byref(bv),
+        A["scale"].data_ptr(), A["shift"].data_ptr(), A["mean"].data_ptr(), A["invstd"].data_ptr(), count, None, dbeta_a3.data_ptr(),
+        B["scale"].data_ptr(), B["shift"].data_ptr(), B["mean"].data_ptr(), B["invstd"].data_ptr(), count, dgam_b3.data_ptr(),
+        dbeta_b3.data_ptr(), sums.data_ptr(), 4 * cp if per_sample else 0, cp, C.byref(dav3), 0, C.byref(dbv3), 0, U.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(dad3, dad) and torch.equal(dbd3, dbd)
+    assert U.rel_err(dgam_b3[:c], dgam_b[:c]) < 1e-5 and U.rel_err(dbeta_a3[:c], dbeta_a[:c]) < 1e-5 and U.rel_err(dbeta_b3[:c], dbeta_b[:c]) < 1e-5
+
     # the fused cooperative kernel (sums -> grid barrier -> finalize -> gradients) must reproduce the three-launch path
     sums2 = torch.zeros(groups * 4 * cp, device="cuda")
     bar = torch.zeros(2, dtype=torch.int32, device="cuda")
