@@ -107,7 +107,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("SEMB_LIB_PATH") or _build.LIB_PATH      # override: A/B builds of the kernels (tuning only)
     if not os.path.exists(path):
         path = _build.build()  # raises when nvcc is unavailable: no fallback path exists
     lib = C.CDLL(path)

@@ -7,6 +7,17 @@
 // atomic per channel per block.
 #include "common.cuh"
 
+// pixels a thread keeps in flight per loop iteration (16-byte loads per operand), tuned on B200
+#ifndef SEMB_AFF_U_FWD
+#define SEMB_AFF_U_FWD 4
+#endif
+#ifndef SEMB_AFF_U_FWD_B
+#define SEMB_AFF_U_FWD_B 2
+#endif
+#ifndef SEMB_AFF_U_BWD
+#define SEMB_AFF_U_BWD 2
+#endif
+
 namespace semb {
 
 struct View { const void* ptr; int pitch, coff; };
@@ -147,7 +158,7 @@ __device__ __forceinline__ void fin_params(const semb_norm_fin& f, int g, int c,
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p) {
     extern __shared__ float sm[];  // [rows][2][C] + [<=256] when moments are requested
-    constexpr int U = HAS_B ? 2 : 4;
+    constexpr int U = HAS_B ? SEMB_AFF_U_FWD_B : SEMB_AFF_U_FWD;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     const int n = blockIdx.y;
@@ -230,7 +241,7 @@ __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p)
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kernel(const AffArgs p) {
     extern __shared__ float sm[];  // [rows][4][C] + [<=256]
-    constexpr int U = 2;
+    constexpr int U = HAS_B ? 2 : SEMB_AFF_U_BWD;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     const int n = blockIdx.y;
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kern
 // Pa = Qa = 0 for a constant affine; same for b with gb = g*actb'(ub).
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kernel(const AffArgs p) {
-    constexpr int U = 2;
+    constexpr int U = HAS_B ? 2 : SEMB_AFF_U_BWD;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
     if (!L.active) return;
