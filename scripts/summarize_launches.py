@@ -13,7 +13,12 @@ def main(path):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
         k = re.sub(r"\(.*", "", row["Kernel Name"])
-        v = float(row["Metric Value"].replace(",", ""))
+        try:
+            v = float(row["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        if v != v:
+            continue
         u = row["Metric Unit"]
         v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)      # -> us
         agg[k][0] += 1
