@@ -181,7 +181,7 @@ def profile_ops(inst, weighting, peaks, size, batch):
             nbytes = (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz             # input + output activations once
             tc = op.use_tc and e.dtype_name == "bf16"
             row.update({"geom": f"{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.R} s{g.stride}{' T' if op.transposed else ''}",
-                        "flops": flops, "bytes": nbytes})
+                        "flops": flops, "bytes": nbytes, "w": op.w})
             if label == "fwd":
                 row["kernel"] = "conv_tma_kernel (fwd+dgrad)" if tc else "conv_simt"
             elif label == "wgrad":
@@ -339,8 +339,8 @@ def run_ours(args):
     roof["net_conv_tflops"] = net_tflops
     roof["net_frac_of_tensor_peak_sustained"] = net_tflops / peaks["tflops_sustained"]
     # the "fused 3x3 stage" of SURVEY 8d: the three chained 3x3 convs of mres6 (32x32) and mres7 (64x64), forward
-    stage = [r for r in rows if r["phase"] == "fwd" and r["op"] == "ConvOp" and " k3 " in r.get("geom", "") and
-             r["geom"].split(" ")[0] in ("32x32", "64x64") and r["flops"] > 2e10]
+    names = {f"conv2d_{i}/kernel" for i in (42, 43, 44, 46, 47, 48)}       # creation order: 41 / 45 are the 1x1 shortcuts
+    stage = [r for r in rows if r["phase"] == "fwd" and r.get("w") in names]
     if stage:
         sf, st = sum(r["flops"] for r in stage), sum(r["ms"] for r in stage)
         roof["stage_3x3_mres6_mres7_fwd"] = {"TFLOPs": sf / (st * 1e-3) / 1e12, "frac_of_tensor_peak": sf / (st * 1e-3) / 1e12 / peaks["tflops_burst"],
