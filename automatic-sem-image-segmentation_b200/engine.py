@@ -12,6 +12,7 @@ and the NCCL all-reduce each run over ONE contiguous tensor per network.
 from __future__ import annotations
 
 import ctypes as C
+import os as _os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -437,6 +438,16 @@ class ConvOp(Op):
             self.pad_buf = eng.new_buf(hp, wp, x.C, f"{w}_dxpad", n=n)
             self.pad_hw = (hp, wp)
             self.geom_p = L.ConvGeom(n, hp, wp, oh, ow, cin, cout, k, k, stride, 0, 0, L.PAD_ZERO, eng.dtype)
+        # Reflect-padded tensor-core convs (CycleGAN residual blocks): the padded input is materialised once per forward
+        # (a cheap copy next to a 512->512 conv) so that forward and weight gradient run the TMA kernels as zero-pad
+        # "valid" convolutions over it; the data gradient already works on the padded domain (pad_buf above).
+        self.x_pad = None
+        if self.use_tc and pad_mode == L.PAD_REFLECT and _os.environ.get("SEMB_NO_REFLECT_TMA") is None:
+            hp = max(h, (oh - 1) * stride + k)
+            wp = max(wd, (ow - 1) * stride + k)
+            self.x_pad = eng.new_buf(hp, wp, x.C, f"{w}_xpad", requires_grad=False, n=n)
+            self.x_pad_hw = (hp, wp)
+            self.geom_v = L.ConvGeom(n, hp, wp, oh, ow, cin, cout, k, k, stride, 0, 0, L.PAD_ZERO, eng.dtype)
         if self.use_tc:
             self.pk_fwd = eng.tc_pack(w, k, k, cin, cout, 0)
             self.pk_bwd = None
@@ -464,6 +475,14 @@ class ConvOp(Op):
         e = self.eng
         sp, ns, cs = self._stats_args() if training else (None, 0, 0)
         bias = e.params.ptr(self.bias) if self.bias else None
+        if self.use_tc and self.x_pad is not None:
+            g = self.geom
+            xp = self.x_pad.view()
+            L.check(e.lib.semb_pad_crop(C.byref(self.x.t), C.byref(xp.t), g.N, g.H, g.W, self.x_pad_hw[0], self.x_pad_hw[1],
+                                        g.pad_t, g.pad_l, 0, e.dtype, 0, e.stream))
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_v), C.byref(xp.t), self.pk_fwd["buf"].data_ptr(), bias,
+                                             C.byref(self.y.t), sp, ns, cs, 0, e.stream))
+            return
         if self.use_tc:
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom), C.byref(self.x.t), self.pk_fwd["buf"].data_ptr(), bias,
                                              C.byref(self.y.t), sp, ns, cs, 0, e.stream))
@@ -476,7 +495,10 @@ class ConvOp(Op):
         e = self.eng
         dbias = e.gptr(self.bias) if self.bias else None
         if not self.transposed:
-            if self.use_tc and dbias is None:
+            if self.use_tc and dbias is None and self.x_pad is not None:
+                e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom_v), C.byref(self.x_pad.view().t),
+                                                                             C.byref(self.y.g), e.gptr(self.w), e.stream)))
+            elif self.use_tc and dbias is None:
                 e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g),
                                                                              e.gptr(self.w), e.stream)))
             else:
