@@ -263,7 +263,9 @@ __global__ void cast_out_kernel(PView src, float* __restrict__ dst, int dst_C, l
 // ---- depth-to-space for Conv2DTranspose(2x2, stride 2) expressed as a 1x1 conv with 4*C outputs ------------------
 // dir 0: dst[n,2y+r,2x+s,c] = src[n,y,x,(2r+s)*C+c] + bias[c]        dir 1: src[n,y,x,(2r+s)*C+c] = dst[n,2y+r,2x+s,c]
 template <typename T>
-__global__ void pixel_shuffle2_kernel(PView src, PView dst, int N, int H, int W, int C8, const float* __restrict__ bias, int dir) {
+__global__ void pixel_shuffle2_kernel(PView src, PView dst, int N, int H, int W, int DH, int DW, int C8, const float* __restrict__ bias,
+                                      int dir, int acc) {
+    // dst is (N, DH, DW, C) with DH <= 2H, DW <= 2W (odd sizes: the missing last row / column reads as zero, is not written)
     const long long total = (long long)N * H * W * 4 * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8) * 8;
@@ -271,20 +273,64 @@ __global__ void pixel_shuffle2_kernel(PView src, PView dst, int N, int H, int W,
         const int q = (int)(t % 4); t /= 4;
         const int x = (int)(t % W), y = (int)((t / W) % H), n = (int)(t / ((long long)W * H));
         const size_t sp = ((size_t)n * H + y) * W + x;
-        const size_t dp = ((size_t)n * 2 * H + 2 * y + (q >> 1)) * (2 * W) + 2 * x + (q & 1);
+        const int dy = 2 * y + (q >> 1), dx = 2 * x + (q & 1);
+        const bool inside = dy < DH && dx < DW;
+        const size_t dp = ((size_t)n * DH + (inside ? dy : 0)) * DW + (inside ? dx : 0);
         float v[8];
         if (dir == 0) {
+            if (!inside) continue;
             Vec8<T>::load(at<T>(src, sp, q * C8 * 8 + c), v);
             if (bias) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) v[k] += bias[c + k];
             }
+            if (acc) {
+                float o[8];
+                Vec8<T>::load(at<T>(dst, dp, c), o);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += o[k];
+            }
             Vec8<T>::store(at<T>(dst, dp, c), v);
         } else {
-            Vec8<T>::load(at<T>(dst, dp, c), v);
+            if (inside) Vec8<T>::load(at<T>(dst, dp, c), v);
+            else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            }
             Vec8<T>::store(at<T>(src, sp, q * C8 * 8 + c), v);
         }
     }
+}
+
+// Stride-2 convolutions on the stride-1 tensor-core kernels: a k x k (k = 3, 4) stride-2 conv over X equals a 2x2 stride-1
+// conv over the space-to-depth image X' (H/2, W/2, 4C), embedded here in a 3x3 kernel (taps with r2 = 2 or s2 = 2 are zero):
+//   w3[r2][s2][(2dy+dx)*Cin + ci][co] = w[2 r2 + dy - pt][2 s2 + dx - pl][ci][co]   (0 outside the k x k kernel)
+// with pt, pl in {0, 1} the leading padding.  dir 0 writes w3 from the master weights, dir 1 ADDS the gradient of w3
+// (written by the weight-gradient kernel) into the master gradient.
+__global__ void s2d_weights_kernel(float* __restrict__ w, int k, int pt, int pl, int Cin, int Cout, float* __restrict__ w3, int dir) {
+    const long long total = 9LL * 4 * Cin * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        long long t = i / Cout;
+        const int kk = (int)(t % (4 * Cin));
+        const int tap = (int)(t / (4 * Cin));
+        const int q = kk / Cin, ci = kk - q * Cin;
+        const int r2 = tap / 3, s2 = tap - 3 * r2;
+        const int r = 2 * r2 + (q >> 1) - pt, s_ = 2 * s2 + (q & 1) - pl;
+        const bool valid = r2 < 2 && s2 < 2 && r >= 0 && r < k && s_ >= 0 && s_ < k;
+        if (dir == 0) w3[i] = valid ? w[((size_t)(r * k + s_) * Cin + ci) * Cout + co] : 0.f;
+        else if (valid) w[((size_t)(r * k + s_) * Cin + ci) * Cout + co] += w3[i];      // the map valid (tap, kk) -> (r, s, ci) is injective
+    }
+}
+
+// stats[g][k][c] += sum_q temp[g][k][q*C + c]: moments of a depth-to-space output from the moments of its 4C-channel source
+__global__ void fold_stats4_kernel(const double* __restrict__ temp, double* __restrict__ stats, int groups, int C, int stats_nstride,
+                                   int stats_cstride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups * 2 * C) return;
+    const int c = i % C, k = (i / C) % 2, g = i / (2 * C);
+    const double* t = temp + ((size_t)g * 2 + k) * 4 * C;
+    stats[(size_t)g * stats_nstride + (size_t)k * stats_cstride + c] += ((t[c] + t[C + c]) + t[2 * C + c]) + t[3 * C + c];
 }
 
 static inline int grid_for(long long total, int block = 256) {
@@ -394,13 +440,37 @@ extern "C" int semb_cast_out(const semb_tensor* src, float* dst, int32_t dst_C, 
     return check_launch("cast_out");
 }
 
-extern "C" int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
-                                   const float* bias, int32_t dir, int32_t dtype, void* stream) {
+extern "C" int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W, int32_t DH,
+                                    int32_t DW, const float* bias, int32_t dir, int32_t acc, int32_t dtype, void* stream) {
     SEMB_REQUIRE(view_ok(src) && view_ok(dst) && src->C == 4 * dst->C, SEMB_ESHAPE, "pixel_shuffle2: src must have 4x the channels of dst");
-    SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && (dir == 0 || dir == 1), SEMB_ESHAPE, "pixel_shuffle2: bad geometry");
+    SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && (dir == 0 || dir == 1) && DH <= 2 * H && DW <= 2 * W && DH >= 2 * H - 1 && DW >= 2 * W - 1,
+                 SEMB_ESHAPE, "pixel_shuffle2: bad geometry");
     const int C8 = dst->C / 8;
     const long long total = (long long)N * H * W * 4 * C8;
-    if (dtype == SEMB_BF16) pixel_shuffle2_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, C8, bias, dir);
-    else pixel_shuffle2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, C8, bias, dir);
+    if (dtype == SEMB_BF16) pixel_shuffle2_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, DH, DW, C8, bias, dir, acc);
+    else pixel_shuffle2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, DH, DW, C8, bias, dir, acc);
     return check_launch("pixel_shuffle2");
+}
+
+extern "C" int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
+                                   const float* bias, int32_t dir, int32_t dtype, void* stream) {
+    return semb_pixel_shuffle2x(src, dst, N, H, W, 2 * H, 2 * W, bias, dir, 0, dtype, stream);
+}
+
+extern "C" int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t Cin, int32_t Cout, float* w3, int32_t dir,
+                                void* stream) {
+    SEMB_REQUIRE(w && w3 && (k == 3 || k == 4) && (pad_t == 0 || pad_t == 1) && (pad_l == 0 || pad_l == 1) && Cin > 0 && Cout > 0 &&
+                 (dir == 0 || dir == 1), SEMB_ESHAPE, "s2d_weights: bad arguments");
+    const long long total = 9LL * 4 * Cin * Cout;
+    s2d_weights_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(w, k, pad_t, pad_l, Cin, Cout, w3, dir);
+    return check_launch("s2d_weights");
+}
+
+extern "C" int semb_fold_stats4(const void* temp, void* stats, int32_t groups, int32_t C, int32_t stats_nstride, int32_t stats_cstride,
+                                void* stream) {
+    SEMB_REQUIRE(temp && stats && groups > 0 && C > 0, SEMB_ESHAPE, "fold_stats4: bad arguments");
+    const int n = groups * 2 * C;
+    fold_stats4_kernel<<<cdiv(n, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const double*>(temp), reinterpret_cast<double*>(stats), groups,
+                                                                    C, stats_nstride, stats_cstride);
+    return check_launch("fold_stats4");
 }

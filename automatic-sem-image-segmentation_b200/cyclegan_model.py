@@ -161,6 +161,7 @@ class CycleGanModel:
     def _adam(self, net: _Net):
         e = net.root
         e.lr.fill_(self.learning_rate)
+        e.fold_virtual_grads()          # gradients of the space-to-depth kernels -> Keras-layout gradients (before the all-reduce)
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(e.grads, op=dist.ReduceOp.SUM, group=self.process_group)
@@ -229,7 +230,7 @@ class CycleGanModel:
         self.DA_pool.in_buf.data.copy_(pa)
         self.DB_pool.in_buf.data.copy_(pb)
         for net in (self.disc_a, self.disc_b):
-            net.root.grads.zero_()
+            net.root.zero_grads()
         D = [self.DA_real, self.DA_pool, self.DB_real, self.DB_pool]
         for b in D:
             b.e.zero_step(False)

@@ -209,10 +209,13 @@ class Engine:
         # weight sharing between towers of the same network (CycleGAN applies each generator three times per step):
         # a sharing engine has its own buffers / ops / scratch but uses the root's parameters, gradients and packs
         self.share = share
+        # stride-2 convs on the stride-1 tensor-core kernels: virtual (3,3,4*Cin,Cout) kernels over the space-to-depth image
+        self.s2d: Dict[tuple, dict] = {}
         if share is not None:
             assert share.finalized and share.dtype == self.dtype
             self.params, self.state, self.specs, self.spec_order = share.params, share.state, share.specs, share.spec_order
             self.tc_packs = share.tc_packs
+            self.s2d = share.s2d
 
     # ---- construction ------------------------------------------------------------------
     def new_buf(self, h: int, w: int, pitch: int, name: str, requires_grad: bool = True, n: Optional[int] = None) -> Buf:
@@ -260,11 +263,42 @@ class Engine:
             pk["buf"] = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device=self.device)
         self.finalized = True
 
-    def tc_pack(self, w: str, R: int, S: int, cin: int, cout: int, flip: int) -> dict:
+    def s2d_weight(self, w: str, k: int, pt: int, pl: int, cin: int, cout: int) -> dict:
+        """Virtual fp32 kernel w3 (3,3,4*cin,cout) of the stride-2 conv `w` and the buffer its gradient is reduced into."""
+        root = self.share or self
+        key = (w, pt, pl)
+        rec = root.s2d.get(key)
+        if rec is None:
+            n = 9 * 4 * cin * cout
+            rec = {"w": w, "k": k, "pt": pt, "pl": pl, "cin": cin, "cout": cout, "key": f"{w}/s2d{pt}{pl}",
+                   "w3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None,
+                   "dw3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None}
+            root.s2d[key] = rec
+            root._pack_dirty = True
+        return rec
+
+    def zero_grads(self):
+        """Zeroes the flat gradient buffer and the gradients of the virtual stride-2 kernels."""
+        assert self.share is None
+        st = self.stream
+        L.check(self.lib.semb_fill_f32(self.grads.data_ptr(), self.grads.numel(), 0.0, st))
+        for rec in self.s2d.values():
+            L.check(self.lib.semb_fill_f32(rec["dw3"].data_ptr(), rec["dw3"].numel(), 0.0, st))
+
+    def fold_virtual_grads(self):
+        """Adds the gradients of the virtual stride-2 kernels into the Keras-layout gradients (before all-reduce / Adam)."""
+        assert self.share is None
+        st = self.stream
+        for rec in self.s2d.values():
+            L.check(self.lib.semb_s2d_weights(self.gptr(rec["w"]), rec["k"], rec["pt"], rec["pl"], rec["cin"], rec["cout"],
+                                              rec["dw3"].data_ptr(), 1, st))
+            L.check(self.lib.semb_fill_f32(rec["dw3"].data_ptr(), rec["dw3"].numel(), 0.0, st))
+
+    def tc_pack(self, w: str, R: int, S: int, cin: int, cout: int, flip: int, vw: Optional[dict] = None) -> dict:
         for pk in self.tc_packs:
             if pk["w"] == w and pk["flip"] == flip:
                 return pk
-        pk = {"w": w, "R": R, "S": S, "Cin": cin, "Cout": cout, "flip": flip, "buf": None}
+        pk = {"w": w, "R": R, "S": S, "Cin": cin, "Cout": cout, "flip": flip, "buf": None, "vw": vw}
         self.tc_packs.append(pk)
         root = self.share or self
         if root.finalized:      # a tower added after the root was finalised needs a pack the root never used
@@ -280,7 +314,8 @@ class Engine:
             host = np.zeros(n * int(self.lib.semb_pack_batch_job_size()), dtype=np.uint8)
             blocks = 0
             for i, pk in enumerate(self.tc_packs):
-                blocks = int(self.lib.semb_pack_batch_prepare(i, self.params.ptr(pk["w"]), pk["buf"].data_ptr(), pk["R"], pk["S"],
+                wptr = pk["vw"]["w3"].data_ptr() if pk.get("vw") else self.params.ptr(pk["w"])
+                blocks = int(self.lib.semb_pack_batch_prepare(i, wptr, pk["buf"].data_ptr(), pk["R"], pk["S"],
                                                                pk["Cin"], pk["Cout"], pk["flip"], blocks, host.ctypes.data))
                 if blocks < 0:
                     L.check(blocks)
@@ -292,6 +327,9 @@ class Engine:
         if self.share is not None:
             return self.share.repack()
         if not self.dry and self.tc_packs:
+            for rec in self.s2d.values():       # virtual stride-2 kernels follow the master weights first
+                L.check(self.lib.semb_s2d_weights(self.params.ptr(rec["w"]), rec["k"], rec["pt"], rec["pl"], rec["cin"], rec["cout"],
+                                                  rec["w3"].data_ptr(), 0, self.stream))
             table, n, blocks = self._pack_jobs()
             L.check(self.lib.semb_pack_weights_tc_batch(table.data_ptr(), n, blocks, self.stream))
         self._pack_dirty = False
@@ -341,7 +379,7 @@ class Engine:
         st = self.stream
         L.check(self.lib.semb_fill_f32(self.zeroed.t.data_ptr(), self.zeroed.t.numel(), 0.0, st))
         if zero_grads and self.share is None:
-            L.check(self.lib.semb_fill_f32(self.grads.data_ptr(), self.grads.numel(), 0.0, st))
+            self.zero_grads()
 
     def forward(self, training: bool):
         if self.dry:
@@ -369,6 +407,8 @@ class Engine:
             fn()
 
     def adam(self, beta1: float, beta2: float, eps: float, gscale: float = 1.0):
+        if self.s2d:
+            self.fold_virtual_grads()       # no-op when the caller already folded (dw3 is zero again)
         L.check(self.lib.semb_adam_step(self.params.t.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                                         self.adam_v.data_ptr(), self.params.t.numel(), self.lr.data_ptr(),
                                         beta1, beta2, eps, gscale, self.adam_state.data_ptr(), self.stream))
@@ -438,6 +478,27 @@ class ConvOp(Op):
             self.pad_buf = eng.new_buf(hp, wp, x.C, f"{w}_dxpad", n=n)
             self.pad_hw = (hp, wp)
             self.geom_p = L.ConvGeom(n, hp, wp, oh, ow, cin, cout, k, k, stride, 0, 0, L.PAD_ZERO, eng.dtype)
+        # Stride-2 3x3 / 4x4 convs (CycleGAN down / up-sampling, PatchGAN): 3x3-embedded 2x2 stride-1 conv over the
+        # space-to-depth image of the big tensor, on the TMA / tcgen05 kernels (2.25x the FLOPs, but ~30x the CUDA-core rate).
+        self.s2d = None
+        if (eng.tc_enabled and stride == 2 and k in (3, 4) and pad_mode == L.PAD_ZERO and pad_tl[0] in (0, 1) and pad_tl[1] in (0, 1)
+                and not (transposed and bias is not None and stats is not None) and _os.environ.get("SEMB_NO_S2D") is None):
+            pt, pl = pad_tl
+            h2, w2 = (h + 1) // 2, (wd + 1) // 2
+            rec = eng.s2d_weight(w, k, pt, pl, cin, cout)
+            big = y if transposed else x
+            self.b2 = eng.new_buf(h2, w2, 4 * cin, f"{w}_s2d", requires_grad=big.requires_grad, n=n)
+            self.s2d = rec
+            self.s2d_hw = (h2, w2)
+            self.geom_s = L.ConvGeom(n, h2, w2, oh, ow, 4 * cin, cout, 3, 3, 1, pt, pl, L.PAD_ZERO, eng.dtype)       # big' -> small
+            self.geom_t = L.ConvGeom(n, oh, ow, h2, w2, cout, 4 * cin, 3, 3, 1, 2 - pt, 2 - pl, L.PAD_ZERO, eng.dtype)  # small -> big'
+            self.pk_s = eng.tc_pack(rec["key"], 3, 3, 4 * cin, cout, 0, vw=rec)
+            self.pk_t = eng.tc_pack(rec["key"], 3, 3, 4 * cin, cout, 1, vw=rec)
+            self.stats4 = None
+            if transposed and stats is not None:
+                groups = n if stats[2] != 0 else 1
+                self.stats4 = eng.zeroed.add(f"{w}/s2d_moments_{len(eng.ops)}", 2 * groups * 2 * 4 * cin)     # fp64: 2 floats each
+                self.stats4_groups = groups
         # Reflect-padded tensor-core convs (CycleGAN residual blocks): the padded input is materialised once per forward
         # (a cheap copy next to a 512->512 conv) so that forward and weight gradient run the TMA kernels as zero-pad
         # "valid" convolutions over it; the data gradient already works on the padded domain (pad_buf above).
@@ -471,10 +532,59 @@ class ConvOp(Op):
         name, off, ns, cs = self.stats
         return self.eng.zeroed.ptr(name, 2 * off), ns, cs      # offsets/strides are in doubles
 
+    def _shuffle(self, four: L.Tensor, full: L.Tensor, direction: int, bias=None, acc: int = 0):
+        g = self.geom
+        e = self.eng
+        L.check(e.lib.semb_pixel_shuffle2x(C.byref(four), C.byref(full), g.N, self.s2d_hw[0], self.s2d_hw[1], g.H, g.W, bias,
+                                           direction, acc, e.dtype, e.stream))
+
+    def _fwd_s2d(self, training: bool, sp, ns, cs, bias):
+        e = self.eng
+        b2 = self.b2.view()
+        if not self.transposed:
+            self._shuffle(b2.t, self.x.t, 1)                                                   # space-to-depth of the input
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_s), C.byref(b2.t), self.pk_s["buf"].data_ptr(), bias, C.byref(self.y.t),
+                                             sp, ns, cs, 0, e.stream))
+            return
+        t4, n4, c4 = (None, 0, 0)
+        if sp is not None:
+            c4 = 4 * self.geom.Cin
+            n4 = 2 * c4 if self.stats4_groups > 1 else 0
+            t4 = e.zeroed.ptr(self.stats4)
+        L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_t), C.byref(self.x.t), self.pk_t["buf"].data_ptr(), None, C.byref(b2.t),
+                                         t4, n4, c4, 0, e.stream))
+        self._shuffle(b2.t, self.y.t, 0, bias=bias)                                            # depth-to-space (+ bias)
+        if sp is not None:
+            L.check(e.lib.semb_fold_stats4(t4, sp, self.stats4_groups, self.geom.Cin, ns, cs, e.stream))
+
+    def _bwd_s2d(self):
+        e = self.eng
+        dbias = e.gptr(self.bias) if self.bias else None
+        b2 = self.b2.view()
+        dw3 = self.s2d["dw3"].data_ptr()
+        if not self.transposed:
+            e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom_s), C.byref(b2.t), C.byref(self.y.g), dw3, e.stream)))
+            if dbias:
+                L.check(e.lib.semb_channel_sum(C.byref(self.y.g), self.geom.N, self.geom.OH * self.geom.OW, dbias, e.dtype, e.stream))
+            if self.x.requires_grad:
+                L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_t), C.byref(self.y.g), self.pk_t["buf"].data_ptr(), None, C.byref(b2.g),
+                                                 None, 0, 0, 0, e.stream))
+                self._shuffle(b2.g, self.x.g, 0, acc=self.acc_x)
+            return
+        self._shuffle(b2.g, self.y.g, 1)                                                       # space-to-depth of the output gradient
+        e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom_s), C.byref(b2.g), C.byref(self.x.t), dw3, e.stream)))
+        if dbias:
+            L.check(e.lib.semb_channel_sum(C.byref(self.y.g), self.geom.N, self.geom.H * self.geom.W, dbias, e.dtype, e.stream))
+        if self.x.requires_grad:
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_s), C.byref(b2.g), self.pk_s["buf"].data_ptr(), None, C.byref(self.x.g),
+                                             None, 0, 0, self.acc_x, e.stream))
+
     def fwd(self, training: bool):
         e = self.eng
         sp, ns, cs = self._stats_args() if training else (None, 0, 0)
         bias = e.params.ptr(self.bias) if self.bias else None
+        if self.s2d is not None:
+            return self._fwd_s2d(training, sp, ns, cs, bias)
         if self.use_tc and self.x_pad is not None:
             g = self.geom
             xp = self.x_pad.view()
@@ -493,6 +603,8 @@ class ConvOp(Op):
 
     def bwd(self):
         e = self.eng
+        if self.s2d is not None:
+            return self._bwd_s2d()
         dbias = e.gptr(self.bias) if self.bias else None
         if not self.transposed:
             if self.use_tc and dbias is None and self.x_pad is not None:

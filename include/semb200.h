@@ -137,6 +137,20 @@ int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void
  * HWIO gradient with coalesced reductions.  Same contract as semb_conv2d_wgrad without dbias. */
 int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* stream);
 
+/* ---- stride-2 convolutions on the stride-1 tensor-core kernels (space-to-depth) ------------------------------
+ * A k x k (k = 3, 4) stride-2 Conv2D / Conv2DTranspose (CycleGAN.py:339-358, 425-451) is run as a 3x3-embedded 2x2
+ * stride-1 conv over the space-to-depth image (H/2, W/2, 4C): semb_pixel_shuffle2x moves activations between the two
+ * domains (DH x DW is the true size of the full-resolution tensor, 2H-1 <= DH <= 2H: a missing last row / column reads
+ * as zero and is not written; acc = 1 accumulates in dir 0), semb_s2d_weights builds the virtual fp32 HWIO kernel
+ * w3 (3,3,4*Cin,Cout) from the Keras kernel (dir 0) or adds the gradient of w3 into the Keras gradient (dir 1), and
+ * semb_fold_stats4 turns the moments of a 4C-channel space-to-depth tensor into those of its C-channel image. */
+int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W, int32_t DH,
+                         int32_t DW, const float* bias, int32_t dir, int32_t acc, int32_t dtype, void* stream);
+int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t Cin, int32_t Cout, float* w3, int32_t dir,
+                     void* stream);
+int semb_fold_stats4(const void* temp, void* stats, int32_t groups, int32_t C, int32_t stats_nstride, int32_t stats_cstride,
+                     void* stream);
+
 /* ---- normalisation + activation (fused elementwise) --------------------------------------- */
 
 /* From moments to the affine that BatchNormalization / GroupNormalization applies.

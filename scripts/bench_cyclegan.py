@@ -30,6 +30,12 @@ b = (torch.rand(n, sz, sz, 1, generator=g) * 2 - 1).numpy()
 for _ in range(2):
     logs = m.train_step((a, b))
 torch.cuda.synchronize()
+if os.environ.get("PROFILE"):          # ncu --profile-from-start off: one profiled step
+    torch.cuda.cudart().cudaProfilerStart()
+    m.train_step((a, b))
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    sys.exit(0)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record()
 for _ in range(args.steps):

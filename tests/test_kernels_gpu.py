@@ -590,3 +590,68 @@ def test_conv_tc_wgrad(case):
         assert float(got[:, :, cin:, :].abs().max()) == 0
     if cpo > cout:
         assert float(got[:, :, :, cout:].abs().max()) == 0
+
+
+# ---- stride-2 convs on the stride-1 tensor-core kernels (space-to-depth) ---------------------------------------------
+# (n, h, w, cin, cout, k, (pad_t, pad_l), transposed)
+S2D_CASES = [
+    (2, 32, 32, 16, 24, 3, (0, 0), False),      # generator downsample: 3x3 s2 'same' on an even size (pad 0 before, 1 after)
+    (1, 30, 22, 8, 16, 4, (0, 0), False),       # PatchGAN: 4x4 s2 valid
+    (2, 31, 27, 13, 8, 4, (0, 0), False),       # odd input size (127 -> 62 in the real discriminator), padded channel lanes
+    (2, 16, 16, 24, 16, 3, (1, 1), True),       # generator upsample: Conv2DTranspose 3x3 s2 'same'
+]
+
+
+@pytest.mark.parametrize("case", S2D_CASES)
+def test_strided_conv_space_to_depth(case):
+    """ConvOp in space-to-depth mode (forward, data gradient, weight gradient folded back into the Keras-layout gradient)
+    against torch on bf16-rounded operands."""
+    import numpy as np
+    import torch.nn.functional as F
+    from sem_b200.engine import ConvOp, Engine, ParamSpec
+    n, h, w_, cin, cout, k, (pt, pl), transposed = case
+    g = torch.Generator().manual_seed(17)
+    cpi, cpo = U.pad8(cin), U.pad8(cout)
+    if not transposed:
+        oh, ow = (h + 1) // 2 if k == 3 else (h - 4) // 2 + 1, (w_ + 1) // 2 if k == 3 else (w_ - 4) // 2 + 1
+        x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+        wt = U.bf16_round(torch.randn(k, k, cin, cout, generator=g) * 0.1)          # Keras HWIO
+        xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        xp = F.pad(xr.permute(0, 3, 1, 2), (pl, 2 * ow + k, pt, 2 * oh + k))          # generous trailing zeros, cropped by the output size
+        y_ref = F.conv2d(xp, wr.permute(3, 2, 0, 1), stride=2)[:, :, :oh, :ow].permute(0, 2, 3, 1)
+        in_hw, out_hw, lw, pw = (h, w_), (oh, ow), (k, k, cin, cout), (k, k, cpi, cpo)
+        maps = {2: np.arange(cin), 3: np.arange(cout)}
+    else:
+        oh, ow = 2 * h, 2 * w_                                                     # x is the SMALL tensor, cin -> cout channels
+        x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+        wt = U.bf16_round(torch.randn(k, k, cout, cin, generator=g) * 0.1)          # Keras Conv2DTranspose kernel (kh,kw,Cout,Cin)
+        xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+        y_ref = F.conv_transpose2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), stride=2, padding=1, output_padding=1).permute(0, 2, 3, 1)
+        in_hw, out_hw, lw, pw = (h, w_), (oh, ow), (k, k, cout, cin), (k, k, cpo, cpi)
+        maps = {2: np.arange(cout), 3: np.arange(cin)}
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+
+    e = Engine(n, "bf16")
+    xb = e.new_buf(in_hw[0], in_hw[1], cpi, "x")
+    yb = e.new_buf(out_hw[0], out_hw[1], cpo, "y")
+    e.add_param(ParamSpec("w/kernel", "conv_kernel", lw, pw, maps, True, "glorot", (1, 1)))
+    op = e.add_op(ConvOp(e, xb.view(), yb.view(), in_hw, out_hw, "w/kernel", None, k, 2, (pt, pl), L.PAD_ZERO, transposed))
+    assert op.s2d is not None
+    e.finalize()
+    e.set_param("w/kernel", wt.numpy())
+    xb.data[..., :cin] = x.cuda().to(torch.bfloat16)
+    e.zero_step(zero_grads=True)
+    e.forward(True)
+    torch.cuda.synchronize()
+    assert U.rel_err(yb.data[..., :cout].float(), y_ref) < 1e-2
+    if cpo > cout:
+        assert float(yb.data[..., cout:].abs().max()) == 0
+    yb.grad_tensor()[..., :cout] = dy.cuda().to(torch.bfloat16)
+    xb.grad_tensor().fill_(1.0)
+    op.acc_x = 1                                   # accumulate on top of ones
+    e.backward()
+    e.fold_virtual_grads()
+    torch.cuda.synchronize()
+    assert U.rel_err(xb.grad_tensor()[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
+    assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 1e-3
