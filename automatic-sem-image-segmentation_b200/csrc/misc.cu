@@ -10,6 +10,9 @@ __device__ __forceinline__ T* at(const PView& v, size_t pixel, int c) {
     return reinterpret_cast<T*>(v.ptr) + pixel * v.pitch + v.coff + c;
 }
 
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+
 // ---- MaxPooling2D((2,2)) ------------------------------------------------------------------------
 template <typename T, bool BWD>
 __global__ void maxpool_kernel(PView x, PView y /* fwd: out, bwd: dy */, PView dx, int N, int H, int W, int C8, int acc) {
@@ -333,6 +336,81 @@ __global__ void fold_stats4_kernel(const double* __restrict__ temp, double* __re
     stats[(size_t)g * stats_nstride + (size_t)k * stats_cstride + c] += ((t[c] + t[C + c]) + t[2 * C + c]) + t[3 * C + c];
 }
 
+// ---- 7x7 single-channel convs (CycleGAN generator stem 1->F and head F->1) as 1x1 tensor-core convs ------------------
+// "big" is the reflect-padded domain (H+k-1, W+k-1), "small" the output domain (H, W); T8 = pad8(k*k) tap channels.
+//   mode 0  patches[p][t]   = big[p + (r,s)][0]                       (stem forward: im2col of ONE channel)
+//   mode 1  dbig[u][0]      = sum_t dpatches[u - (r,s)][t]            (stem data gradient, padded domain)
+//   mode 2  small[p][0]     = bias + sum_t zbig[p + (r,s)][t]         (head forward: shift-and-add of the per-tap 1x1 conv)
+//   mode 3  dzbig[u][t]     = dsmall[u - (r,s)][0]                    (head backward)
+// channel lanes beyond the real ones are written as zeros.
+template <typename T>
+__global__ void tap_patch_kernel(PView small, PView big, int N, int H, int W, int k, int T8, const float* __restrict__ bias, int mode) {
+    const int BH = H + k - 1, BW = W + k - 1, taps = k * k;
+    if (mode == 0 || mode == 3) {
+        // one thread = 8 tap channels of one pixel (mode 0: output pixel p of `small`-sized patches; mode 3: padded pixel u)
+        const int OHh = mode == 0 ? H : BH, OWw = mode == 0 ? W : BW;
+        const int G = T8 / 8;
+        const long long total = (long long)N * OHh * OWw * G;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int g = (int)(i % G);
+            long long t = i / G;
+            const int x = (int)(t % OWw), y = (int)((t / OWw) % OHh), n = (int)(t / ((long long)OWw * OHh));
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int tp = g * 8 + j;
+                v[j] = 0.f;
+                if (tp < taps) {
+                    const int r = tp / k, s_ = tp - r * k;
+                    if (mode == 0) {
+                        v[j] = to_f(at<T>(big, ((size_t)n * BH + y + r) * BW + x + s_, 0)[0]);
+                    } else {
+                        const int py = y - r, px = x - s_;
+                        if (py >= 0 && py < H && px >= 0 && px < W) v[j] = to_f(at<T>(small, ((size_t)n * H + py) * W + px, 0)[0]);
+                    }
+                }
+            }
+            if (mode == 0) Vec8<T>::store(at<T>(small, ((size_t)n * H + y) * W + x, g * 8), v);      // `small` view = the patches tensor
+            else Vec8<T>::store(at<T>(big, ((size_t)n * BH + y) * BW + x, g * 8), v);
+        }
+    } else {
+        // one thread = one pixel, sums over all taps into channel 0
+        const int OHh = mode == 1 ? BH : H, OWw = mode == 1 ? BW : W;
+        const long long total = (long long)N * OHh * OWw;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int x = (int)(i % OWw), y = (int)((i / OWw) % OHh), n = (int)(i / ((long long)OWw * OHh));
+            float acc = (mode == 2 && bias) ? bias[0] : 0.f;
+            for (int tp = 0; tp < taps; ++tp) {
+                const int r = tp / k, s_ = tp - r * k;
+                if (mode == 2) {
+                    acc += to_f(at<T>(big, ((size_t)n * BH + y + r) * BW + x + s_, tp)[0]);
+                } else {
+                    const int py = y - r, px = x - s_;
+                    if (py >= 0 && py < H && px >= 0 && px < W) acc += to_f(at<T>(small, ((size_t)n * H + py) * W + px, tp)[0]);
+                }
+            }
+            float v[8] = {acc, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (mode == 2) Vec8<T>::store(at<T>(small, ((size_t)n * H + y) * W + x, 0), v);
+            else Vec8<T>::store(at<T>(big, ((size_t)n * BH + y) * BW + x, 0), v);
+        }
+    }
+}
+
+// virtual 1x1 kernels of the tap-folded 7x7 convs.  kind 0 (stem, Cin = 1): w1[t][co] <-> w[t][ci = 0][co];
+// kind 1 (head, Cout = 1): w1[ci][t] <-> w[t][ci][co = 0].  dir 0 writes w1, dir 1 adds the gradient of w1 into w.
+__global__ void tapfold_weights_kernel(float* __restrict__ w, int taps, int T8, int Cin, int Cout, float* __restrict__ w1, int kind, int dir) {
+    const int rows = kind == 0 ? T8 : Cin, cols = kind == 0 ? Cout : T8;
+    const long long total = (long long)rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cols), r = (int)(i / cols);
+        const int t = kind == 0 ? r : c;
+        const bool valid = t < taps;
+        const size_t m = kind == 0 ? ((size_t)t * Cin + 0) * Cout + c : ((size_t)t * Cin + r) * Cout + 0;
+        if (dir == 0) w1[i] = valid ? w[m] : 0.f;
+        else if (valid) w[m] += w1[i];
+    }
+}
+
 static inline int grid_for(long long total, int block = 256) {
     long long b = cdivl(total, block);
     const long long cap = 148LL * 16;
@@ -473,4 +551,27 @@ extern "C" int semb_fold_stats4(const void* temp, void* stats, int32_t groups, i
     fold_stats4_kernel<<<cdiv(n, 128), 128, 0, as_stream(stream)>>>(reinterpret_cast<const double*>(temp), reinterpret_cast<double*>(stats), groups,
                                                                     C, stats_nstride, stats_cstride);
     return check_launch("fold_stats4");
+}
+
+extern "C" int semb_tap_patch(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t k,
+                              const float* bias, int32_t mode, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(small) && view_ok(big) && N > 0 && H > 0 && W > 0 && k > 1 && mode >= 0 && mode <= 3, SEMB_ESHAPE, "tap_patch: bad arguments");
+    const int T8 = (k * k + 7) / 8 * 8;
+    // the tap-channel tensor is `small` in modes 0/1 (patches) and `big` in modes 2/3 (per-tap conv on the padded domain)
+    SEMB_REQUIRE((mode <= 1 ? small->C : big->C) == T8, SEMB_ESHAPE, "tap_patch: the tap tensor needs %d channels", T8);
+    const long long total = mode == 0 ? (long long)N * H * W * (T8 / 8)
+                          : mode == 3 ? (long long)N * (H + k - 1) * (W + k - 1) * (T8 / 8)
+                          : mode == 1 ? (long long)N * (H + k - 1) * (W + k - 1) : (long long)N * H * W;
+    if (dtype == SEMB_BF16) tap_patch_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, k, T8, bias, mode);
+    else tap_patch_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, k, T8, bias, mode);
+    return check_launch("tap_patch");
+}
+
+extern "C" int semb_tapfold_weights(float* w, int32_t k, int32_t Cin, int32_t Cout, float* w1, int32_t kind, int32_t dir, void* stream) {
+    SEMB_REQUIRE(w && w1 && k > 1 && Cin > 0 && Cout > 0 && (kind == 0 || kind == 1) && (dir == 0 || dir == 1), SEMB_ESHAPE,
+                 "tapfold_weights: bad arguments");
+    const int T8 = (k * k + 7) / 8 * 8;
+    const long long total = (long long)T8 * (kind == 0 ? Cout : Cin);
+    tapfold_weights_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(w, k * k, T8, Cin, Cout, w1, kind, dir);
+    return check_launch("tapfold_weights");
 }

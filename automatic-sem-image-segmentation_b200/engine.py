@@ -270,12 +270,36 @@ class Engine:
         rec = root.s2d.get(key)
         if rec is None:
             n = 9 * 4 * cin * cout
-            rec = {"w": w, "k": k, "pt": pt, "pl": pl, "cin": cin, "cout": cout, "key": f"{w}/s2d{pt}{pl}",
+            rec = {"kind": "s2d", "w": w, "k": k, "pt": pt, "pl": pl, "cin": cin, "cout": cout, "key": f"{w}/s2d{pt}{pl}",
                    "w3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None,
                    "dw3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None}
             root.s2d[key] = rec
             root._pack_dirty = True
         return rec
+
+    def tapfold_weight(self, w: str, k: int, cin: int, cout: int, kind: str) -> dict:
+        """Virtual 1x1 kernel of a k x k conv with ONE input channel ('stem': (T8, cout)) or ONE output channel
+        ('head': (cin, T8)), T8 = pad8(k*k); see semb_tapfold_weights."""
+        root = self.share or self
+        key = (w, kind)
+        rec = root.s2d.get(key)
+        if rec is None:
+            t8 = (k * k + 7) // 8 * 8
+            n = t8 * (cout if kind == "stem" else cin)
+            rec = {"kind": kind, "w": w, "k": k, "cin": cin, "cout": cout, "key": f"{w}/{kind}", "t8": t8,
+                   "w3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None,
+                   "dw3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None}
+            root.s2d[key] = rec
+            root._pack_dirty = True
+        return rec
+
+    def _virtual_weight_kernel(self, rec: dict, master_ptr: int, virt_ptr: int, direction: int):
+        if rec["kind"] == "s2d":
+            L.check(self.lib.semb_s2d_weights(master_ptr, rec["k"], rec["pt"], rec["pl"], rec["cin"], rec["cout"], virt_ptr, direction,
+                                              self.stream))
+        else:
+            L.check(self.lib.semb_tapfold_weights(master_ptr, rec["k"], rec["cin"], rec["cout"], virt_ptr,
+                                                  0 if rec["kind"] == "stem" else 1, direction, self.stream))
 
     def zero_grads(self):
         """Zeroes the flat gradient buffer and the gradients of the virtual stride-2 kernels."""
@@ -290,8 +314,7 @@ class Engine:
         assert self.share is None
         st = self.stream
         for rec in self.s2d.values():
-            L.check(self.lib.semb_s2d_weights(self.gptr(rec["w"]), rec["k"], rec["pt"], rec["pl"], rec["cin"], rec["cout"],
-                                              rec["dw3"].data_ptr(), 1, st))
+            self._virtual_weight_kernel(rec, self.gptr(rec["w"]), rec["dw3"].data_ptr(), 1)
             L.check(self.lib.semb_fill_f32(rec["dw3"].data_ptr(), rec["dw3"].numel(), 0.0, st))
 
     def tc_pack(self, w: str, R: int, S: int, cin: int, cout: int, flip: int, vw: Optional[dict] = None) -> dict:
@@ -327,9 +350,8 @@ class Engine:
         if self.share is not None:
             return self.share.repack()
         if not self.dry and self.tc_packs:
-            for rec in self.s2d.values():       # virtual stride-2 kernels follow the master weights first
-                L.check(self.lib.semb_s2d_weights(self.params.ptr(rec["w"]), rec["k"], rec["pt"], rec["pl"], rec["cin"], rec["cout"],
-                                                  rec["w3"].data_ptr(), 0, self.stream))
+            for rec in self.s2d.values():       # virtual (space-to-depth / tap-folded) kernels follow the master weights first
+                self._virtual_weight_kernel(rec, self.params.ptr(rec["w"]), rec["w3"].data_ptr(), 0)
             table, n, blocks = self._pack_jobs()
             L.check(self.lib.semb_pack_weights_tc_batch(table.data_ptr(), n, blocks, self.stream))
         self._pack_dirty = False
@@ -499,6 +521,32 @@ class ConvOp(Op):
                 groups = n if stats[2] != 0 else 1
                 self.stats4 = eng.zeroed.add(f"{w}/s2d_moments_{len(eng.ops)}", 2 * groups * 2 * 4 * cin)     # fp64: 2 floats each
                 self.stats4_groups = groups
+        # 7x7 reflect-padded convs with ONE input channel (generator stem) or ONE output channel (head): the 49 taps become
+        # channels of a 1x1 tensor-core conv (im2col of a single channel / shift-and-add of a per-tap conv); on the CUDA
+        # cores these two layers took 144 of the 215 ms of a CycleGAN step.
+        self.tapfold = None
+        lshape = eng.specs[w].logical_shape if w in eng.specs else (k, k, cin, cout)       # LOGICAL channel counts decide
+        if (eng.tc_enabled and k == 7 and stride == 1 and pad_mode == L.PAD_REFLECT and tuple(pad_tl) == (3, 3) and not transposed
+                and (lshape[2] == 1 or lshape[3] == 1) and _os.environ.get("SEMB_NO_TAPFOLD") is None):
+            kind = "stem" if lshape[2] == 1 else "head"
+            if not (kind == "head" and stats is not None):
+                rec = eng.tapfold_weight(w, k, cin, cout, kind)
+                t8 = rec["t8"]
+                self.tapfold = rec
+                self.tf_xpad = eng.new_buf(h + k - 1, wd + k - 1, cin, f"{w}_xpad", requires_grad=x.requires_grad, n=n)
+                if kind == "stem":
+                    self.tf_mid = eng.new_buf(h, wd, t8, f"{w}_patches", requires_grad=x.requires_grad, n=n)
+                    self.geom1 = L.ConvGeom(n, h, wd, h, wd, t8, cout, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
+                    self.geom1d = L.ConvGeom(n, h, wd, h, wd, cout, t8, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
+                    self.pk1 = eng.tc_pack(rec["key"], 1, 1, t8, cout, 0, vw=rec)
+                    self.pk1d = eng.tc_pack(rec["key"], 1, 1, t8, cout, 1, vw=rec) if x.requires_grad else None
+                else:
+                    hp, wp = h + k - 1, wd + k - 1
+                    self.tf_mid = eng.new_buf(hp, wp, t8, f"{w}_ztaps", requires_grad=True, n=n)
+                    self.geom1 = L.ConvGeom(n, hp, wp, hp, wp, cin, t8, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
+                    self.geom1d = L.ConvGeom(n, hp, wp, hp, wp, t8, cin, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
+                    self.pk1 = eng.tc_pack(rec["key"], 1, 1, cin, t8, 0, vw=rec)
+                    self.pk1d = eng.tc_pack(rec["key"], 1, 1, cin, t8, 1, vw=rec) if x.requires_grad else None
         # Reflect-padded tensor-core convs (CycleGAN residual blocks): the padded input is materialised once per forward
         # (a cheap copy next to a 512->512 conv) so that forward and weight gradient run the TMA kernels as zero-pad
         # "valid" convolutions over it; the data gradient already works on the padded domain (pad_buf above).
@@ -579,10 +627,50 @@ class ConvOp(Op):
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_s), C.byref(b2.g), self.pk_s["buf"].data_ptr(), None, C.byref(self.x.g),
                                              None, 0, 0, self.acc_x, e.stream))
 
+    def _fwd_tapfold(self, sp, ns, cs, bias):
+        e, g = self.eng, self.geom
+        xp, mid = self.tf_xpad.view(), self.tf_mid.view()
+        L.check(e.lib.semb_pad_crop(C.byref(self.x.t), C.byref(xp.t), g.N, g.H, g.W, g.H + g.R - 1, g.W + g.S - 1, g.pad_t, g.pad_l, 0,
+                                    e.dtype, 0, e.stream))
+        if self.tapfold["kind"] == "stem":
+            L.check(e.lib.semb_tap_patch(C.byref(mid.t), C.byref(xp.t), g.N, g.H, g.W, g.R, None, 0, e.dtype, e.stream))
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1), C.byref(mid.t), self.pk1["buf"].data_ptr(), bias, C.byref(self.y.t),
+                                             sp, ns, cs, 0, e.stream))
+        else:
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1), C.byref(xp.t), self.pk1["buf"].data_ptr(), None, C.byref(mid.t),
+                                             None, 0, 0, 0, e.stream))
+            L.check(e.lib.semb_tap_patch(C.byref(self.y.t), C.byref(mid.t), g.N, g.H, g.W, g.R, bias, 2, e.dtype, e.stream))
+
+    def _bwd_tapfold(self):
+        e, g = self.eng, self.geom
+        xp, mid = self.tf_xpad.view(), self.tf_mid.view()
+        dw1 = self.tapfold["dw3"].data_ptr()
+        dbias = e.gptr(self.bias) if self.bias else None
+        if dbias:
+            L.check(e.lib.semb_channel_sum(C.byref(self.y.g), g.N, g.OH * g.OW, dbias, e.dtype, e.stream))
+        if self.tapfold["kind"] == "stem":
+            e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom1), C.byref(mid.t), C.byref(self.y.g), dw1, e.stream)))
+            if not self.x.requires_grad:
+                return
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1d), C.byref(self.y.g), self.pk1d["buf"].data_ptr(), None, C.byref(mid.g),
+                                             None, 0, 0, 0, e.stream))
+            L.check(e.lib.semb_tap_patch(C.byref(mid.g), C.byref(xp.g), g.N, g.H, g.W, g.R, None, 1, e.dtype, e.stream))
+        else:
+            L.check(e.lib.semb_tap_patch(C.byref(self.y.g), C.byref(mid.g), g.N, g.H, g.W, g.R, None, 3, e.dtype, e.stream))
+            e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom1), C.byref(xp.t), C.byref(mid.g), dw1, e.stream)))
+            if not self.x.requires_grad:
+                return
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1d), C.byref(mid.g), self.pk1d["buf"].data_ptr(), None, C.byref(xp.g),
+                                             None, 0, 0, 0, e.stream))
+        L.check(e.lib.semb_pad_crop(C.byref(xp.g), C.byref(self.x.g), g.N, g.H + g.R - 1, g.W + g.S - 1, g.H, g.W, g.pad_t, g.pad_l, 3,
+                                    e.dtype, self.acc_x, e.stream))
+
     def fwd(self, training: bool):
         e = self.eng
         sp, ns, cs = self._stats_args() if training else (None, 0, 0)
         bias = e.params.ptr(self.bias) if self.bias else None
+        if self.tapfold is not None:
+            return self._fwd_tapfold(sp, ns, cs, bias)
         if self.s2d is not None:
             return self._fwd_s2d(training, sp, ns, cs, bias)
         if self.use_tc and self.x_pad is not None:
@@ -603,6 +691,8 @@ class ConvOp(Op):
 
     def bwd(self):
         e = self.eng
+        if self.tapfold is not None:
+            return self._bwd_tapfold()
         if self.s2d is not None:
             return self._bwd_s2d()
         dbias = e.gptr(self.bias) if self.bias else None

@@ -151,6 +151,18 @@ int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t 
 int semb_fold_stats4(const void* temp, void* stats, int32_t groups, int32_t C, int32_t stats_nstride, int32_t stats_cstride,
                      void* stream);
 
+/* ---- 7x7 single-channel convolutions as 1x1 tensor-core convolutions (CycleGAN.py:372, 393: generator stem / head) ----
+ * "big" is the reflect-padded domain (N, H+k-1, W+k-1, .), "small" the output domain (N, H, W, .), T8 = pad8(k*k):
+ *   mode 0  small = patches (T8 ch):  patches[p][t] = big[p + (r,s)][0]                (stem forward)
+ *   mode 1  dbig[u][0] = sum_t dpatches[u - (r,s)][t]                                   (stem data gradient)
+ *   mode 2  small[p][0] = bias[0] + sum_t big[p + (r,s)][t],  big = per-tap 1x1 conv    (head forward)
+ *   mode 3  dbig[u][t] = dsmall[u - (r,s)][0]                                           (head backward)
+ * semb_tapfold_weights maps the Keras kernel to the virtual 1x1 kernel (kind 0: w1[t][co] = w[t][0][co]; kind 1:
+ * w1[ci][t] = w[t][ci][0]; dir 0 writes w1, dir 1 adds the gradient of w1 into the Keras-layout gradient). */
+int semb_tap_patch(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t k,
+                   const float* bias, int32_t mode, int32_t dtype, void* stream);
+int semb_tapfold_weights(float* w, int32_t k, int32_t Cin, int32_t Cout, float* w1, int32_t kind, int32_t dir, void* stream);
+
 /* ---- normalisation + activation (fused elementwise) --------------------------------------- */
 
 /* From moments to the affine that BatchNormalization / GroupNormalization applies.

@@ -655,3 +655,53 @@ def test_strided_conv_space_to_depth(case):
     torch.cuda.synchronize()
     assert U.rel_err(xb.grad_tensor()[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
     assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 1e-3
+
+
+# ---- 7x7 reflect-padded convs with one input / one output channel as 1x1 tensor-core convs ------------------------------
+@pytest.mark.parametrize("case", [(2, 20, 16, 1, 24, False), (1, 18, 26, 16, 1, True), (2, 16, 16, 64, 1, True)])
+def test_conv7x7_tap_folding(case):
+    """Generator stem (1 -> F) and head (F -> 1, bias) of CycleGAN.py:372,393 through ConvOp's tap-folded tensor-core path."""
+    import numpy as np
+    from sem_b200.engine import ConvOp, Engine, ParamSpec
+    n, h, w_, cin, cout, has_bias = case
+    g = torch.Generator().manual_seed(23)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wt = U.bf16_round(torch.randn(7, 7, cin, cout, generator=g) * 0.1)
+    bias = torch.randn(cout, generator=g) if has_bias else None
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True) if has_bias else None
+    y_ref = OL.conv2d(OL.reflection_pad(xr, 6, 6), wr, br, 1, "valid")
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    cpi, cpo = U.pad8(cin), U.pad8(cout)
+    e = Engine(n, "bf16")
+    xb = e.new_buf(h, w_, cpi, "x")
+    yb = e.new_buf(h, w_, cpo, "y")
+    e.add_param(ParamSpec("w/kernel", "conv_kernel", (7, 7, cin, cout), (7, 7, cpi, cpo), {2: np.arange(cin), 3: np.arange(cout)}, True,
+                          "glorot", (1, 1)))
+    if has_bias:
+        e.add_param(ParamSpec("w/bias", "vector", (cout,), (cpo,), {0: np.arange(cout)}, True, "zeros"))
+    op = e.add_op(ConvOp(e, xb.view(), yb.view(), (h, w_), (h, w_), "w/kernel", "w/bias" if has_bias else None, 7, 1, (3, 3),
+                         L.PAD_REFLECT, False))
+    assert op.tapfold is not None
+    e.finalize()
+    e.set_param("w/kernel", wt.numpy())
+    if has_bias:
+        e.set_param("w/bias", bias.numpy())
+    xb.data[..., :cin] = x.cuda().to(torch.bfloat16)
+    e.zero_step(zero_grads=True)
+    e.forward(True)
+    torch.cuda.synchronize()
+    assert U.rel_err(yb.data[..., :cout].float(), y_ref) < 1e-2
+    if cpo > cout:
+        assert float(yb.data[..., cout:].abs().max()) == 0
+    yb.grad_tensor()[..., :cout] = dy.cuda().to(torch.bfloat16)
+    xb.grad_tensor().fill_(1.0)
+    op.acc_x = 1
+    e.backward()
+    e.fold_virtual_grads()
+    torch.cuda.synchronize()
+    assert U.rel_err(xb.grad_tensor()[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
+    assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 1e-3
+    if has_bias:
+        assert U.rel_err(torch.from_numpy(e.get_grad("w/bias")), br.grad) < 1e-3
