@@ -118,6 +118,9 @@ class CycleGanModel:
         _, self.GA_rb = self.gen_a.tower("same_b", n, in_buf=self.real_b)
         _, self.DA_fa = self.disc_a.tower("fake", n, in_buf=self.fake_a)
         _, self.DB_fb = self.disc_b.tower("fake", n, in_buf=self.fake_b)
+        # In the generator phase the discriminators only pass the adversarial gradient back to the fake images: their weight
+        # gradients would be discarded (the reference's autograd computes and drops them; SURVEY 8d counts the minimum).
+        self.DA_fa.e.skip_wgrad = self.DB_fb.e.skip_wgrad = True
         _, self.DA_real = self.disc_a.tower("real", n, in_buf=self.real_a)
         _, self.DB_real = self.disc_b.tower("real", n, in_buf=self.real_b)
         _, self.DA_pool = self.disc_a.tower("pool", npool)

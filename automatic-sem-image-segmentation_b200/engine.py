@@ -206,6 +206,7 @@ class Engine:
         # weight gradients run on a side stream, concurrently with the data-gradient / normalisation chain (they only
         # meet again at the optimizer); set by the model front end, off for weight-sharing towers
         self.wgrad_stream: Optional[torch.cuda.Stream] = None
+        self.skip_wgrad = False
         # weight sharing between towers of the same network (CycleGAN applies each generator three times per step):
         # a sharing engine has its own buffers / ops / scratch but uses the root's parameters, gradients and packs
         self.share = share
@@ -421,6 +422,8 @@ class Engine:
     def on_wgrad_stream(self, fn):
         """Runs `fn` (kernel launches that only produce weight gradients) on the side stream, after everything queued
         so far on the current stream; the caller's stream does not wait for it (see backward())."""
+        if self.skip_wgrad:
+            return None         # this tower only back-propagates data gradients (discriminator inside the generator phase)
         side = self.wgrad_stream
         if side is None:
             return fn()
