@@ -2,6 +2,7 @@
 // descriptors, tile iterator.
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace semb {
 
@@ -14,7 +15,8 @@ struct TcPlan { int KC, NC, nchunks, kchunks, tmem_cols; };
 static inline TcPlan tc_plan(int Cin, int Cout, int taps) {
     TcPlan p;
     const int c16 = (Cout + 15) / 16 * 16;
-    p.nchunks = (c16 + 255) / 256;
+    static const int nc_max = [] { const char* e = getenv("SEMB_TC_NC_MAX"); const int v = e ? atoi(e) : 256; return v >= 16 && v <= 256 ? v / 16 * 16 : 256; }();
+    p.nchunks = (c16 + nc_max - 1) / nc_max;
     p.NC = ((c16 + p.nchunks - 1) / p.nchunks + 15) / 16 * 16;
     const int cin16 = (Cin + 15) / 16 * 16;
     int kc = 64;
