@@ -559,6 +559,33 @@ def test_conv_tc_fwd_and_dgrad(case):
     assert U.rel_err(dxd[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("case", [(3, 32, 24, 8, 16, 3), (2, 16, 16, 64, 24, 3), (2, 16, 16, 144, 216, 3), (3, 16, 8, 56, 32, 1)])
+def test_conv_tc_per_sample_moments(case):
+    """InstanceNorm statistics (one moment pair per sample) from the conv epilogue: register-moment and generic paths,
+    sample boundaries inside a CTA's tile sequence."""
+    n, h, w_, cin, cout, k = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(29)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g) + 0.3)
+    wt = U.bf16_round(torch.randn(k, k, cin, cout, generator=g) * 0.1)
+    y_ref = OL.conv2d(x, wt, None, 1, "same")
+    cpi, cpo = U.pad8(cin), U.pad8(cout)
+    p = (k - 1) // 2
+    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, L.PAD_ZERO, L.BF16)
+    xd = U.to_dev(x, "bf16")
+    yd = torch.zeros((n, h, w_, cpo), dtype=torch.bfloat16, device="cuda")
+    wd = U.pad_w(wt)
+    wp = torch.zeros(lib.semb_pack_weights_tc(None, k, k, cpi, cpo, 0, None, None) // 2, dtype=torch.bfloat16, device="cuda")
+    assert lib.semb_pack_weights_tc(wd.data_ptr(), k, k, cpi, cpo, 0, wp.data_ptr(), U.stream()) > 0
+    stats = torch.zeros(n, 2, cpo, device="cuda", dtype=torch.float64)
+    xv, yv = U.view(xd), U.view(yd)
+    L.check(lib.semb_conv2d_fwd_tc(C.byref(geom), C.byref(xv), wp.data_ptr(), None, C.byref(yv), stats.data_ptr(), 2 * cpo, cpo, 0, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(yd[..., :cout], y_ref) < 1e-2
+    assert U.rel_err(stats[:, 0, :cout], y_ref.double().sum(dim=(1, 2))) < 1e-4
+    assert U.rel_err(stats[:, 1, :cout], (y_ref.double() ** 2).sum(dim=(1, 2))) < 1e-4
+
+
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_wgrad(case):
     """tcgen05 weight gradient (MN-major operands, split-K over pixel tiles) vs autograd on bf16-rounded x, dy."""
