@@ -157,7 +157,7 @@ def run_reference(args):
         "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -272,8 +272,6 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version / INFO lines to stdout: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = load_peaks()
     size, batch = args.size, args.batch
@@ -407,7 +405,7 @@ def run_ours(args):
         "clocks": clocks,
         "last_step_metrics": last,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump({"total_ms_eager": total_ms, "rows": rows}, fh, indent=1)
@@ -416,7 +414,26 @@ def run_ours(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to stdout (NCCL writes "NCCL version ..." there): point fd 1 at stderr for the whole run and keep the
+    # original stdout for the JSON line only.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
