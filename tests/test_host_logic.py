@@ -108,3 +108,37 @@ def test_otsu_threshold_separates_bimodal():
     t = HF.threshold_otsu(img)
     assert 80 < t < 170
     assert HF.segment(img.reshape(100, 80), threshold=-1).dtype == np.uint8
+
+
+def test_gan_builders_route_strided_and_7x7_convs_to_the_tensor_core_paths():
+    """Host logic only (dry engines): in bf16 mode every stride-2 conv of the CycleGAN nets is a space-to-depth op with a
+    virtual (3,3,4*Cin,Cout) kernel and the 7x7 stem / head are tap-folded; in fp32 parity mode none of them is."""
+    from sem_b200.engine import ConvOp
+    from sem_b200.gan_nets import DiscriminatorBuilder, GeneratorBuilder
+    for dtype, expect in (("bf16", True), ("f32", False)):
+        e = Engine(1, dtype, dry=True)
+        GeneratorBuilder(e, 32, 32, filters=8, n_res=1)
+        e.finalize()
+        convs = [op for op in e.ops if isinstance(op, ConvOp)]
+        strided = [op for op in convs if op.geom.stride == 2]
+        seven = [op for op in convs if op.geom.R == 7]
+        assert len(strided) == 6 and len(seven) == 2
+        assert all((op.s2d is not None) == expect for op in strided)
+        assert all((op.tapfold is not None) == expect for op in seven)
+        if expect:
+            assert [op.tapfold["kind"] for op in seven] == ["stem", "head"]      # decided by LOGICAL channel counts (filters = 8 here)
+            down = strided[0]
+            assert down.s2d["k"] == 3 and (down.s2d["pt"], down.s2d["pl"]) == (0, 0) and down.geom_s.Cin == 4 * down.geom.Cin
+            up = strided[-1]
+            assert up.transposed and (up.s2d["pt"], up.s2d["pl"]) == (1, 1) and up.geom_t.pad_t == 1
+            keys = [pk["w"] for pk in e.tc_packs if pk.get("vw")]
+            # forward + flipped image per virtual kernel; the stem reads the (gradient-free) input image: no flipped image
+            assert len(keys) == 2 * (len(strided) + len(seven)) - 1
+        d = Engine(1, dtype, dry=True)
+        DiscriminatorBuilder(d, 64, 64, filters=16)
+        d.finalize()
+        dconvs = [op for op in d.ops if isinstance(op, ConvOp)]
+        assert [op.geom.stride for op in dconvs] == [2, 2, 2, 1]
+        assert all((op.s2d is not None) == expect for op in dconvs[:3]) and dconvs[3].s2d is None
+        if expect:
+            assert dconvs[1].geom.H == 31 and dconvs[1].s2d_hw == (16, 16)        # odd size: zero-extended space-to-depth image
