@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH, *objs, "-lcudart", "-lcuda"]
     subprocess.run(cmd, check=True)
     with open(STAMP, "w") as fh:
         fh.write(digest)
