@@ -7,6 +7,7 @@ Models are saved as `model.npz`; the per-epoch image mosaics of GANMonitor are n
 """
 from __future__ import annotations
 
+import collections
 import os
 import time
 
@@ -14,7 +15,7 @@ import numpy as np
 from PIL import Image
 
 from . import HelperFunctions
-from .cyclegan_model import CycleGanModel, ImagePool
+from .cyclegan_model import CycleGanModel, GeneratorModel, ImagePool
 
 
 class DataLoader:
@@ -61,6 +62,7 @@ class CycleGAN:
         self.gaussian_noise_value = 0.15
         self.invert_images = False
         self.image_pool_size = 50
+        self.inference_batch_size = 8       # tiles per engine call in run_inference(tile_images=True)
         self.model = self.data = None
         self.root_dir = root_dir
         self.model_dir = os.path.join(root_dir, "2_CycleGAN", "Models")
@@ -76,18 +78,20 @@ class CycleGAN:
         self.train_a, self.test_a, self.train_b, self.test_b = ls("trainA"), ls("testA"), ls("trainB"), ls("testB")
 
     def create_model(self) -> CycleGanModel:
-        unsupported = {"use_skip_connection": self.use_skip_connection, "use_resize_convolution": self.use_resize_convolution,
-                       "use_binary_crossentropy": self.use_binary_crossentropy, "gaussian_noise_value": self.gaussian_noise_value > 0}
-        bad = [k for k, v in unsupported.items() if v]
-        if bad:
-            raise NotImplementedError(f"CycleGAN options {bad} are outside the accelerated path; StartProcess.py sets them off")
-        if (self.num_downsampling_blocks_gen, self.num_upsampling_blocks_gen, self.num_downsampling_blocks_disc) != (3, 3, 2):
-            raise NotImplementedError("only the 3-down / 3-up generator and the 2-block PatchGAN are built")
+        if self.use_binary_crossentropy:
+            # CycleGAN.py:117-121: BinaryCrossentropy cycle / identity losses and a sigmoid head on gen_a
+            raise NotImplementedError("use_binary_crossentropy=True is outside the accelerated path (MAE cycle / identity losses, "
+                                      "tanh heads only); StartProcess.py leaves it off")
+        if self.num_upsampling_blocks_gen != self.num_downsampling_blocks_gen:
+            raise ValueError("num_upsampling_blocks_gen must equal num_downsampling_blocks_gen (the output would change size)")
         model = CycleGanModel(image_shape=self.image_shape, batch_size=self.batch_size, filters=self.filters, dtype=self.dtype,
                               n_res=self.num_residual_blocks_gen, lambda_cycle_a=self.lambda_cycle_a, lambda_cycle_b=self.lambda_cycle_b,
                               lambda_identity_a=self.lambda_identity_a, lambda_identity_b=self.lambda_identity_b,
                               image_pool_a=self.image_pool_a, image_pool_b=self.image_pool_b,
-                              label_smoothing_factor=self.label_smoothing_factor)
+                              label_smoothing_factor=self.label_smoothing_factor, use_skip_connection=self.use_skip_connection,
+                              use_resize_convolution=self.use_resize_convolution, gaussian_noise_value=self.gaussian_noise_value,
+                              n_down=self.num_downsampling_blocks_gen, n_up=self.num_upsampling_blocks_gen,
+                              n_down_disc=self.num_downsampling_blocks_disc)
         model.compile(learning_rate=self.learning_rate, beta_1=0.5)
         return model
 
@@ -165,27 +169,33 @@ class CycleGAN:
         if self.model is None and weights_from is None:
             newest = sorted(os.listdir(self.model_dir))[-1]
             weights_from = os.path.join(self.model_dir, newest, "model.npz")
-        cache = {}
+        cache = collections.OrderedDict()          # at most two generator instances alive (LRU): sizes vary per image
+        named = None
+        if weights_from is not None:
+            with np.load(weights_from) as z:
+                named = {k[len(which) + 1:]: z[k] for k in z.files if k.startswith(which + "/")}
         for i in range(images.shape[0]):
             img = images[i]
             if which == "gen_a" and self.invert_images:
                 img = img * -1
             th, tw = (self.image_shape[0], self.image_shape[1]) if tile_images else (img.shape[0], img.shape[1])
             tiles = HelperFunctions.tile_image(img, tw, th, min_overlap=min_overlap) if tile_images else img[None]
-            key = (len(tiles), th, tw)
-            if key not in cache:          # generators are fully convolutional: re-instantiate at this size, same weights
-                saved_shape, saved_bs, saved_model = self.image_shape, self.batch_size, self.model
-                self.image_shape, self.batch_size, self.model = (th, tw, 1), len(tiles), None
-                m = self.create_model()
-                if weights_from is not None:
-                    self.model = m
-                    self.load(weights_from)
-                elif saved_model is not None:
-                    for name, net in m.nets.items():
-                        net.set_weights(saved_model.nets[name].get_weights())
-                cache[key] = m
-                self.image_shape, self.batch_size, self.model = saved_shape, saved_bs, saved_model
-            pred = cache[key].generate(which, tiles)
+            nb = min(len(tiles), self.inference_batch_size)
+            key = (nb, th, tw)
+            if key in cache:
+                cache.move_to_end(key)
+            else:          # generators are fully convolutional: ONE generator tower at this size, same weights
+                while len(cache) >= 2:
+                    cache.popitem(last=False)
+                g = GeneratorModel((th, tw, 1), nb, filters=self.filters, dtype=self.dtype, n_res=self.num_residual_blocks_gen,
+                                   use_skip_connection=self.use_skip_connection, use_resize_convolution=self.use_resize_convolution,
+                                   n_down=self.num_downsampling_blocks_gen, n_up=self.num_upsampling_blocks_gen)
+                if named is not None:
+                    g.set_named(named)
+                elif self.model is not None:
+                    g.set_weights(self.model.nets[which].get_weights())
+                cache[key] = g
+            pred = cache[key].predict(tiles)
             out = (HelperFunctions.stitch_image(pred, img.shape[1], img.shape[0], min_overlap=min_overlap,
                                                 manage_overlap_mode=manage_overlap_mode) if tile_images else pred[0])[:, :, 0].copy()
             if which == "gen_b" and self.invert_images:

@@ -131,6 +131,7 @@ class UNet:
         self.allow_memory_growth = allow_memory_growth
         self.use_gpus_no = use_gpus_no
         self.dtype = os.environ.get("SEMB_DTYPE", "bf16")       # storage mode of the engine: bf16 (throughput) | f32 (parity)
+        self.inference_batch_size = 16      # tiles per engine call in run_inference(tile_images=True)
         self.dataset_train = self.dataset_val = self.training_data = self.validation_data = self.model = None
 
     # ---- data ------------------------------------------------------------------------------------------
@@ -222,7 +223,7 @@ class UNet:
                 th, tw = self.image_shape[0], self.image_shape[1]
                 tiles = HelperFunctions.tile_image(img, tw, th, min_overlap=min_overlap)
                 # all tiles of an image go through the engine as ONE batch (the reference calls the model tile by tile)
-                pred = self.model.predict(tiles, batch_size=len(tiles))
+                pred = self.model.predict(tiles, batch_size=min(len(tiles), self.inference_batch_size))
                 out = HelperFunctions.stitch_image(pred, img.shape[1], img.shape[0], min_overlap=min_overlap,
                                                    manage_overlap_mode=manage_overlap_mode)
             else:

@@ -84,11 +84,13 @@ SIGNATURES = {
     "semb_pad_crop": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semb_pixel_shuffle2": (C.c_int, [_TP, _TP, _I, _I, _I, _P, _I, _I, _P]),
     "semb_pixel_shuffle2x": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "semb_upsample2x": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _P]),
     "semb_s2d_weights": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "semb_fold_stats4": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "semb_tap_patch": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _P, _I, _I, _P]),
     "semb_tapfold_weights": (C.c_int, [_P, _I, _I, _I, _P, _I, _I, _P]),
     "semb_loss_wbce": (C.c_int, [_TP, _P, _TP, _L, _F, _P, _I, _P]),
+    "semb_loss_wbce_logits": (C.c_int, [_TP, _P, _P, _P, _TP, _L, _F, _P, _I, _P]),
     "semb_loss_l1_l2": (C.c_int, [_TP, _TP, _F, _I, _L, _I, _F, _TP, _I, _P, _I, _P]),
     "semb_adam_step": (C.c_int, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P]),
     "semb_fill_f32": (C.c_int, [_P, _L, _F, _P]),

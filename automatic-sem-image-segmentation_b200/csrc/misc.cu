@@ -159,6 +159,37 @@ __global__ void __launch_bounds__(256) loss_wbce_kernel(PView p, const float* __
     block_flush<3>(acc, out);
 }
 
+// Same loss, but the probability is recomputed in fp32 from the head's PRE-activation u = z*scale + shift (z = the stored
+// conv output, scale/shift = the head BatchNorm's affine).  In bf16 storage the stored sigmoid output has a spacing of 2^-8
+// just below 1, so p > 0.998 would round to exactly 1: the Keras clip would then zero the gradient of a confidently wrong
+// pixel and dL/dp = 1/(1-p) would be off by tens of percent near saturation.  Keras (fp32) only saturates past |u| ~ 16.
+template <typename T>
+__global__ void __launch_bounds__(256) loss_wbce_logits_kernel(PView z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                               const float* __restrict__ yt, PView dp, long long count, float weighting,
+                                                               float* out) {
+    float acc[3] = {0.f, 0.f, 0.f};
+    const float eps = 1e-7f, inv_count = 1.f / (float)count;
+    const float sc = scale[0], sh = shift[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        Vec8<T>::load(at<T>(z, (size_t)i, 0), v);
+        const float u = fmaf(v[0], sc, sh);
+        const float pr = 1.f / (1.f + expf(-u));
+        const float y = yt[i];
+        const float pc = fminf(fmaxf(pr, eps), 1.f - eps);
+        const float w = y * (weighting - 1.f) + 1.f;
+        acc[0] += -w * (y * logf(pc) + (1.f - y) * logf(1.f - pc));
+        acc[1] += fabsf(y - pr);
+        acc[2] += ((pr > 0.5f ? 1.f : 0.f) == y) ? 1.f : 0.f;
+        if (dp.ptr) {
+            float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (pr >= eps && pr <= 1.f - eps) g[0] = w * (-(y / pc) + (1.f - y) / (1.f - pc)) * inv_count;
+            Vec8<T>::store(at<T>(dp, (size_t)i, 0), g);
+        }
+    }
+    block_flush<3>(acc, out);
+}
+
 // L1 / L2 between a and b (or a constant target) over all 8-padded channels (pads are zero in both)
 template <typename T>
 __global__ void __launch_bounds__(256) loss_l1_l2_kernel(PView a, PView b, float target, int kind, long long n_pixels, int C8,
@@ -301,6 +332,43 @@ __global__ void pixel_shuffle2_kernel(PView src, PView dst, int N, int H, int W,
                 for (int k = 0; k < 8; ++k) v[k] = 0.f;
             }
             Vec8<T>::store(at<T>(src, sp, q * C8 * 8 + c), v);
+        }
+    }
+}
+
+// ---- UpSampling2D(size=(2,2)), nearest neighbour (CycleGAN.py:349, use_resize_convolution) --------------------------------
+// dir 0: big[n,2y+r,2x+s,c] = small[n,y,x,c];   dir 1 (its gradient): small[n,y,x,c] (+)= sum_{r,s} big[n,2y+r,2x+s,c]
+template <typename T>
+__global__ void upsample2x_kernel(PView small, PView big, int N, int H, int W, int C8, int dir, int acc) {
+    const long long total = (long long)N * H * W * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const long long t = i / C8;
+        const int x = (int)(t % W), y = (int)((t / W) % H), n = (int)(t / ((long long)W * H));
+        const size_t sp = ((size_t)n * H + y) * W + x;
+        const size_t bp = ((size_t)n * 2 * H + 2 * y) * (2 * W) + 2 * x;
+        float v[8];
+        if (dir == 0) {
+            Vec8<T>::load(at<T>(small, sp, c), v);
+            Vec8<T>::store(at<T>(big, bp, c), v);
+            Vec8<T>::store(at<T>(big, bp + 1, c), v);
+            Vec8<T>::store(at<T>(big, bp + 2 * W, c), v);
+            Vec8<T>::store(at<T>(big, bp + 2 * W + 1, c), v);
+        } else {
+            float a[8], b[8], d[8], e[8];
+            Vec8<T>::load(at<T>(big, bp, c), a);
+            Vec8<T>::load(at<T>(big, bp + 1, c), b);
+            Vec8<T>::load(at<T>(big, bp + 2 * W, c), d);
+            Vec8<T>::load(at<T>(big, bp + 2 * W + 1, c), e);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (a[k] + b[k]) + (d[k] + e[k]);
+            if (acc) {
+                float o[8];
+                Vec8<T>::load(at<T>(small, sp, c), o);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += o[k];
+            }
+            Vec8<T>::store(at<T>(small, sp, c), v);
         }
     }
 }
@@ -470,6 +538,15 @@ extern "C" int semb_loss_wbce(const semb_tensor* p, const float* y_true, const s
     return check_launch("loss_wbce");
 }
 
+extern "C" int semb_loss_wbce_logits(const semb_tensor* z, const float* scale, const float* shift, const float* y_true,
+                                     const semb_tensor* dp, int64_t count, float weighting, float* out, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(z) && scale && shift && y_true && out && count > 0 && (!dp || view_ok(dp)), SEMB_ESHAPE,
+                 "loss_wbce_logits: bad arguments");
+    if (dtype == SEMB_BF16) loss_wbce_logits_kernel<bf16><<<grid_for(count), 256, 0, as_stream(stream)>>>(pv(z), scale, shift, y_true, pv(dp), count, weighting, out);
+    else loss_wbce_logits_kernel<float><<<grid_for(count), 256, 0, as_stream(stream)>>>(pv(z), scale, shift, y_true, pv(dp), count, weighting, out);
+    return check_launch("loss_wbce_logits");
+}
+
 extern "C" int semb_loss_l1_l2(const semb_tensor* a, const semb_tensor* b, float target, int32_t kind, int64_t n_pixels,
                                int32_t c_logical, float gscale, const semb_tensor* da, int32_t accumulate, float* out,
                                int32_t dtype, void* stream) {
@@ -533,6 +610,17 @@ extern "C" int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* d
 extern "C" int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
                                    const float* bias, int32_t dir, int32_t dtype, void* stream) {
     return semb_pixel_shuffle2x(src, dst, N, H, W, 2 * H, 2 * W, bias, dir, 0, dtype, stream);
+}
+
+extern "C" int semb_upsample2x(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t dir,
+                               int32_t acc, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(small) && view_ok(big) && small->C == big->C && N > 0 && H > 0 && W > 0 && (dir == 0 || dir == 1), SEMB_ESHAPE,
+                 "upsample2x: bad arguments");
+    const int C8 = small->C / 8;
+    const long long total = (long long)N * H * W * C8;
+    if (dtype == SEMB_BF16) upsample2x_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, C8, dir, acc);
+    else upsample2x_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, C8, dir, acc);
+    return check_launch("upsample2x");
 }
 
 extern "C" int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t Cin, int32_t Cout, float* w3, int32_t dir,

@@ -28,21 +28,27 @@ METRICS = ["d_a", "d_b", "d_fake_a", "d_fake_b", "d_real_a", "d_real_b", "g_a", 
 class _Net:
     """One network (flat parameters, Adam state) plus its towers (engines that share those parameters)."""
 
-    def __init__(self, kind: str, h: int, w: int, filters: int, dtype: str, n_res: int, use_tc: bool):
+    def __init__(self, kind: str, h: int, w: int, filters: int, dtype: str, n_res: int, use_tc: bool, seed: int = 0,
+                 options: Optional[dict] = None):
         self.kind, self.h, self.w, self.filters, self.dtype, self.n_res, self.use_tc = kind, h, w, filters, dtype, n_res, use_tc
+        self.seed = seed
+        self.options = dict(options or {})
         self.root: Optional[Engine] = None
         self.towers: Dict[str, tuple] = {}
 
     def tower(self, name: str, n: int, in_buf=None):
         eng = Engine(n, self.dtype, use_tc=self.use_tc, share=self.root)
         if self.kind == "gen":
-            b = GeneratorBuilder(eng, self.h, self.w, self.filters, n_res=self.n_res, in_buf=in_buf)
+            b = GeneratorBuilder(eng, self.h, self.w, self.filters, n_res=self.n_res, in_buf=in_buf, **self.options)
         else:
-            b = DiscriminatorBuilder(eng, self.h, self.w, self.filters, in_buf=in_buf)
+            b = DiscriminatorBuilder(eng, self.h, self.w, self.filters, in_buf=in_buf, **self.options)
         eng.finalize()
         if self.root is None:
             self.root = eng
             self.names = list(b.creation_names)
+            # GlorotUniform kernels, gamma = ones, beta / bias = zeros (CycleGAN.py:125-128).  The reference draws all four
+            # networks from ONE stateful SeedGenerator(0) in construction order; here every network has its own seed.
+            eng.init_params(self.seed)
         self.towers[name] = (eng, b)
         return eng, b
 
@@ -89,11 +95,51 @@ class ImagePool:
         return torch.cat(out, 0)
 
 
+class GeneratorModel:
+    """ONE generator tower for inference (`generator(x, training=False)`, CycleGAN.py:266-277): no discriminators, no
+    sharing towers, no gradient or optimizer traffic.  InstanceNorm has no inference mode, every sample is independent."""
+
+    def __init__(self, image_shape, batch_size: int, filters: int = 64, dtype: str = "bf16", n_res: int = 9, use_tc: bool = True,
+                 **options):
+        h, w = image_shape[0], image_shape[1]
+        self.n, self.h, self.w = batch_size, h, w
+        self.net = _Net("gen", h, w, filters, dtype, n_res, use_tc, options=options)
+        self.eng, self.b = self.net.tower("x", batch_size)
+        self.x_dev = torch.zeros((batch_size, h, w, 1), dtype=torch.float32, device=self.eng.device)
+        self.out_dev = torch.zeros((batch_size,) + tuple(self.b.out_hw) + (1,), dtype=torch.float32, device=self.eng.device)
+
+    def set_weights(self, ws):
+        self.net.set_weights(ws)
+
+    def set_named(self, d):
+        self.net.set_named(d)
+
+    def __call__(self, x, training: bool = False) -> np.ndarray:
+        """x: (m <= batch, H, W, 1) float32 in [-1, 1]; returns (m, H', W', 1)."""
+        x = np.asarray(x, dtype=np.float32)
+        m = x.shape[0]
+        e, b = self.eng, self.b
+        self.x_dev.zero_()
+        self.x_dev[:m].copy_(torch.from_numpy(np.ascontiguousarray(x)))
+        L.check(e.lib.semb_cast_in(self.x_dev.data_ptr(), 1, C.byref(b.in_buf.view().t), self.n * self.h * self.w, e.dtype, e.stream))
+        e.zero_step(False)
+        e.forward(True)
+        oh, ow = b.out_hw
+        L.check(e.lib.semb_cast_out(C.byref(b.out_buf.view().t), self.out_dev.data_ptr(), 1, self.n * oh * ow, e.dtype, e.stream))
+        return self.out_dev[:m].cpu().numpy()
+
+    def predict(self, x, batch_size: Optional[int] = None) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float32)
+        return np.concatenate([self(x[i:i + self.n]) for i in range(0, x.shape[0], self.n)], 0)
+
+
 class CycleGanModel:
     def __init__(self, image_shape=(256, 256, 1), batch_size: int = 8, filters: int = 64, dtype: str = "bf16", n_res: int = 9,
                  lambda_cycle_a: float = 10.0, lambda_cycle_b: float = 10.0, lambda_identity_a: float = 0.5,
                  lambda_identity_b: float = 0.5, image_pool_a: Optional[ImagePool] = None, image_pool_b: Optional[ImagePool] = None,
-                 label_smoothing_factor: float = 0.0, use_tc: bool = True):
+                 label_smoothing_factor: float = 0.0, use_tc: bool = True, use_skip_connection: bool = False,
+                 use_resize_convolution: bool = False, gaussian_noise_value: float = 0.0, n_down: int = 3, n_up: int = 3,
+                 n_down_disc: int = 2, seed: int = 0, use_cuda_graph: bool = True):
         h, w = image_shape[0], image_shape[1]
         self.h, self.w, self.n, self.dtype = h, w, batch_size, dtype
         self.lc_a, self.lc_b, self.li_a, self.li_b = lambda_cycle_a, lambda_cycle_b, lambda_identity_a, lambda_identity_b
@@ -103,9 +149,11 @@ class CycleGanModel:
         npool = min(self.pool_a.batch_size, batch_size) if self.pool_a.pool_size > 0 else batch_size
         self.npool = npool
         n = batch_size
-        mk = lambda kind, f: _Net(kind, h, w, f, dtype, n_res, use_tc)
-        self.gen_a, self.gen_b = mk("gen", filters), mk("gen", filters)
-        self.disc_a, self.disc_b = mk("disc", 2 * filters), mk("disc", 2 * filters)
+        gopt = {"use_skip_connection": use_skip_connection, "use_resize_convolution": use_resize_convolution, "n_down": n_down, "n_up": n_up}
+        dopt = {"gaussian_noise": gaussian_noise_value, "n_down": n_down_disc}
+        mk = lambda kind, f, sd: _Net(kind, h, w, f, dtype, n_res, use_tc, seed=sd, options=gopt if kind == "gen" else dopt)
+        self.gen_a, self.gen_b = mk("gen", filters, seed), mk("gen", filters, seed + 1)
+        self.disc_a, self.disc_b = mk("disc", 2 * filters, seed + 2), mk("disc", 2 * filters, seed + 3)
         # generator towers; fake_b = gen_a(real_a) feeds gen_b and disc_b, so their inputs ALIAS the producer's output
         _, self.GA_ra = self.gen_a.tower("real_a", n)
         _, self.GB_rb = self.gen_b.tower("real_b", n)
@@ -137,6 +185,11 @@ class CycleGanModel:
         self.learning_rate = 2e-4
         self.beta_1, self.beta_2, self.epsilon = 0.5, 0.999, 1e-7
         self.world_size, self.process_group = 1, None
+        self.use_cuda_graph = use_cuda_graph
+        self._warm, self._graphs, self._graph_key = False, None, None
+        npix = n * h * w
+        dpix = n * self.DA_fa.out_hw[0] * self.DA_fa.out_hw[1]
+        self._counts = (npix, dpix, self.npool * self.DA_pool.out_hw[0] * self.DA_pool.out_hw[1])
 
     # ---- helpers -------------------------------------------------------------------------------------
     @property
@@ -149,8 +202,12 @@ class CycleGanModel:
     def set_distributed(self, process_group=None):
         import torch.distributed as dist
         self.process_group, self.world_size = process_group, dist.get_world_size(process_group)
+        from . import dp
         for net in self.nets.values():
-            dist.broadcast(net.root.params.t, src=0, group=process_group)
+            r = net.root
+            for t in (r.params.t, r.state.t, r.adam_m, r.adam_v, r.adam_state):
+                dp.broadcast_(t, 0, process_group)
+            r._pack_dirty = True        # packed tensor-core weight images / virtual stride-2 kernels follow the new master weights
 
     def _loss(self, eng: Engine, view_a, view_b, target, kind, npix, gscale, slot, acc=0, with_grad=True):
         L.check(self.lib.semb_loss_l1_l2(C.byref(view_a.t), C.byref(view_b.t) if view_b is not None else None, float(target), kind,
@@ -163,7 +220,6 @@ class CycleGanModel:
 
     def _adam(self, net: _Net):
         e = net.root
-        e.lr.fill_(self.learning_rate)
         e.fold_virtual_grads()          # gradients of the space-to-depth kernels -> Keras-layout gradients (before the all-reduce)
         if self.world_size > 1:
             import torch.distributed as dist
@@ -195,6 +251,32 @@ class CycleGanModel:
         return self._metrics()
 
     def step_device(self):
+        """One train_step_torch (CycleGAN.py:615-710) with the inputs already in a_dev / b_dev.  The first call runs
+        eagerly (it also allocates the lazy gradient buffers); from the second call on each phase is ONE CUDA-graph
+        replay -- the step has ~1600 launches and is otherwise bound by the host's launch rate.  The image pools sit
+        between the two graphs: their swaps are decided by the host RNG, exactly like the reference's Python pool."""
+        for net in self.nets.values():
+            net.root.lr.fill_(self.learning_rate)         # outside the graphs: the schedule may change it
+        use_graph = self.use_cuda_graph and self.world_size == 1
+        key = (self.beta_1, self.beta_2, self.epsilon, self.lc_a, self.lc_b, self.li_a, self.li_b, self.ls)
+        if use_graph and self._warm and (self._graphs is None or self._graph_key != key):
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._gen_phase()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                self._disc_phase()
+            self._graphs, self._graph_key = (g1, g2), key
+        if use_graph and self._graphs is not None:
+            self._graphs[0].replay()
+            self._query_pools()
+            self._graphs[1].replay()
+        else:
+            self._gen_phase()
+            self._query_pools()
+            self._disc_phase()
+            self._warm = True
+
+    def _gen_phase(self):
         n, h, w = self.n, self.h, self.w
         npix = n * h * w
         G = [self.GA_ra, self.GB_rb, self.GB_fb, self.GA_fa, self.GB_ra, self.GA_rb]
@@ -209,7 +291,6 @@ class CycleGanModel:
                 b.e.zero_step(False)
             b.e.forward(True)
         one = (1.0 - self.ls) + self.ls / 2
-        zero = self.ls / 2
         dpix = n * self.DA_fa.out_hw[0] * self.DA_fa.out_hw[1]
         # adversarial (LSGAN): adv_a uses disc_b(fake_b), adv_b uses disc_a(fake_a)
         self._loss(self.DB_fb.e, self.DB_fb.out_buf.view(), None, one, 1, dpix, 1.0 / dpix, 8)
@@ -227,11 +308,21 @@ class CycleGanModel:
             b.e.backward()
         self._adam(self.gen_a)
         self._adam(self.gen_b)
-        # ---------------- discriminator phase (generator outputs are detached; weights of D unchanged so far)
+
+    def _query_pools(self):
+        # ---------------- image pools (generator outputs are detached; the host RNG decides the swaps)
         pa = self.pool_a.query(self.fake_a.data)
         pb = self.pool_b.query(self.fake_b.data)
         self.DA_pool.in_buf.data.copy_(pa)
         self.DB_pool.in_buf.data.copy_(pb)
+
+    def _disc_phase(self):
+        # ---------------- discriminator phase (weights of D unchanged so far)
+        n = self.n
+        one = (1.0 - self.ls) + self.ls / 2
+        zero = self.ls / 2
+        npix = n * self.h * self.w
+        dpix = n * self.DA_fa.out_hw[0] * self.DA_fa.out_hw[1]
         for net in (self.disc_a, self.disc_b):
             net.root.zero_grads()
         D = [self.DA_real, self.DA_pool, self.DB_real, self.DB_pool]

@@ -997,3 +997,56 @@ class ShuffleOp(Op):
         L.check(e.lib.semb_pixel_shuffle2(C.byref(self.y4.g), C.byref(self.out.g), e.N, self.h, self.w, None, 1, e.dtype, e.stream))
         if self.bias:
             L.check(e.lib.semb_channel_sum(C.byref(self.out.g), e.N, 4 * self.h * self.w, e.gptr(self.bias), e.dtype, e.stream))
+
+
+class UpsampleOp(Op):
+    """UpSampling2D(size=(2,2)), nearest neighbour (CycleGAN.py:349)."""
+
+    def __init__(self, eng: Engine, x: View, y: View, h: int, w: int, n: Optional[int] = None):
+        self.eng, self.x, self.y, self.h, self.w = eng, x, y, h, w
+        self.n = eng.N if n is None else n
+        self.acc = 0
+
+    def plan_backward(self):
+        if self.x.requires_grad:
+            self.acc = plan_grad_write(self.x)
+
+    def fwd(self, training: bool):
+        e = self.eng
+        L.check(e.lib.semb_upsample2x(C.byref(self.x.t), C.byref(self.y.t), self.n, self.h, self.w, 0, 0, e.dtype, e.stream))
+
+    def bwd(self):
+        if not self.x.requires_grad:
+            return
+        e = self.eng
+        L.check(e.lib.semb_upsample2x(C.byref(self.x.g), C.byref(self.y.g), self.n, self.h, self.w, 1, self.acc, e.dtype, e.stream))
+
+
+class NoiseOp(Op):
+    """keras.layers.GaussianNoise(stddev) (CycleGAN.py:427-447): y = x + N(0, stddev) while training, identity otherwise.
+
+    The normal deviates are drawn by torch's device generator into `noise` (plumbing: random bits, not arithmetic of the
+    path); the add and its gradient run in the affine kernels.  `frozen=True` keeps the current content of `noise`
+    (parity tests feed the same deviates to the oracle)."""
+
+    def __init__(self, eng: Engine, x: View, y: View, hw: int, stddev: float, n: Optional[int] = None, c_logical: Optional[int] = None):
+        self.eng, self.x, self.y, self.stddev = eng, x, y, float(stddev)
+        self.c_logical = x.C if c_logical is None else c_logical       # padded channel lanes must stay exactly zero
+        self.noise = eng.new_buf(x.buf.H, x.buf.W, x.C, f"noise_{len(eng.ops)}", requires_grad=False, n=n)
+        self.frozen = False
+        self.add = AffineOp(eng, hw, x, None, self.noise.view(), None, y, L.ACT_NONE, n=n)
+
+    def plan_backward(self):
+        self.add.plan_backward()
+
+    def fwd(self, training: bool):
+        if training and not self.frozen:
+            self.noise.data.normal_(0.0, self.stddev)
+            if self.c_logical < self.x.C:
+                self.noise.data[..., self.c_logical:].zero_()
+        elif not training:
+            self.noise.data.zero_()
+        self.add.fwd(training)
+
+    def bwd(self):
+        self.add.bwd()

@@ -15,7 +15,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import _lib as L
-from .engine import AffineOp, Buf, ConvOp, Engine, Layout, NormOp, PadCropOp, ParamSpec, View, pad8
+from .engine import AffineOp, Buf, ConvOp, Engine, Layout, NoiseOp, NormOp, PadCropOp, ParamSpec, UpsampleOp, View, pad8
 from .nets import IN_EPS
 
 
@@ -41,6 +41,11 @@ class _Base:
         return self._p(name + "/kernel", "conv_kernel", (k, k, cin_l, cout_l), (k, k, ci, co),
                        {2: np.arange(cin_l), 3: np.arange(cout_l)}, "glorot", (k * k * cin_l, k * k * cout_l))
 
+    def conv_w_layout(self, name, k, lin: Layout, lout: Layout):
+        """Conv2D kernel whose input / output channels live in segmented (concat) physical layouts."""
+        return self._p(name + "/kernel", "conv_kernel", (k, k, lin.logical, lout.logical), (k, k, lin.phys, lout.phys),
+                       {2: lin.index_map(), 3: lout.index_map()}, "glorot", (k * k * lin.logical, k * k * lout.logical))
+
     def convT_w(self, name, k, cin_l, cout_l):
         # Keras Conv2DTranspose kernel (kh,kw,Cout,Cin) == HWIO kernel of the equivalent strided conv (I=Cout_T, O=Cin_T)
         ci, co = pad8(cin_l), pad8(cout_l)
@@ -58,10 +63,14 @@ class _Base:
 
 class GeneratorBuilder(_Base):
     def __init__(self, eng: Engine, h: int, w: int, filters: int = 64, n_down: int = 3, n_res: int = 9, n_up: int = 3,
-                 prefix: str = "", in_buf: Optional[Buf] = None):
+                 prefix: str = "", in_buf: Optional[Buf] = None, use_skip_connection: bool = False,
+                 use_resize_convolution: bool = False, **_ignored):
         super().__init__(eng, prefix)
         e = eng
         m = 2 ** n_down
+        if use_skip_connection and (h % m or w % m):
+            # the reference adds the (un-cropped, CycleGAN.py:394) padded output to a branch of the un-padded input
+            raise ValueError(f"use_skip_connection needs an input size divisible by {m} (got {h}x{w}); Keras fails likewise")
         ph, pw = (m - h % m) % m, (m - w % m) % m
         self.in_buf = in_buf if in_buf is not None else e.new_buf(h, w, 8, prefix + "input", requires_grad=False)
         x, H, W = self.in_buf.view(), h, w
@@ -93,14 +102,46 @@ class GeneratorBuilder(_Base):
             x = conv_in_act(y, (H, W), (H, W), self.conv_w(f"res{i}_1", 3, f, f), 3, 1, (1, 1), L.PAD_REFLECT, f, f"res{i}_1_in",
                             L.ACT_NONE, residual=x)
         for i in range(n_up):
-            # Conv2DTranspose(3x3, s2, 'same') == torch padding 1, output_padding 1: the equivalent strided conv has pad 1
-            x = conv_in_act(x, (H, W), (2 * H, 2 * W), self.convT_w(f"up{i}", 3, f, f // 2), 3, 2, (1, 1), L.PAD_ZERO, f // 2,
-                            f"up{i}_in", L.ACT_RELU, transposed=True)
+            if use_resize_convolution:
+                # UpSampling2D(nearest) -> ReflectionPadding2D(1) -> Conv2D(3x3, valid, no bias) (CycleGAN.py:348-351)
+                up = e.new_buf(2 * H, 2 * W, pad8(f), f"{prefix}up{i}_nearest")
+                e.add_op(UpsampleOp(e, x, up.view(), H, W))
+                x = conv_in_act(up.view(), (2 * H, 2 * W), (2 * H, 2 * W), self.conv_w(f"up{i}", 3, f, f // 2), 3, 1, (1, 1),
+                                L.PAD_REFLECT, f // 2, f"up{i}_in", L.ACT_RELU)
+            else:
+                # Conv2DTranspose(3x3, s2, 'same') == torch padding 1, output_padding 1: the equivalent strided conv has pad 1
+                x = conv_in_act(x, (H, W), (2 * H, 2 * W), self.convT_w(f"up{i}", 3, f, f // 2), 3, 2, (1, 1), L.PAD_ZERO, f // 2,
+                                f"up{i}_in", L.ACT_RELU, transposed=True)
             f, H, W = f // 2, 2 * H, 2 * W
         wh = self.conv_w("head", 7, f, 1)
         bh = self.vec("head/bias", 1, "zeros")
-        raw = e.new_buf(H, W, 8, prefix + "head_raw")
-        e.add_op(ConvOp(e, x, raw.view(), (H, W), (H, W), wh, bh, 7, 1, (3, 3), L.PAD_REFLECT, False))
+        if use_skip_connection:
+            # CycleGAN.py:396-415: [relu(IN(conv1x1(img))) + relu(IN(conv3x3(reflect_pad(img))))] -> IN -> relu, concatenated
+            # with the head conv's output, then a bias-free 1x1 conv back to one channel.
+            img = self.in_buf.view()
+            fp = pad8(f)
+            cat = e.new_buf(H, W, fp + 8, prefix + "skip_cat")
+            s_act = conv_in_act(img, (H, W), (H, W), self.conv_w("skip_short", 1, 1, f), 1, 1, (0, 0), L.PAD_ZERO, f, "skip_short_in",
+                                L.ACT_RELU)
+            w_o = self.conv_w("skip_conv", 3, 1, f)
+            n_o = self.inorm("skip_conv_in", f, H * W)
+            o_raw = e.new_buf(H, W, fp, prefix + "skip_conv_raw")
+            e.add_op(ConvOp(e, img, o_raw.view(), (H, W), (H, W), w_o, None, 3, 1, (1, 1), L.PAD_REFLECT, False, stats=n_o.stats_ref()))
+            e.add_op(n_o)
+            n_s = self.inorm("skip_sum_in", f, H * W)
+            summed = e.new_buf(H, W, fp, prefix + "skip_sum")
+            e.add_op(AffineOp(e, H * W, s_act, None, o_raw.view(), n_o, summed.view(), L.ACT_NONE, actb=L.ACT_RELU,
+                              stats_out=n_s.stats_ref()))
+            e.add_op(n_s)
+            e.add_op(AffineOp(e, H * W, summed.view(), n_s, None, None, cat.view(0, fp), L.ACT_RELU))
+            e.add_op(ConvOp(e, x, cat.view(fp, 8), (H, W), (H, W), wh, bh, 7, 1, (3, 3), L.PAD_REFLECT, False))
+            lcat = Layout([(f, fp), (1, 8)])
+            wf = self.conv_w_layout("skip_out", 1, lcat, Layout.simple(1))
+            raw = e.new_buf(H, W, 8, prefix + "head_raw")
+            e.add_op(ConvOp(e, cat.view(), raw.view(), (H, W), (H, W), wf, None, 1, 1, (0, 0), L.PAD_ZERO, False))
+        else:
+            raw = e.new_buf(H, W, 8, prefix + "head_raw")
+            e.add_op(ConvOp(e, x, raw.view(), (H, W), (H, W), wh, bh, 7, 1, (3, 3), L.PAD_REFLECT, False))
         self.out_buf = e.new_buf(H, W, 8, prefix + "output")
         e.add_op(AffineOp(e, H * W, raw.view(), None, None, None, self.out_buf.view(), L.ACT_TANH))
         self.out_hw = (H, W)
@@ -108,12 +149,26 @@ class GeneratorBuilder(_Base):
 
 class DiscriminatorBuilder(_Base):
     def __init__(self, eng: Engine, h: int, w: int, filters: int = 128, n_down: int = 2, prefix: str = "",
-                 in_buf: Optional[Buf] = None):
+                 in_buf: Optional[Buf] = None, gaussian_noise: float = 0.0, **_ignored):
         super().__init__(eng, prefix)
         e = eng
+        if n_down > 3:
+            raise NotImplementedError("PatchGAN blocks past the third use stride 1 (CycleGAN.py:441-444): not built")
         self.in_buf = in_buf if in_buf is not None else e.new_buf(h, w, 8, prefix + "input", requires_grad=False)
         x, H, W = self.in_buf.view(), h, w
         f = filters
+        self.noise_ops: List[NoiseOp] = []
+
+        def noisy(x, H, W, tag):
+            """GaussianNoise(gaussian_noise_value) in front of every conv of the discriminator (CycleGAN.py:427-447)."""
+            if gaussian_noise <= 0:
+                return x
+            out = e.new_buf(H, W, x.C, f"{prefix}{tag}_noisy", requires_grad=x.requires_grad)
+            op = NoiseOp(e, x, out.view(), H * W, gaussian_noise, c_logical=(1 if tag == "d0" else x.C))
+            self.noise_ops.append(e.add_op(op))
+            return out.view()
+
+        x = noisy(x, H, W, "d0")
         oh, ow = (H - 4) // 2 + 1, (W - 4) // 2 + 1
         w0, b0 = self.conv_w("d0", 4, 1, f), self.vec("d0/bias", f, "zeros")
         raw = e.new_buf(oh, ow, pad8(f), prefix + "d0_raw")
@@ -123,6 +178,7 @@ class DiscriminatorBuilder(_Base):
         x, H, W = act.view(), oh, ow
         for i in range(n_down):
             oh, ow = (H - 4) // 2 + 1, (W - 4) // 2 + 1
+            x = noisy(x, H, W, f"d{i + 1}")
             wn = self.conv_w(f"d{i + 1}", 4, f, 2 * f)
             norm = self.inorm(f"d{i + 1}_in", 2 * f, oh * ow)
             raw = e.new_buf(oh, ow, pad8(2 * f), f"{prefix}d{i + 1}_raw")
@@ -131,6 +187,7 @@ class DiscriminatorBuilder(_Base):
             act = e.new_buf(oh, ow, pad8(2 * f), f"{prefix}d{i + 1}_out")
             e.add_op(AffineOp(e, oh * ow, raw.view(), norm, None, None, act.view(), L.ACT_LEAKY))
             x, H, W, f = act.view(), oh, ow, 2 * f
+        x = noisy(x, H, W, "out")
         oh, ow = H - 3, W - 3
         wo, bo = self.conv_w("out", 4, f, 1), self.vec("out/bias", 1, "zeros")
         self.out_buf = e.new_buf(oh, ow, 8, prefix + "output")

@@ -7,6 +7,7 @@ sequence (forward(training=True) -> loss -> backward -> Adam -> metrics) [K3.5].
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import json
 import math
@@ -64,9 +65,12 @@ class _Instance:
     def loss(self, weighting: float, with_grad: bool):
         e = self.eng
         ov = self.net.out_buf.view()
-        L.check(e.lib.semb_loss_wbce(C.byref(ov.t), self.y_dev.data_ptr(), C.byref(ov.g) if with_grad else None,
-                                     self.n * self.h * self.w, float(weighting), e.zeroed.ptr(self.loss_sums), e.dtype,
-                                     e.stream))
+        # p = sigmoid(BN(z)) is recomputed in fp32 from the stored pre-activation z: a bf16 probability saturates at
+        # p ~ 0.998, long before Keras' clip at 1 - 1e-7 (UNet_Segmentation.py:379-384)
+        hn = self.net.head_norm
+        L.check(e.lib.semb_loss_wbce_logits(C.byref(self.net.head_raw.view.t), hn.s("scale"), hn.s("shift"), self.y_dev.data_ptr(),
+                                            C.byref(ov.g) if with_grad else None, self.n * self.h * self.w, float(weighting),
+                                            e.zeroed.ptr(self.loss_sums), e.dtype, e.stream))
 
     def fwd_bwd(self, weighting: float):
         e = self.eng
@@ -75,6 +79,8 @@ class _Instance:
         e.forward(training=True)
         self.loss(weighting, with_grad=True)
         e.backward()
+        if e.s2d:
+            e.fold_virtual_grads()      # `grads` must be complete BEFORE the data-parallel all-reduce (Engine.adam folds too late)
 
 
 class UNetModel:
@@ -89,7 +95,12 @@ class UNetModel:
         self.filters, self.dtype, self.seed = filters, dtype, seed
         self.use_cuda_graph = use_cuda_graph
         self.use_tc = use_tc
-        self._instances: Dict[tuple, _Instance] = {}
+        # engines are specialised to (N, H, W); keep the training instance plus a few most-recently-used others (a
+        # directory of differently sized images must not grow device / pinned memory without bound)
+        self._instances: "collections.OrderedDict[tuple, _Instance]" = collections.OrderedDict()
+        self.max_instances = 3
+        self._primary = None
+        self._current = None
         self._primary = self._instance(batch_size, input_shape[0], input_shape[1], init=True)
         self._current = self._primary
         self.weighting = 1.0
@@ -105,10 +116,22 @@ class UNetModel:
         key = (n, h, w)
         inst = self._instances.get(key)
         if inst is None:
+            # evict least-recently-used instances first (never the training instance or the one holding the live weights)
+            for k in list(self._instances):
+                if len(self._instances) < self.max_instances:
+                    break
+                victim = self._instances[k]
+                if victim is self._primary or victim is self._current:
+                    continue
+                del self._instances[k]
+                victim.graph = None
+                del victim
             inst = _Instance(n, h, w, self.filters, self.dtype, self.use_tc)
             if init:
                 inst.eng.init_params(self.seed)
             self._instances[key] = inst
+        else:
+            self._instances.move_to_end(key)
         return inst
 
     def _use(self, inst: _Instance):
@@ -186,8 +209,18 @@ class UNetModel:
         return inst.out_pin.clone()
 
     def predict(self, x, batch_size: int = 8):
-        x = _to_numpy(x)
-        outs = [self(x[i:i + batch_size]).numpy() for i in range(0, x.shape[0], batch_size)]
+        """Inference in chunks of exactly `batch_size` tiles (the last chunk is zero-padded: with moving statistics every
+        sample is independent), so that one engine instance serves any number of tiles."""
+        x = _to_numpy(x).astype(np.float32, copy=False)
+        n = x.shape[0]
+        batch_size = max(1, min(int(batch_size), n))
+        outs = []
+        for i in range(0, n, batch_size):
+            chunk = x[i:i + batch_size]
+            m = chunk.shape[0]
+            if m < batch_size:
+                chunk = np.concatenate([chunk, np.zeros((batch_size - m,) + chunk.shape[1:], dtype=np.float32)], 0)
+            outs.append(self(chunk).numpy()[:m])
         return np.concatenate(outs, 0)
 
     # ---- training ------------------------------------------------------------------------------------

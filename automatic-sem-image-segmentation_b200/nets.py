@@ -316,6 +316,7 @@ class UNetBuilder:
             c = T(m9.view, H, W, m9.layout, kcrop)
         lout = Layout.simple(1)
         head_raw, bnh = self.conv2d_bn_raw(c, lout, 1)
+        self.head_raw, self.head_norm = head_raw, bnh      # the loss recomputes the probability from the pre-activation
         kout = self.kg.layer("output", [head_raw.klayer])
         self.out_buf = e.new_buf(H, W, lout.phys, "output")
         e.add_op(AffineOp(e, H * W, head_raw.view, bnh, None, None, self.out_buf.view(), L.ACT_SIGMOID))

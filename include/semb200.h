@@ -302,6 +302,12 @@ int semb_pad_crop(const semb_tensor* x, const semb_tensor* y, int32_t N, int32_t
 int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
                         const float* bias, int32_t dir, int32_t dtype, void* stream);
 
+/* UpSampling2D(size=(2,2)) nearest neighbour (CycleGAN.py:349, the use_resize_convolution branch of `upsample`).
+ * dir 0: big[n,2y+r,2x+s,c] = small[n,y,x,c];  dir 1: small (+)= sum over the 2x2 block of big (its gradient).
+ * (H,W) is the size of `small`; `big` is (2H,2W). */
+int semb_upsample2x(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t dir,
+                    int32_t accumulate, int32_t dtype, void* stream);
+
 /* ---- losses ------------------------------------------------------------------------------ */
 
 /* weighted_bce (UNet_Segmentation.py:379-384) + the 'mae' and 'acc' metrics (:395) + d(loss)/d(p).
@@ -309,6 +315,13 @@ int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t 
  * dp = w*(-(y/p)+(1-y)/(1-p))/count inside the Keras clip range [1e-7,1-1e-7], else 0 (dp may be NULL). */
 int semb_loss_wbce(const semb_tensor* p, const float* y_true, const semb_tensor* dp, int64_t count,
                    float weighting, float* out, int32_t dtype, void* stream);
+
+/* Same loss / metrics / gradient, with p = sigmoid(z*scale[0] + shift[0]) recomputed in fp32 from the head's stored
+ * pre-activation z (conv2d_bn(..., activation='sigmoid'), UNet_Segmentation.py:556-557; scale/shift = its BatchNorm affine).
+ * The product path uses this one: a probability stored in bf16 rounds to exactly 1 above ~0.998, where Keras' fp32 clip
+ * (1e-7) is still far away.  dp is still d(loss)/d(p), consumed by the sigmoid backward. */
+int semb_loss_wbce_logits(const semb_tensor* z, const float* scale, const float* shift, const float* y_true,
+                          const semb_tensor* dp, int64_t count, float weighting, float* out, int32_t dtype, void* stream);
 
 /* sum |a-b| (kind 0, MeanAbsoluteError) or sum (a-b)^2 (kind 1, MeanSquaredError) into out[0] over the
  * first c_logical channels; b==NULL compares against the constant `target` (LSGAN labels,

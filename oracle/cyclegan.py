@@ -7,8 +7,9 @@ Follows /root/reference/Releases/Version 1.2.0/CycleGAN.py:
   generator_loss_fn / discriminator_loss_fn :301-308,
   CycleGanModel.train_step_torch :615-710, ImagePool.query :927-964.
 
-Configuration restated = the one StartProcess.py drives (StartProcess.py:91-102): use_skip_connection=False,
-gaussian_noise_value=0.0, use_resize_convolution=False, use_binary_crossentropy=False, lambda_identity 0.5.
+Default configuration = the one StartProcess.py drives (StartProcess.py:91-102): use_skip_connection=False,
+gaussian_noise_value=0.0, use_resize_convolution=False, use_binary_crossentropy=False, lambda_identity 0.5; the
+skip-connection (:396-415), resize-convolution (:348-351) and GaussianNoise (:427-447) variants are restated as options.
 Parity status: unpinned by the reference (no tests, Keras not installable); layer semantics per SURVEY.md
 Appendix B; cross-checked against naive loops in tests/test_oracle_layers.py.
 """
@@ -23,7 +24,8 @@ from . import layers as L
 
 
 # ------------------------------------------------------------------------------------------ parameter specs
-def generator_spec(filters: int = 64, n_down: int = 3, n_res: int = 9, n_up: int = 3, channels: int = 1):
+def generator_spec(filters: int = 64, n_down: int = 3, n_res: int = 9, n_up: int = 3, channels: int = 1,
+                   use_skip_connection: bool = False, use_resize_convolution: bool = False):
     """[(name, shape, kind)] in creation order."""
     e = []
     f = filters
@@ -38,11 +40,21 @@ def generator_spec(filters: int = 64, n_down: int = 3, n_res: int = 9, n_up: int
             e.append((f"res{i}_{j}/kernel", (3, 3, f, f), "conv"))
             e += [(f"res{i}_{j}_in/gamma", (f,), "gamma"), (f"res{i}_{j}_in/beta", (f,), "beta")]
     for i in range(n_up):
-        e.append((f"up{i}/kernel", (3, 3, f // 2, f), "convT"))       # Keras Conv2DTranspose kernel (kh,kw,Cout,Cin)
+        if use_resize_convolution:
+            e.append((f"up{i}/kernel", (3, 3, f, f // 2), "conv"))      # UpSampling2D + ReflectionPadding2D + Conv2D (:348-351)
+        else:
+            e.append((f"up{i}/kernel", (3, 3, f // 2, f), "convT"))       # Keras Conv2DTranspose kernel (kh,kw,Cout,Cin)
         f //= 2
         e += [(f"up{i}_in/gamma", (f,), "gamma"), (f"up{i}_in/beta", (f,), "beta")]
     e.append(("head/kernel", (7, 7, f, channels), "conv"))
     e.append(("head/bias", (channels,), "bias"))
+    if use_skip_connection:         # CycleGAN.py:396-415
+        e.append(("skip_short/kernel", (1, 1, channels, f), "conv"))
+        e += [("skip_short_in/gamma", (f,), "gamma"), ("skip_short_in/beta", (f,), "beta")]
+        e.append(("skip_conv/kernel", (3, 3, channels, f), "conv"))
+        e += [("skip_conv_in/gamma", (f,), "gamma"), ("skip_conv_in/beta", (f,), "beta")]
+        e += [("skip_sum_in/gamma", (f,), "gamma"), ("skip_sum_in/beta", (f,), "beta")]
+        e.append(("skip_out/kernel", (1, 1, f + channels, channels), "conv"))
     return e
 
 
@@ -83,7 +95,9 @@ def _in_relu(x, p, name, act=torch.relu):
 
 
 def generator_forward(x, p, n_down: int = 3, n_res: int = 9, n_up: int = 3, taps=None):
-    """get_resnet_generator(...)(x, training=True).  x NHWC in [-1,1]."""
+    """get_resnet_generator(...)(x, training=True).  x NHWC in [-1,1].  The skip-connection / resize-convolution
+    variants are recognised from the parameter set (generator_spec)."""
+    img_input = x
     H, W = x.shape[1], x.shape[2]
     m = 2 ** n_down
     ph, pw = (m - H % m) % m, (m - W % m) % m
@@ -109,20 +123,38 @@ def generator_forward(x, p, n_down: int = 3, n_res: int = 9, n_up: int = 3, taps
     if taps is not None:
         taps["res"] = x
     for i in range(n_up):
-        x = L.conv2d_transpose(x, p[f"up{i}/kernel"], None, 2)
+        k = p[f"up{i}/kernel"]
+        if k.shape[2] > k.shape[3]:        # Conv2D kernel (3,3,f,f/2): the use_resize_convolution branch (:348-351)
+            x = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)       # UpSampling2D nearest
+            x = L.reflection_pad(x, 2, 2)
+            x = L.conv2d(x, k, None, 1, "valid")
+        else:
+            x = L.conv2d_transpose(x, k, None, 2)
         x = _in_relu(x, p, f"up{i}_in")
     x = L.reflection_pad(x, 6, 6)
     x = L.conv2d(x, p["head/kernel"], p["head/bias"], 1, "valid")
+    if "skip_out/kernel" in p:          # use_skip_connection (:396-415)
+        shortcut = L.conv2d(img_input, p["skip_short/kernel"], None, 1, "valid")
+        shortcut = _in_relu(shortcut, p, "skip_short_in")
+        out = L.reflection_pad(img_input, 2, 2)
+        out = L.conv2d(out, p["skip_conv/kernel"], None, 1, "valid")
+        out = _in_relu(out, p, "skip_conv_in")
+        out = _in_relu(shortcut + out, p, "skip_sum_in")
+        x = torch.cat([out, x], dim=3)
+        x = L.conv2d(x, p["skip_out/kernel"], None, 1, "valid")
     return torch.tanh(x)
 
 
-def discriminator_forward(x, p, n_down: int = 2):
-    x = L.conv2d(x, p["d0/kernel"], p["d0/bias"], 2, "valid")
+def discriminator_forward(x, p, n_down: int = 2, noise=None):
+    """get_discriminator(...)(x, training=True).  `noise`: the GaussianNoise deviates added in front of each conv
+    (d0, d1.., out), one tensor per conv, or None (gaussian_noise_value = 0)."""
+    nz = (lambda t, i: t + noise[i]) if noise is not None else (lambda t, i: t)
+    x = L.conv2d(nz(x, 0), p["d0/kernel"], p["d0/bias"], 2, "valid")
     x = L.leaky_relu(x, 0.2)
     for i in range(n_down):
-        x = L.conv2d(x, p[f"d{i + 1}/kernel"], None, 2, "valid")
+        x = L.conv2d(nz(x, i + 1), p[f"d{i + 1}/kernel"], None, 2, "valid")
         x = _in_relu(x, p, f"d{i + 1}_in", act=lambda t: L.leaky_relu(t, 0.2))
-    return L.conv2d(x, p["out/kernel"], p["out/bias"], 1, "valid")
+    return L.conv2d(nz(x, n_down + 1), p["out/kernel"], p["out/bias"], 1, "valid")
 
 
 # ------------------------------------------------------------------------------------------ image pool

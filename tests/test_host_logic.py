@@ -142,3 +142,43 @@ def test_gan_builders_route_strided_and_7x7_convs_to_the_tensor_core_paths():
         assert all((op.s2d is not None) == expect for op in dconvs[:3]) and dconvs[3].s2d is None
         if expect:
             assert dconvs[1].geom.H == 31 and dconvs[1].s2d_hw == (16, 16)        # odd size: zero-extended space-to-depth image
+
+
+def test_image_pool_swap_branch_matches_oracle_pool():
+    """ImagePool.query past pool_size entries (CycleGAN.py:927-964): same random.Random stream -> same swaps, same outputs
+    as the oracle pool, including the batch_size truncation quirk (pool built with batch 2, fed batches of 5)."""
+    import random
+    from oracle import cyclegan as OC
+    from sem_b200.cyclegan_model import ImagePool
+    for pool_batch, feed in ((2, 5), (4, 4)):
+        ours, ref = ImagePool(pool_batch, 6, random.Random(7)), OC.ImagePool(pool_batch, 6, random.Random(7))
+        g = torch.Generator().manual_seed(0)
+        swaps = 0
+        for step in range(40):
+            imgs = torch.rand(feed, 4, 4, 1, generator=g)
+            a, b = ours.query(imgs.clone()), ref.query(imgs.clone())
+            assert a.shape == b.shape == (min(pool_batch, feed), 4, 4, 1)
+            assert torch.equal(a, b), step
+            swaps += int(not torch.equal(a, imgs[:a.shape[0]]))
+        assert ours.num_imgs == ref.num_imgs == 6 and swaps > 5
+        for x, y in zip(ours.images, ref.images):
+            assert torch.equal(x, y)
+    assert torch.equal(ImagePool(2, 0).query(imgs), imgs)
+
+
+def test_cyclegan_builders_options_create_the_reference_variables():
+    from sem_b200.gan_nets import DiscriminatorBuilder, GeneratorBuilder
+    from oracle import cyclegan as OC
+    for opts in ({"use_skip_connection": True}, {"use_resize_convolution": True}, {}):
+        e = Engine(1, "bf16", dry=True)
+        b = GeneratorBuilder(e, 32, 32, 8, n_res=1, **opts)
+        e.finalize()
+        spec = OC.generator_spec(8, n_res=1, **opts)
+        assert b.creation_names == [n for n, _, _ in spec]
+        for n, shape, _ in spec:
+            assert e.specs[n].logical_shape == tuple(shape), n
+    e = Engine(1, "bf16", dry=True)
+    b = DiscriminatorBuilder(e, 64, 64, 16, gaussian_noise=0.15)
+    assert len(b.noise_ops) == 4 and b.creation_names == [n for n, _, _ in OC.discriminator_spec(16)]
+    with pytest.raises(ValueError):
+        GeneratorBuilder(Engine(1, "bf16", dry=True), 36, 36, 8, n_res=1, use_skip_connection=True)

@@ -436,6 +436,44 @@ def test_loss_wbce(dtype):
     assert U.rel_err(dpd[..., :1], pr.grad) < (1e-5 if dtype == "f32" else 1e-2)
 
 
+@pytest.mark.parametrize("dtype", DT)
+def test_loss_wbce_logits_saturated_pixels_keep_their_gradient(dtype):
+    """with the probability recomputed in fp32 from the stored pre-activation, a confidently wrong pixel
+    (logit 8, p = 0.99966 -- exactly 1.0 after bf16 rounding) keeps the Keras gradient; the clip only acts past |u| ~ 16."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(8)
+    n, h, w_ = 2, 16, 16
+    z = torch.randn(n, h, w_, 1, generator=g) * 3.0
+    z[0, 0, 0, 0], z[0, 0, 1, 0], z[0, 0, 2, 0] = 8.0, -8.0, 40.0
+    z = _prep(z, dtype)
+    y = (torch.rand(n, h, w_, 1, generator=g) < 0.3).float()
+    y[0, 0, 0, 0], y[0, 0, 1, 0], y[0, 0, 2, 0] = 0.0, 1.0, 0.0
+    sc, sh = 1.25, -0.1
+    zr = z.clone().requires_grad_(True)
+    pr = torch.sigmoid(zr * sc + sh)
+    pr.retain_grad()
+    loss = OL.weighted_bce(y, pr, 4.5)
+    loss.backward()
+    zd = U.to_dev(z, dtype)
+    dpd = torch.zeros_like(zd)
+    out = torch.zeros(4, device="cuda")
+    scd, shd = torch.full((8,), sc, device="cuda"), torch.full((8,), sh, device="cuda")
+    zv, dpv = U.view(zd), U.view(dpd)
+    yd = y.cuda().contiguous()
+    L.check(lib.semb_loss_wbce_logits(C.byref(zv), scd.data_ptr(), shd.data_ptr(), yd.data_ptr(), C.byref(dpv), n * h * w_, 4.5,
+                                      out.data_ptr(), U.ldtype(dtype), U.stream()))
+    torch.cuda.synchronize()
+    cnt = n * h * w_
+    assert abs(float(out[0]) / cnt - float(loss)) < 1e-4 * max(1.0, abs(float(loss)))
+    assert abs(float(out[2]) / cnt - float(((pr > 0.5).float() == y).float().mean())) < 1e-6
+    got = dpd[..., :1].float().cpu()
+    ref = pr.grad
+    assert float(got[0, 0, 2, 0]) == 0.0 and float(ref[0, 0, 2, 0]) == 0.0            # past the fp32 clip: zero in Keras too
+    for ix in ((0, 0, 0, 0), (0, 0, 1, 0)):                                            # saturated in bf16, alive in fp32
+        assert abs(float(got[ix]) - float(ref[ix])) < (1e-4 if dtype == "f32" else 1e-2) * abs(float(ref[ix])) and float(ref[ix]) != 0.0
+    assert U.rel_err(got, ref) < (1e-4 if dtype == "f32" else 1e-2)
+
+
 @pytest.mark.parametrize("kind", [0, 1])
 def test_loss_l1_l2(kind):
     lib = L.load()
