@@ -122,24 +122,36 @@ def stitch_image(img, image_size_w, image_size_h, min_overlap=2, manage_overlap_
     return out
 
 
+def eight_to_four_connected(img):
+    """HelperFunctions.py:144-152: breaks diagonal-only (8-connected) contacts.  The reference's scan is sequential
+    (every fix is visible to the following 2x2 windows), so it is reproduced pixel by pixel; `count > 2 or count <
+    size - 2` is the reference's own guard."""
+    if np.count_nonzero(img) > 2 or np.count_nonzero(img) < img.size - 2:
+        a = img
+        for x in range(a.shape[0] - 1):
+            r0, r1 = a[x], a[x + 1]
+            # candidate columns only: a diagonal pair of zeros next to a diagonal pair of non-zeros
+            d1 = (r0[:-1] == 0) & (r1[1:] == 0) & (r1[:-1] != 0) & (r0[1:] != 0)
+            d2 = (r1[:-1] == 0) & (r0[1:] == 0) & (r0[:-1] != 0) & (r1[1:] != 0)
+            for y in np.flatnonzero(d1 | d2):
+                if a[x, y] == 0 and a[x + 1, y + 1] == 0 and a[x + 1, y] != 0 and a[x, y + 1] != 0:
+                    a[x + 1, y] = 0
+                elif a[x + 1, y] == 0 and a[x, y + 1] == 0 and a[x, y] != 0 and a[x + 1, y + 1] != 0:
+                    a[x, y] = 0
+    return img
+
+
 def threshold_otsu(image_u8: np.ndarray) -> float:
-    """Otsu's threshold on an 8-bit image (skimage.filters.threshold_otsu semantics: bin centres, maximise between-class variance)."""
-    hist = np.bincount(image_u8.ravel(), minlength=256).astype(np.float64)
-    centers = np.arange(256, dtype=np.float64)
-    w1 = np.cumsum(hist)
-    w2 = np.cumsum(hist[::-1])[::-1]
-    m1 = np.cumsum(hist * centers) / np.maximum(w1, 1e-300)
-    m2 = (np.cumsum((hist * centers)[::-1]) / np.maximum(w2[::-1], 1e-300))[::-1]
-    var = w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2
-    return float(centers[int(np.argmax(var))])
+    """Otsu's threshold (skimage.filters.threshold_otsu semantics); see Measurements.threshold_otsu."""
+    from .Measurements import threshold_otsu as _otsu
+    return _otsu(image_u8)
 
 
 def segment(image, threshold=-1, watershed_lines=True, min_distance=9, use_four_connectivity=True):
-    """Threshold half of HelperFunctions.segment: Otsu when threshold < 0 (reference :144-185).  The watershed split
-    is classical CPU post-processing outside the hot path: masks are returned unsplit."""
-    if image.dtype == bool:
-        mask = image
-    else:
-        t = threshold_otsu(image) if threshold < 0 else threshold * 255.0
-        mask = image > t
-    return np.asarray(mask, dtype="uint8") * 255
+    """HelperFunctions.py:155-160: Measure.segment (threshold, Otsu when < 0; distance-transform watershed with lines) and
+    the 8 -> 4 connectivity fix.  uint8 {0, 255}."""
+    from .Measurements import Measure
+    labels = Measure.segment(image, threshold, watershed_lines, min_distance, darkBackground=True)
+    if use_four_connectivity:
+        labels = eight_to_four_connected(labels)
+    return labels

@@ -66,6 +66,8 @@ SIGNATURES = {
     "semb_pack_weights_tc_batch": (C.c_int, [_P, _I, _I, _P]),
     "semb_conv2d_fwd_tc": (C.c_int, [_GP, _TP, _P, _P, _TP, _P, _I, _I, _I, _P]),
     "semb_conv2d_wgrad_tc": (C.c_int, [_GP, _TP, _TP, _P, _P]),
+    "semb_conv2d_wgrad_tc_workspace": (C.c_int64, [_GP]),
+    "semb_conv2d_wgrad_tc_ws": (C.c_int, [_GP, _TP, _TP, _P, _P, _L, _P]),
     "semb_norm_finalize": (C.c_int, [_P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P]),
     "semb_norm_from_moving": (C.c_int, [_I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "semb_affine_act_fwd": (C.c_int, [_AP, _TP, _P, _P, _TP, _P, _P, _TP, _P, _I, _I, _P]),

@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, launch counter, device check.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace semb {
 
@@ -12,6 +13,11 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SEMB_NO_PDL"); return !(e && e[0] && e[0] != '0'); }();
+    return on;
 }
 
 int check_launch(const char* what) {

@@ -25,6 +25,32 @@ extern long long g_launch_count;
     } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch ------------------------------------------------------------
+// A training step is ~400 dependent launches of 10-80 us kernels: without overlap every kernel boundary costs the launch
+// latency plus the next kernel's prologue (barrier init, TMEM allocation, shared-memory zeroing, tensor-map prefetch).
+// Kernels launched through launch_pdl() may start while their predecessor in the stream drains; they call pdl_wait()
+// before their first access to global memory (it returns once the predecessor grid has completed and flushed), and
+// pdl_trigger() at their top so that their own successor can be scheduled early.  SEMB_NO_PDL=1 launches them serially.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivl(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -56,6 +56,8 @@ struct PackJob {
 };
 
 __global__ void pack_weights_batch_kernel(const PackJob* __restrict__ jobs, int njobs) {
+    pdl_trigger();
+    pdl_wait();
     int j = 0;
     while (j + 1 < njobs && (int)blockIdx.x >= jobs[j + 1].block0) ++j;
     const PackJob job = jobs[j];
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
     __shared__ __align__(8) uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], done_bar;
     __shared__ uint32_t tmem_slot;
 
+    pdl_trigger();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int taps = a.R * a.S;
     const int NCH = a.p.NCH;
@@ -464,6 +467,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgArgs a) {
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
     const uint32_t smem_base = smem_u32(smem);
+    pdl_wait();
 
     if (warp < 4) {
         // ===================== producers =====================
@@ -732,7 +736,7 @@ extern "C" int semb_pack_batch_prepare(int32_t index, const float* w, void* dst,
 
 extern "C" int semb_pack_weights_tc_batch(const void* device_jobs, int32_t njobs, int32_t total_blocks, void* stream) {
     SEMB_REQUIRE(device_jobs && njobs > 0 && total_blocks > 0, SEMB_ESHAPE, "pack_weights_tc_batch: bad arguments");
-    pack_weights_batch_kernel<<<total_blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const PackJob*>(device_jobs), njobs);
+    launch_pdl(pack_weights_batch_kernel, dim3(total_blocks), dim3(256), 0, as_stream(stream), reinterpret_cast<const PackJob*>(device_jobs), njobs);
     return check_launch("pack_weights_tc_batch");
 }
 
@@ -804,6 +808,27 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     return check_launch("conv_tc");
 }
 
+extern "C" int64_t semb_conv2d_wgrad_tc_workspace(const semb_conv_geom* g) {
+    if (!g || g->dtype != SEMB_BF16 || g->stride != 1 || g->R != 3 || g->S != 3 || g->pad_mode != SEMB_PAD_ZERO || g->pad_t > 2 || g->pad_l > 2)
+        return 0;
+    // planar staging pays where the channel-group count makes the 16-byte NHWC box rows the limit (measured on the CycleGAN layers)
+    static const int min_c = [] { const char* e = getenv("SEMB_WGRAD_PLANAR_MIN_C"); return e ? atoi(e) : 128; }();
+    if (g->Cin < min_c || g->Cout < min_c) return 0;
+    return (int64_t)wgrad_tma_workspace_bytes(g);
+}
+
+extern "C" int semb_conv2d_wgrad_tc_ws(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+    if (!workspace) return semb_conv2d_wgrad_tc(g, x, dy, dw, stream);
+    SEMB_REQUIRE(g && x && dy && dw, SEMB_ESHAPE, "wgrad_tc_ws: null argument");
+    const int64_t need = semb_conv2d_wgrad_tc_workspace(g);
+    SEMB_REQUIRE(need > 0, SEMB_ESHAPE, "wgrad_tc_ws: this geometry has no planar path (query semb_conv2d_wgrad_tc_workspace first)");
+    SEMB_REQUIRE(workspace_bytes >= need, SEMB_EWORKSPACE, "wgrad_tc_ws: %lld bytes of workspace needed, %lld given", (long long)need,
+                 (long long)workspace_bytes);
+    SEMB_REQUIRE(view_ok(x) && view_ok(dy) && x->C == g->Cin && dy->C == g->Cout, SEMB_EALIGN, "wgrad_tc_ws: bad tensor views");
+    return wgrad_tma_launch(g, x, dy, dw, workspace, stream);
+}
+
 extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw,
                                     void* stream) {
     SEMB_REQUIRE(g && x && dy && dw, SEMB_ESHAPE, "wgrad_tc: null argument");
@@ -812,7 +837,7 @@ extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* 
                  "wgrad_tc: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
     SEMB_REQUIRE(view_ok(x) && view_ok(dy) && x->C == g->Cin && dy->C == g->Cout, SEMB_EALIGN, "wgrad_tc: bad tensor views");
     if (g->R == 3 && g->pad_mode == SEMB_PAD_ZERO && g->pad_t <= 2 && g->pad_l <= 2 && !getenv("SEMB_WGRAD_NO_TMA"))
-        return wgrad_tma_launch(g, x, dy, dw, stream);
+        return wgrad_tma_launch(g, x, dy, dw, nullptr, stream);
     if (g->R == 3 && g->Cin <= 40 && g->Cout <= 128 && g->pad_t <= 2 && g->pad_l <= 2 && !getenv("SEMB_WGRAD_NO_STACK")) {
         WsArgs w{};
         w.N = g->N; w.H = g->H; w.W = g->W; w.OH = g->OH; w.OW = g->OW; w.Cin = g->Cin; w.Cout = g->Cout;
@@ -884,10 +909,10 @@ extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* 
 #define SEMB_WG_LAUNCH(COLS)                                                                                          \
     if (a.p.stages == 3) {                                                                                            \
         e = cudaFuncSetAttribute(wgrad_tc_kernel<COLS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (e == cudaSuccess) wgrad_tc_kernel<COLS, 3><<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);             \
+        if (e == cudaSuccess) e = launch_pdl(wgrad_tc_kernel<COLS, 3>, grid, dim3(WG_THREADS), smem, as_stream(stream), a); \
     } else {                                                                                                          \
         e = cudaFuncSetAttribute(wgrad_tc_kernel<COLS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        if (e == cudaSuccess) wgrad_tc_kernel<COLS, 2><<<grid, WG_THREADS, smem, as_stream(stream)>>>(a);             \
+        if (e == cudaSuccess) e = launch_pdl(wgrad_tc_kernel<COLS, 2>, grid, dim3(WG_THREADS), smem, as_stream(stream), a); \
     }
     switch (a.p.cols) {
         case 32: SEMB_WG_LAUNCH(32) break;

@@ -34,6 +34,7 @@ struct TmArgs {
     int plane_pitch;      // bytes between channel-group planes of a stage (multiple of 128)
     int plane_box;        // bytes the TMA writes per plane (halo_h * halo_w * 16)
     int nstages;
+    int bsplit;           // bulk copies per streamed weight chunk (b_bytes / bsplit must be a multiple of 16)
 };
 
 // all three are called by a CONVERGED warp; elect.sync picks the lane that issues (see umma_bf16_elect)
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TM_MAX_STAGES], empty_bar[TM_MAX_STAGES], acc_full[TM_MAX_ACC], acc_empty[TM_MAX_ACC], b_full;
     __shared__ uint32_t tmem_slot;
+    pdl_trigger();                  // the successor's prologue may overlap this kernel's tail
     const TcArgs& a = args.t;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KC = a.p.KC, NC = NCT > 0 ? NCT : a.p.NC, kchunks = a.p.kchunks;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();                     // everything above touched only shared memory / TMEM; global memory from here on
 
     if (warp == 10) {
         // ============================== TMA producer (whole warp converged) ==============================
@@ -136,8 +139,13 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                         asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
                                      "@e mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;\n\t}" ::"r"(bar), "r"((uint32_t)(real * args.plane_box)) : "memory");
                     }
-                    if (!a.b_resident)
-                        bulk_load(sbase + a.a_bytes, a.wp + ((size_t)nchunk * kchunks + kc) * taps * KC * NC, (uint32_t)a.b_bytes, bar);
+                    if (!a.b_resident) {
+                        // the weight chunk of a stage as `bsplit` concurrent bulk copies (one 70 KB copy is served at ~25 B/clk)
+                        const uint32_t piece = (uint32_t)a.b_bytes / (uint32_t)args.bsplit;
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wp + ((size_t)nchunk * kchunks + kc) * taps * KC * NC);
+                        for (int q = 0; q < args.bsplit; ++q)
+                            bulk_load(sbase + a.a_bytes + q * piece, src + (size_t)q * piece, piece, bar);
+                    }
                     if (w) { if (++slot1 == half) { slot1 = 0; ph1 ^= 1; } }
                     else   { if (++slot0 == half) { slot0 = 0; ph0 ^= 1; } }
                 }
@@ -394,6 +402,13 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     if (A.nmma == 2) nst &= ~1;             // two half-rings, one per MMA warp
     A.nstages = nst;
     a.stages = nst;
+    A.bsplit = 1;
+    if (!a.b_resident) {
+        static const int want = [] { const char* e = getenv("SEMB_TMA_BSPLIT"); return e ? atoi(e) : 1; }();
+        int q = want < 1 ? 1 : want;
+        while (q > 1 && (a.b_bytes % (q * 16)) != 0) --q;
+        A.bsplit = q;
+    }
     const size_t smem = (size_t)nst * a.stage_bytes + fixed;
     SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tma: %zu bytes of shared memory needed", smem);
     A.nacc = a.p.NC <= 64 ? 4 : 2;
@@ -428,7 +443,7 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     cudaError_t e = cudaSuccess;
 #define SEMB_TM_LAUNCH3(NCT, KR, KS)                                                                                     \
     e = cudaFuncSetAttribute(conv_tma_kernel<NCT, KR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    if (e == cudaSuccess) conv_tma_kernel<NCT, KR, KS><<<grid, TM_THREADS, smem, as_stream(stream)>>>(A, xmap);
+    if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<NCT, KR, KS>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap);
 #define SEMB_TM_LAUNCH2(NCT, KR)                                                                                         \
     switch (ks_fixed) {                                                                                                  \
         case 1: SEMB_TM_LAUNCH3(NCT, KR, 1) break;                                                                       \
@@ -444,7 +459,7 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
 #undef SEMB_TM_LAUNCH
 #undef SEMB_TM_LAUNCH2
 #undef SEMB_TM_LAUNCH3
-    if (e != cudaSuccess) { set_error("conv_tma: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
+    if (e != cudaSuccess) { set_error("conv_tma: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SEMB_ECUDA; }
     return check_launch("conv_tma");
 }
 

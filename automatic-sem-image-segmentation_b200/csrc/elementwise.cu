@@ -157,6 +157,8 @@ __device__ __forceinline__ void fin_params(const semb_norm_fin& f, int g, int c,
 // y = act(a*sa+ta [+ actb(b*sb+tb)]), optional fp64 moments of y.  U pixels per thread are loaded before any is used.
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];  // [rows][2][C] + [<=256] when moments are requested
     constexpr int U = HAS_B ? SEMB_AFF_U_FWD_B : SEMB_AFF_U_FWD;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p)
 // output y is never re-read.
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kernel(const AffArgs p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sm[];  // [rows][4][C] + [<=256]
     constexpr int U = HAS_B ? 2 : SEMB_AFF_U_BWD;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
@@ -330,6 +334,8 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kern
 // Pa = Qa = 0 for a constant affine; same for b with gb = g*actb'(ub).
 template <typename T, bool HAS_B, int ACT, int ACTB>
 __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kernel(const AffArgs p) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int U = HAS_B ? 2 : SEMB_AFF_U_BWD;
     const int act = ACT >= 0 ? ACT : p.act, actb = ACTB >= 0 ? ACTB : p.actb;
     const Lanes L(p.C);
@@ -795,17 +801,20 @@ extern "C" int semb_norm_bwd_finalize(const float* sums, int32_t which, int32_t 
 }
 
 
+// every affine kernel starts with pdl_trigger() / pdl_wait() (the fused cooperative one is launched elsewhere)
+#define SEMB_AFF_GO(grid, smem, st, p, ...) launch_pdl(__VA_ARGS__, dim3(grid), dim3(256), smem, st, p)
+
 // (activation, second-operand activation) combinations compiled statically; anything else takes the runtime path
 #define SEMB_AFF_DISPATCH(KERNEL, T, HASB, grid, smem, st, p)                                                       \
     do {                                                                                                            \
         if ((p).act == SEMB_ACT_NONE && (!(HASB) || (p).actb == SEMB_ACT_NONE))                                     \
-            KERNEL<T, HASB, SEMB_ACT_NONE, SEMB_ACT_NONE><<<grid, 256, smem, st>>>(p);                              \
+            SEMB_AFF_GO(grid, smem, st, p, KERNEL<T, HASB, SEMB_ACT_NONE, SEMB_ACT_NONE>);                              \
         else if ((p).act == SEMB_ACT_RELU && (!(HASB) || (p).actb == SEMB_ACT_NONE))                                \
-            KERNEL<T, HASB, SEMB_ACT_RELU, SEMB_ACT_NONE><<<grid, 256, smem, st>>>(p);                              \
+            SEMB_AFF_GO(grid, smem, st, p, KERNEL<T, HASB, SEMB_ACT_RELU, SEMB_ACT_NONE>);                              \
         else if ((p).act == SEMB_ACT_RELU && (p).actb == SEMB_ACT_RELU)                                             \
-            KERNEL<T, HASB, SEMB_ACT_RELU, SEMB_ACT_RELU><<<grid, 256, smem, st>>>(p);                              \
+            SEMB_AFF_GO(grid, smem, st, p, KERNEL<T, HASB, SEMB_ACT_RELU, SEMB_ACT_RELU>);                              \
         else                                                                                                        \
-            KERNEL<T, HASB, -1, -1><<<grid, 256, smem, st>>>(p);                                                    \
+            SEMB_AFF_GO(grid, smem, st, p, KERNEL<T, HASB, -1, -1>);                                                    \
     } while (0)
 
 #define SEMB_AFF_LAUNCH(KERNEL, dtype, has_b, grid, smem, st, p)                                                    \

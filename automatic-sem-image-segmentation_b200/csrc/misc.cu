@@ -16,6 +16,8 @@ __device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
 // ---- MaxPooling2D((2,2)) ------------------------------------------------------------------------
 template <typename T, bool BWD>
 __global__ void maxpool_kernel(PView x, PView y /* fwd: out, bwd: dy */, PView dx, int N, int H, int W, int C8, int acc) {
+    pdl_trigger();
+    pdl_wait();
     const int OH = H / 2, OW = W / 2;
     const long long total = (long long)N * OH * OW * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -66,6 +68,8 @@ __global__ void maxpool_kernel(PView x, PView y /* fwd: out, bwd: dy */, PView d
 template <typename T>
 __global__ void pad_crop_kernel(PView x, PView y, int N, int H, int W, int OH, int OW, int top, int left, int mode,
                                 int C8, int acc) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = (long long)N * OH * OW * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8) * 8;
@@ -167,6 +171,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) loss_wbce_logits_kernel(PView z, const float* __restrict__ scale, const float* __restrict__ shift,
                                                                const float* __restrict__ yt, PView dp, long long count, float weighting,
                                                                float* out) {
+    pdl_trigger();
+    pdl_wait();
     float acc[3] = {0.f, 0.f, 0.f};
     const float eps = 1e-7f, inv_count = 1.f / (float)count;
     const float sc = scale[0], sh = shift[0];
@@ -194,6 +200,8 @@ __global__ void __launch_bounds__(256) loss_wbce_logits_kernel(PView z, const fl
 template <typename T>
 __global__ void __launch_bounds__(256) loss_l1_l2_kernel(PView a, PView b, float target, int kind, long long n_pixels, int C8,
                                                          int c_logical, float gscale, PView da, int acc, float* out) {
+    pdl_trigger();
+    pdl_wait();
     float sum[1] = {0.f};
     const long long total = n_pixels * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -227,6 +235,8 @@ __global__ void __launch_bounds__(256) loss_l1_l2_kernel(PView a, PView b, float
 struct AdamState { long long t; float alpha; float pad; };
 
 __global__ void adam_tick_kernel(AdamState* st, const float* lr, float b1, float b2) {
+    pdl_trigger();
+    pdl_wait();
     const long long t = st->t + 1;
     st->t = t;
     st->alpha = (float)((double)lr[0] * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
@@ -235,6 +245,8 @@ __global__ void adam_tick_kernel(AdamState* st, const float* lr, float b1, float
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, const AdamState* st, float b1, float b2,
                                                    float eps, float gscale) {
+    pdl_trigger();
+    pdl_wait();
     const float alpha = st->alpha;
     for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
         if (i + 4 <= n) {
@@ -263,11 +275,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const 
 }
 
 __global__ void fill_kernel(float* p, long long n, float value) {
+    pdl_trigger();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = value;
 }
 
 template <typename T>
 __global__ void cast_in_kernel(const float* __restrict__ src, int src_C, PView dst, long long n_pixels, int C8) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = n_pixels * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C8) * 8;
@@ -299,6 +315,8 @@ __global__ void cast_out_kernel(PView src, float* __restrict__ dst, int dst_C, l
 template <typename T>
 __global__ void pixel_shuffle2_kernel(PView src, PView dst, int N, int H, int W, int DH, int DW, int C8, const float* __restrict__ bias,
                                       int dir, int acc) {
+    pdl_trigger();
+    pdl_wait();
     // dst is (N, DH, DW, C) with DH <= 2H, DW <= 2W (odd sizes: the missing last row / column reads as zero, is not written)
     const long long total = (long long)N * H * W * 4 * C8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -495,8 +513,8 @@ extern "C" int semb_maxpool2x2_fwd(const semb_tensor* x, const semb_tensor* y, i
     SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, SEMB_ESHAPE, "maxpool fwd: H,W must be even");
     const int C8 = x->C / 8;
     const long long total = (long long)N * (H / 2) * (W / 2) * C8;
-    if (dtype == SEMB_BF16) maxpool_kernel<bf16, false><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), PView{}, N, H, W, C8, 0);
-    else maxpool_kernel<float, false><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), PView{}, N, H, W, C8, 0);
+    if (dtype == SEMB_BF16) launch_pdl(maxpool_kernel<bf16, false>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(x), pv(y), PView{}, N, H, W, C8, 0);
+    else launch_pdl(maxpool_kernel<float, false>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(x), pv(y), PView{}, N, H, W, C8, 0);
     return check_launch("maxpool_fwd");
 }
 
@@ -506,8 +524,8 @@ extern "C" int semb_maxpool2x2_bwd(const semb_tensor* x, const semb_tensor* dy, 
     SEMB_REQUIRE(N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, SEMB_ESHAPE, "maxpool bwd: H,W must be even");
     const int C8 = x->C / 8;
     const long long total = (long long)N * (H / 2) * (W / 2) * C8;
-    if (dtype == SEMB_BF16) maxpool_kernel<bf16, true><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(dy), pv(dx), N, H, W, C8, accumulate);
-    else maxpool_kernel<float, true><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(dy), pv(dx), N, H, W, C8, accumulate);
+    if (dtype == SEMB_BF16) launch_pdl(maxpool_kernel<bf16, true>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(x), pv(dy), pv(dx), N, H, W, C8, accumulate);
+    else launch_pdl(maxpool_kernel<float, true>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(x), pv(dy), pv(dx), N, H, W, C8, accumulate);
     return check_launch("maxpool_bwd");
 }
 
@@ -525,8 +543,8 @@ extern "C" int semb_pad_crop(const semb_tensor* x, const semb_tensor* y, int32_t
     }
     const int C8 = x->C / 8;
     const long long total = (long long)N * OH * OW * C8;
-    if (dtype == SEMB_BF16) pad_crop_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), N, H, W, OH, OW, top, left, mode, C8, accumulate);
-    else pad_crop_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(x), pv(y), N, H, W, OH, OW, top, left, mode, C8, accumulate);
+    if (dtype == SEMB_BF16) launch_pdl(pad_crop_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(x), pv(y), N, H, W, OH, OW, top, left, mode, C8, accumulate);
+    else launch_pdl(pad_crop_kernel<float>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(x), pv(y), N, H, W, OH, OW, top, left, mode, C8, accumulate);
     return check_launch("pad_crop");
 }
 
@@ -542,8 +560,8 @@ extern "C" int semb_loss_wbce_logits(const semb_tensor* z, const float* scale, c
                                      const semb_tensor* dp, int64_t count, float weighting, float* out, int32_t dtype, void* stream) {
     SEMB_REQUIRE(view_ok(z) && scale && shift && y_true && out && count > 0 && (!dp || view_ok(dp)), SEMB_ESHAPE,
                  "loss_wbce_logits: bad arguments");
-    if (dtype == SEMB_BF16) loss_wbce_logits_kernel<bf16><<<grid_for(count), 256, 0, as_stream(stream)>>>(pv(z), scale, shift, y_true, pv(dp), count, weighting, out);
-    else loss_wbce_logits_kernel<float><<<grid_for(count), 256, 0, as_stream(stream)>>>(pv(z), scale, shift, y_true, pv(dp), count, weighting, out);
+    if (dtype == SEMB_BF16) launch_pdl(loss_wbce_logits_kernel<bf16>, dim3(grid_for(count)), dim3(256), 0, as_stream(stream), pv(z), scale, shift, y_true, pv(dp), count, weighting, out);
+    else launch_pdl(loss_wbce_logits_kernel<float>, dim3(grid_for(count)), dim3(256), 0, as_stream(stream), pv(z), scale, shift, y_true, pv(dp), count, weighting, out);
     return check_launch("loss_wbce_logits");
 }
 
@@ -555,8 +573,8 @@ extern "C" int semb_loss_l1_l2(const semb_tensor* a, const semb_tensor* b, float
     SEMB_REQUIRE(kind == 0 || kind == 1, SEMB_ESHAPE, "loss_l1_l2: kind must be 0 (L1) or 1 (L2)");
     const int C8 = a->C / 8;
     const long long total = n_pixels * C8;
-    if (dtype == SEMB_BF16) loss_l1_l2_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(a), pv(b), target, kind, n_pixels, C8, c_logical, gscale, pv(da), accumulate, out);
-    else loss_l1_l2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(a), pv(b), target, kind, n_pixels, C8, c_logical, gscale, pv(da), accumulate, out);
+    if (dtype == SEMB_BF16) launch_pdl(loss_l1_l2_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(a), pv(b), target, kind, n_pixels, C8, c_logical, gscale, pv(da), accumulate, out);
+    else launch_pdl(loss_l1_l2_kernel<float>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(a), pv(b), target, kind, n_pixels, C8, c_logical, gscale, pv(da), accumulate, out);
     return check_launch("loss_l1_l2");
 }
 
@@ -565,25 +583,25 @@ extern "C" int semb_adam_step(float* w, const float* g, float* m, float* v, int6
     SEMB_REQUIRE(w && g && m && v && lr_ptr && state && n > 0, SEMB_ESHAPE, "adam: bad arguments");
     SEMB_REQUIRE(((uintptr_t)w % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0,
                  SEMB_EALIGN, "adam: buffers must be 16B aligned");
-    adam_tick_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<AdamState*>(state), lr_ptr, beta1, beta2);
+    launch_pdl(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), reinterpret_cast<AdamState*>(state), lr_ptr, beta1, beta2);
     int rc = check_launch("adam_tick");
     if (rc) return rc;
-    adam_kernel<<<grid_for(cdivl(n, 4)), 256, 0, as_stream(stream)>>>(w, g, m, v, n, reinterpret_cast<const AdamState*>(state), beta1, beta2, eps, gscale);
+    launch_pdl(adam_kernel, dim3(grid_for(cdivl(n, 4))), dim3(256), 0, as_stream(stream), w, g, m, v, n, reinterpret_cast<const AdamState*>(state), beta1, beta2, eps, gscale);
     return check_launch("adam");
 }
 
 extern "C" int semb_fill_f32(float* p, int64_t n, float value, void* stream) {
     SEMB_REQUIRE(p && n >= 0, SEMB_ESHAPE, "fill: bad arguments");
     if (n == 0) return SEMB_OK;
-    fill_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(p, n, value);
+    launch_pdl(fill_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), p, n, value);
     return check_launch("fill");
 }
 
 extern "C" int semb_cast_in(const float* src, int32_t src_C, const semb_tensor* dst, int64_t n_pixels, int32_t dtype, void* stream) {
     SEMB_REQUIRE(src && view_ok(dst) && n_pixels > 0 && src_C > 0 && src_C <= dst->C, SEMB_ESHAPE, "cast_in: bad arguments");
     const int C8 = dst->C / 8;
-    if (dtype == SEMB_BF16) cast_in_kernel<bf16><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(src, src_C, pv(dst), n_pixels, C8);
-    else cast_in_kernel<float><<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(src, src_C, pv(dst), n_pixels, C8);
+    if (dtype == SEMB_BF16) launch_pdl(cast_in_kernel<bf16>, dim3(grid_for(n_pixels * C8)), dim3(256), 0, as_stream(stream), src, src_C, pv(dst), n_pixels, C8);
+    else launch_pdl(cast_in_kernel<float>, dim3(grid_for(n_pixels * C8)), dim3(256), 0, as_stream(stream), src, src_C, pv(dst), n_pixels, C8);
     return check_launch("cast_in");
 }
 
@@ -602,8 +620,8 @@ extern "C" int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* d
                  SEMB_ESHAPE, "pixel_shuffle2: bad geometry");
     const int C8 = dst->C / 8;
     const long long total = (long long)N * H * W * 4 * C8;
-    if (dtype == SEMB_BF16) pixel_shuffle2_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, DH, DW, C8, bias, dir, acc);
-    else pixel_shuffle2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), N, H, W, DH, DW, C8, bias, dir, acc);
+    if (dtype == SEMB_BF16) launch_pdl(pixel_shuffle2_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(src), pv(dst), N, H, W, DH, DW, C8, bias, dir, acc);
+    else launch_pdl(pixel_shuffle2_kernel<float>, dim3(grid_for(total)), dim3(256), 0, as_stream(stream), pv(src), pv(dst), N, H, W, DH, DW, C8, bias, dir, acc);
     return check_launch("pixel_shuffle2");
 }
 

@@ -222,6 +222,7 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
                     void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream);
 
 // wgrad_tma.cu: TMA-staged weight gradient of the zero-padded 3x3 layers
-int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* stream);
+int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace, void* stream);
+size_t wgrad_tma_workspace_bytes(const semb_conv_geom* g);
 
 }  // namespace semb

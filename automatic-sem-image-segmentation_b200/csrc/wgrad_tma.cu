@@ -32,6 +32,8 @@ constexpr int WT_PLANE_A = (TILE_H + 2) * TILE_W * 16;   // 2304 bytes: [18 rows
 constexpr int WT_PLANE_B = TILE_H * TILE_W * 16;         // 2048 bytes: [16 rows][8 pixels][8 channels]
 
 struct WtArgs {
+    int planar;              // operands are planar copies [N][C/8][H][W][8]: ONE TMA box per replica with 128-byte rows
+    int ps;                  // planes between two horizontal-tap replicas in shared memory (p, or pc for planar boxes)
     int Cin, Cout, x_coff, dy_coff, pad_t, pad_l;
     float* dw;
     int tiles_x, tiles_y, total_tiles, splits;
@@ -63,6 +65,7 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tma_kernel(const WtArgs a, c
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[WT_MAX_STAGES], empty_bar[WT_MAX_STAGES], done_bar;
     __shared__ uint32_t tmem_slot;
+    pdl_trigger();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = blockIdx.y;
     const int cic = chunk % a.cin_chunks, coc = chunk / a.cin_chunks;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tma_kernel(const WtArgs a, c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();
 
     if (warp == 6) {
         // ===================== TMA producer (whole warp converged) =====================
@@ -101,18 +105,27 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tma_kernel(const WtArgs a, c
         TileIter it(blockIdx.x, a.splits, a.tiles_x, a.tiles_y);
         int stage = 0;
         uint32_t phase = 1;
-        const uint32_t bytes = (uint32_t)(3 * p * WT_PLANE_A + nb8 * WT_PLANE_B);
+        // planar boxes always carry pc (resp. NB/8) planes; planes past the end of the tensor are zero-filled by the TMA
+        const uint32_t bytes = a.planar ? (uint32_t)(3 * a.pc * WT_PLANE_A + (NB >> 3) * WT_PLANE_B)
+                                        : (uint32_t)(3 * p * WT_PLANE_A + nb8 * WT_PLANE_B);
         for (int i = 0; i < ntiles; ++i, it.next()) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase);
             const int y0 = it.ty * TILE_H, x0 = it.tx * TILE_W;
             const uint32_t sbase = smem_base + stage * a.stage_bytes;
             const uint32_t bar = smem_u32(&full_bar[stage]);
             wt_expect_tx(bar, bytes);
-            for (int k8 = 0; k8 < nb8; ++k8)
-                wt_tma_4d(sbase + a.a_bytes + k8 * WT_PLANE_B, &dymap, a.dy_coff + co0 + k8 * 8, x0, y0, it.n, bar);
-            for (int s = 0; s < 3; ++s)
-                for (int k8 = 0; k8 < p; ++k8)
-                    wt_tma_4d(sbase + (s * p + k8) * WT_PLANE_A, &xmap, a.x_coff + (plane0 + k8) * 8, x0 - a.pad_l + s, y0 - a.pad_t, it.n, bar);
+            if (a.planar) {
+                // tensor map dims {W*8, H, C/8, N}: dim 0 runs over the 8-channel groups of one image row (16 B per pixel)
+                wt_tma_4d(sbase + a.a_bytes, &dymap, x0 * 8, y0, co0 >> 3, it.n, bar);
+                for (int s = 0; s < 3; ++s)
+                    wt_tma_4d(sbase + s * a.ps * WT_PLANE_A, &xmap, (x0 - a.pad_l + s) * 8, y0 - a.pad_t, plane0, it.n, bar);
+            } else {
+                for (int k8 = 0; k8 < nb8; ++k8)
+                    wt_tma_4d(sbase + a.a_bytes + k8 * WT_PLANE_B, &dymap, a.dy_coff + co0 + k8 * 8, x0, y0, it.n, bar);
+                for (int s = 0; s < 3; ++s)
+                    for (int k8 = 0; k8 < p; ++k8)
+                        wt_tma_4d(sbase + (s * p + k8) * WT_PLANE_A, &xmap, a.x_coff + (plane0 + k8) * 8, x0 - a.pad_l + s, y0 - a.pad_t, it.n, bar);
+            }
             if (++stage == a.nstages) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4) {
@@ -152,8 +165,9 @@ __global__ void __launch_bounds__(WT_THREADS) wgrad_tma_kernel(const WtArgs a, c
         if (ntiles > 0) {
             const int l = warp * 32 + lane;
             const int g = l >> 3;
-            const bool rvalid = g < 3 * p;
-            const int s = g / p, k8 = g - s * p;
+            const int ps = a.planar ? a.ps : p;
+            const int s = g / ps, k8 = g - s * ps;
+            const bool rvalid = s < 3 && k8 < p;
             const int ci = (plane0 + k8) * 8 + (l & 7);
             const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
             for (int r = 0; r < 3; ++r) {
@@ -200,9 +214,53 @@ static bool wt_make_map(EncodeTiledFn enc, CUtensorMap* map, const semb_tensor* 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// NHWC view (pitch, coff) -> planar [N][C/8][H][W][8]: the layout whose TMA boxes have 128-byte rows.  A block moves
+// 32 pixels x 32 channel groups through shared memory so that both the reads (across channel groups of a pixel) and the
+// writes (across pixels of a plane) are contiguous.
+__global__ void __launch_bounds__(256) nhwc_to_planar_kernel(const bf16* __restrict__ src, int pitch, int coff, uint4* __restrict__ dst,
+                                                             long long HW, int P) {
+    __shared__ uint4 tile[32][33];
+    pdl_trigger();
+    pdl_wait();
+    const int n = blockIdx.z;
+    const long long px0 = (long long)blockIdx.x * 32;
+    const int p0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;           // 32 x 8 threads
+    for (int j = ty; j < 32; j += 8) {                                 // j = pixel, tx = plane
+        const long long px = px0 + j;
+        if (px < HW && p0 + tx < P)
+            tile[j][tx] = *reinterpret_cast<const uint4*>(src + ((size_t)n * HW + px) * pitch + coff + (size_t)(p0 + tx) * 8);
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {                                 // j = plane, tx = pixel
+        const long long px = px0 + tx;
+        if (px < HW && p0 + j < P) dst[((size_t)n * P + p0 + j) * HW + px] = tile[tx][j];
+    }
+}
+
+static bool wt_make_planar_map(EncodeTiledFn enc, CUtensorMap* map, const void* base, int W, int H, int P, int N, int box_h, int box_p) {
+    const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)P, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)P * H * W * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)TILE_W * 8, (cuuint32_t)box_h, (cuuint32_t)box_p, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t wgrad_tma_workspace_bytes(const semb_conv_geom* g) {
+    // planar copies of x and dy, each starting on a 128-byte boundary
+    const size_t xb = ((size_t)g->N * g->H * g->W * g->Cin * 2 + 127) / 128 * 128;
+    const size_t yb = ((size_t)g->N * g->OH * g->OW * g->Cout * 2 + 127) / 128 * 128;
+    return xb + yb;
+}
+
 // Called by semb_conv2d_wgrad_tc (conv_tc.cu) after argument validation, for zero-padded 3x3 geometries.
-int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* stream) {
+// workspace != NULL: the operands are first copied into planar layout (see nhwc_to_planar_kernel) -- for the layers with
+// hundreds of channels (CycleGAN residual blocks) the NHWC boxes (16-byte rows, one per pixel and channel group) made the
+// TMA unit, not the tensor pipe, the limit of this kernel.
+int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace, void* stream) {
     WtArgs a{};
+    a.planar = workspace != nullptr;
     a.Cin = g->Cin; a.Cout = g->Cout; a.x_coff = x->coff; a.dy_coff = dy->coff; a.pad_t = g->pad_t; a.pad_l = g->pad_l;
     a.dw = dw;
     a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
@@ -213,6 +271,7 @@ int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_t
     a.cout_chunks = cdiv(g->Cout, 80);
     a.NB = (cdiv(g->Cout, a.cout_chunks) + 15) / 16 * 16;
     a.cout_chunks = cdiv(g->Cout, a.NB);
+    a.ps = a.pc;
     a.a_bytes = 3 * a.pc * WT_PLANE_A;
     a.stage_bytes = a.a_bytes + (a.NB / 8) * WT_PLANE_B;
     const int need = 6 * a.NB;                                         // two issuers x three vertical taps
@@ -242,11 +301,31 @@ int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_t
     EncodeTiledFn enc = wt_encode_tiled();
     SEMB_REQUIRE(enc != nullptr, SEMB_ECUDA, "wgrad_tma: cuTensorMapEncodeTiled is not available from the driver");
     CUtensorMap xmap, dymap;
-    SEMB_REQUIRE(wt_make_map(enc, &xmap, x, g->W, g->H, g->N, TILE_H + 2) && wt_make_map(enc, &dymap, dy, g->OW, g->OH, g->N, TILE_H),
-                 SEMB_ECUDA, "wgrad_tma: cuTensorMapEncodeTiled failed");
+    if (a.planar) {
+        SEMB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) % 128) == 0, SEMB_EALIGN, "wgrad_tma: the workspace must be 128-byte aligned");
+        uint8_t* xp = reinterpret_cast<uint8_t*>(workspace);
+        uint8_t* yp = xp + ((size_t)g->N * g->H * g->W * g->Cin * 2 + 127) / 128 * 128;
+        const long long hwx = (long long)g->H * g->W, hwy = (long long)g->OH * g->OW;
+        const int Px = g->Cin / 8, Py = g->Cout / 8;
+        launch_pdl(nhwc_to_planar_kernel, dim3((unsigned)cdivl(hwx, 32), cdiv(Px, 32), g->N), dim3(256), 0, as_stream(stream),
+                   reinterpret_cast<const bf16*>(x->ptr), x->pitch, x->coff, reinterpret_cast<uint4*>(xp), hwx, Px);
+        int rc = check_launch("nhwc_to_planar(x)");
+        if (rc) return rc;
+        launch_pdl(nhwc_to_planar_kernel, dim3((unsigned)cdivl(hwy, 32), cdiv(Py, 32), g->N), dim3(256), 0, as_stream(stream),
+                   reinterpret_cast<const bf16*>(dy->ptr), dy->pitch, dy->coff, reinterpret_cast<uint4*>(yp), hwy, Py);
+        rc = check_launch("nhwc_to_planar(dy)");
+        if (rc) return rc;
+        SEMB_REQUIRE(wt_make_planar_map(enc, &xmap, xp, g->W, g->H, Px, g->N, TILE_H + 2, a.pc) &&
+                     wt_make_planar_map(enc, &dymap, yp, g->OW, g->OH, Py, g->N, TILE_H, a.NB / 8),
+                     SEMB_ECUDA, "wgrad_tma: cuTensorMapEncodeTiled failed (planar)");
+    } else {
+        SEMB_REQUIRE(wt_make_map(enc, &xmap, x, g->W, g->H, g->N, TILE_H + 2) && wt_make_map(enc, &dymap, dy, g->OW, g->OH, g->N, TILE_H),
+                     SEMB_ECUDA, "wgrad_tma: cuTensorMapEncodeTiled failed");
+    }
     cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("wgrad_tma: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SEMB_ECUDA; }
-    wgrad_tma_kernel<<<dim3(a.splits, chunks), WT_THREADS, smem, as_stream(stream)>>>(a, xmap, dymap);
+    e = launch_pdl(wgrad_tma_kernel, dim3(a.splits, chunks), dim3(WT_THREADS), smem, as_stream(stream), a, xmap, dymap);
+    if (e != cudaSuccess) { set_error("wgrad_tma: launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return SEMB_ECUDA; }
     return check_launch("wgrad_tma");
 }
 

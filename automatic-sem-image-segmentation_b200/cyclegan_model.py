@@ -241,10 +241,17 @@ class CycleGanModel:
     # ---- the step ------------------------------------------------------------------------------------------
     def train_step(self, batch) -> Dict[str, float]:
         real_a, real_b = batch
-        self.a_pin.copy_(torch.as_tensor(np.ascontiguousarray(real_a, dtype=np.float32)))
-        self.b_pin.copy_(torch.as_tensor(np.ascontiguousarray(real_b, dtype=np.float32)))
-        self.a_dev.copy_(self.a_pin, non_blocking=True)
-        self.b_dev.copy_(self.b_pin, non_blocking=True)
+
+        def host(arr, pin):
+            # a caller-pinned float32 tensor is uploaded as it is (zero copy); anything else is staged through pinned memory
+            if isinstance(arr, torch.Tensor) and arr.device.type == "cpu" and arr.dtype == torch.float32 and arr.is_contiguous() \
+                    and arr.is_pinned() and tuple(arr.shape) == tuple(pin.shape):
+                return arr
+            pin.copy_(torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)))
+            return pin
+
+        self.a_dev.copy_(host(real_a, self.a_pin), non_blocking=True)
+        self.b_dev.copy_(host(real_b, self.b_pin), non_blocking=True)
         self.step_device()
         self.sums_pin.copy_(self.sums, non_blocking=True)
         torch.cuda.current_stream().synchronize()

@@ -357,6 +357,25 @@ class Engine:
             L.check(self.lib.semb_pack_weights_tc_batch(table.data_ptr(), n, blocks, self.stream))
         self._pack_dirty = False
 
+    def wgrad_tc(self, geom, x_t, dy_t, dw_ptr: int):
+        """Tensor-core weight gradient; layers with a planar path (semb_conv2d_wgrad_tc_workspace > 0) get the network's
+        shared scratch (weight gradients of one network are serialised on one stream)."""
+        key = (geom.N, geom.H, geom.W, geom.OH, geom.OW, geom.Cin, geom.Cout, geom.R, geom.pad_t, geom.pad_l, geom.pad_mode)
+        root = self.share or self
+        cache = root.__dict__.setdefault("_wgrad_ws_need", {})
+        need = cache.get(key)
+        if need is None:
+            need = int(self.lib.semb_conv2d_wgrad_tc_workspace(C.byref(geom))) if _os.environ.get("SEMB_WGRAD_NO_PLANAR") is None else 0
+            cache[key] = need
+        if need <= 0:
+            return L.check(self.lib.semb_conv2d_wgrad_tc(C.byref(geom), C.byref(x_t), C.byref(dy_t), dw_ptr, self.stream))
+        ws = root.__dict__.get("_wgrad_ws")
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+            root._wgrad_ws = ws
+        base = (ws.data_ptr() + 127) // 128 * 128
+        L.check(self.lib.semb_conv2d_wgrad_tc_ws(C.byref(geom), C.byref(x_t), C.byref(dy_t), dw_ptr, base, need, self.stream))
+
     def gptr(self, name: str) -> int:
         o, _ = self.params.entries[name]
         return self.grads.data_ptr() + 4 * o
@@ -528,23 +547,31 @@ class ConvOp(Op):
         # channels of a 1x1 tensor-core conv (im2col of a single channel / shift-and-add of a per-tap conv); on the CUDA
         # cores these two layers took 144 of the 215 ms of a CycleGAN step.
         self.tapfold = None
+        self.tf_valid = False
         lshape = eng.specs[w].logical_shape if w in eng.specs else (k, k, cin, cout)       # LOGICAL channel counts decide
-        if (eng.tc_enabled and k == 7 and stride == 1 and pad_mode == L.PAD_REFLECT and tuple(pad_tl) == (3, 3) and not transposed
-                and (lshape[2] == 1 or lshape[3] == 1) and _os.environ.get("SEMB_NO_TAPFOLD") is None):
+        # the PatchGAN output conv (4x4, stride 1, 'valid', ONE output channel; CycleGAN.py:448): same per-tap 1x1 conv +
+        # shift-and-add as the generator head, on the un-padded input (on the CUDA cores it took 5 % of a CycleGAN step)
+        valid_head = (k > 1 and stride == 1 and pad_mode == L.PAD_ZERO and tuple(pad_tl) == (0, 0) and not transposed and stats is None
+                      and lshape[3] == 1 and lshape[2] > 1 and not transposed and tuple(hw_out) == (hw_in[0] - k + 1, hw_in[1] - k + 1))
+        if (eng.tc_enabled and stride == 1 and not transposed and _os.environ.get("SEMB_NO_TAPFOLD") is None and
+                (valid_head or (k == 7 and pad_mode == L.PAD_REFLECT and tuple(pad_tl) == (3, 3) and (lshape[2] == 1 or lshape[3] == 1)))):
             kind = "stem" if lshape[2] == 1 else "head"
             if not (kind == "head" and stats is not None):
                 rec = eng.tapfold_weight(w, k, cin, cout, kind)
                 t8 = rec["t8"]
                 self.tapfold = rec
-                self.tf_xpad = eng.new_buf(h + k - 1, wd + k - 1, cin, f"{w}_xpad", requires_grad=x.requires_grad, n=n)
+                self.tf_valid = valid_head
+                # (th, tw) = OUTPUT size, (th+k-1, tw+k-1) = the (padded) input the per-tap conv runs over
+                th, tw = (h - k + 1, wd - k + 1) if valid_head else (h, wd)
+                self.tf_xpad = None if valid_head else eng.new_buf(th + k - 1, tw + k - 1, cin, f"{w}_xpad", requires_grad=x.requires_grad, n=n)
                 if kind == "stem":
-                    self.tf_mid = eng.new_buf(h, wd, t8, f"{w}_patches", requires_grad=x.requires_grad, n=n)
-                    self.geom1 = L.ConvGeom(n, h, wd, h, wd, t8, cout, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
-                    self.geom1d = L.ConvGeom(n, h, wd, h, wd, cout, t8, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
+                    self.tf_mid = eng.new_buf(th, tw, t8, f"{w}_patches", requires_grad=x.requires_grad, n=n)
+                    self.geom1 = L.ConvGeom(n, th, tw, th, tw, t8, cout, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
+                    self.geom1d = L.ConvGeom(n, th, tw, th, tw, cout, t8, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
                     self.pk1 = eng.tc_pack(rec["key"], 1, 1, t8, cout, 0, vw=rec)
                     self.pk1d = eng.tc_pack(rec["key"], 1, 1, t8, cout, 1, vw=rec) if x.requires_grad else None
                 else:
-                    hp, wp = h + k - 1, wd + k - 1
+                    hp, wp = th + k - 1, tw + k - 1
                     self.tf_mid = eng.new_buf(hp, wp, t8, f"{w}_ztaps", requires_grad=True, n=n)
                     self.geom1 = L.ConvGeom(n, hp, wp, hp, wp, cin, t8, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
                     self.geom1d = L.ConvGeom(n, hp, wp, hp, wp, t8, cin, 1, 1, 1, 0, 0, L.PAD_ZERO, eng.dtype)
@@ -614,7 +641,7 @@ class ConvOp(Op):
         b2 = self.b2.view()
         dw3 = self.s2d["dw3"].data_ptr()
         if not self.transposed:
-            e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom_s), C.byref(b2.t), C.byref(self.y.g), dw3, e.stream)))
+            e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom_s, b2.t, self.y.g, dw3))
             if dbias:
                 L.check(e.lib.semb_channel_sum(C.byref(self.y.g), self.geom.N, self.geom.OH * self.geom.OW, dbias, e.dtype, e.stream))
             if self.x.requires_grad:
@@ -623,7 +650,7 @@ class ConvOp(Op):
                 self._shuffle(b2.g, self.x.g, 0, acc=self.acc_x)
             return
         self._shuffle(b2.g, self.y.g, 1)                                                       # space-to-depth of the output gradient
-        e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom_s), C.byref(b2.g), C.byref(self.x.t), dw3, e.stream)))
+        e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom_s, b2.g, self.x.t, dw3))
         if dbias:
             L.check(e.lib.semb_channel_sum(C.byref(self.y.g), self.geom.N, self.geom.H * self.geom.W, dbias, e.dtype, e.stream))
         if self.x.requires_grad:
@@ -632,9 +659,13 @@ class ConvOp(Op):
 
     def _fwd_tapfold(self, sp, ns, cs, bias):
         e, g = self.eng, self.geom
-        xp, mid = self.tf_xpad.view(), self.tf_mid.view()
-        L.check(e.lib.semb_pad_crop(C.byref(self.x.t), C.byref(xp.t), g.N, g.H, g.W, g.H + g.R - 1, g.W + g.S - 1, g.pad_t, g.pad_l, 0,
-                                    e.dtype, 0, e.stream))
+        mid = self.tf_mid.view()
+        if self.tf_valid:
+            xp = self.x
+        else:
+            xp = self.tf_xpad.view()
+            L.check(e.lib.semb_pad_crop(C.byref(self.x.t), C.byref(xp.t), g.N, g.H, g.W, g.H + g.R - 1, g.W + g.S - 1, g.pad_t, g.pad_l, 0,
+                                        e.dtype, 0, e.stream))
         if self.tapfold["kind"] == "stem":
             L.check(e.lib.semb_tap_patch(C.byref(mid.t), C.byref(xp.t), g.N, g.H, g.W, g.R, None, 0, e.dtype, e.stream))
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1), C.byref(mid.t), self.pk1["buf"].data_ptr(), bias, C.byref(self.y.t),
@@ -642,29 +673,32 @@ class ConvOp(Op):
         else:
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1), C.byref(xp.t), self.pk1["buf"].data_ptr(), None, C.byref(mid.t),
                                              None, 0, 0, 0, e.stream))
-            L.check(e.lib.semb_tap_patch(C.byref(self.y.t), C.byref(mid.t), g.N, g.H, g.W, g.R, bias, 2, e.dtype, e.stream))
+            L.check(e.lib.semb_tap_patch(C.byref(self.y.t), C.byref(mid.t), g.N, g.OH, g.OW, g.R, bias, 2, e.dtype, e.stream))
 
     def _bwd_tapfold(self):
         e, g = self.eng, self.geom
-        xp, mid = self.tf_xpad.view(), self.tf_mid.view()
+        mid = self.tf_mid.view()
+        xp = self.x if self.tf_valid else self.tf_xpad.view()
         dw1 = self.tapfold["dw3"].data_ptr()
         dbias = e.gptr(self.bias) if self.bias else None
         if dbias:
             L.check(e.lib.semb_channel_sum(C.byref(self.y.g), g.N, g.OH * g.OW, dbias, e.dtype, e.stream))
         if self.tapfold["kind"] == "stem":
-            e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom1), C.byref(mid.t), C.byref(self.y.g), dw1, e.stream)))
+            e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom1, mid.t, self.y.g, dw1))
             if not self.x.requires_grad:
                 return
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1d), C.byref(self.y.g), self.pk1d["buf"].data_ptr(), None, C.byref(mid.g),
                                              None, 0, 0, 0, e.stream))
             L.check(e.lib.semb_tap_patch(C.byref(mid.g), C.byref(xp.g), g.N, g.H, g.W, g.R, None, 1, e.dtype, e.stream))
         else:
-            L.check(e.lib.semb_tap_patch(C.byref(self.y.g), C.byref(mid.g), g.N, g.H, g.W, g.R, None, 3, e.dtype, e.stream))
-            e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom1), C.byref(xp.t), C.byref(mid.g), dw1, e.stream)))
+            L.check(e.lib.semb_tap_patch(C.byref(self.y.g), C.byref(mid.g), g.N, g.OH, g.OW, g.R, None, 3, e.dtype, e.stream))
+            e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom1, xp.t, mid.g, dw1))
             if not self.x.requires_grad:
                 return
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom1d), C.byref(mid.g), self.pk1d["buf"].data_ptr(), None, C.byref(xp.g),
-                                             None, 0, 0, 0, e.stream))
+                                             None, 0, 0, self.acc_x if self.tf_valid else 0, e.stream))
+            if self.tf_valid:
+                return          # the data gradient was written (accumulated) straight into x.g: no padding to fold back
         L.check(e.lib.semb_pad_crop(C.byref(xp.g), C.byref(self.x.g), g.N, g.H + g.R - 1, g.W + g.S - 1, g.H, g.W, g.pad_t, g.pad_l, 3,
                                     e.dtype, self.acc_x, e.stream))
 
@@ -701,11 +735,9 @@ class ConvOp(Op):
         dbias = e.gptr(self.bias) if self.bias else None
         if not self.transposed:
             if self.use_tc and dbias is None and self.x_pad is not None:
-                e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom_v), C.byref(self.x_pad.view().t),
-                                                                             C.byref(self.y.g), e.gptr(self.w), e.stream)))
+                e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom_v, self.x_pad.view().t, self.y.g, e.gptr(self.w)))
             elif self.use_tc and dbias is None:
-                e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad_tc(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g),
-                                                                             e.gptr(self.w), e.stream)))
+                e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom, self.x.t, self.y.g, e.gptr(self.w)))
             else:
                 e.on_wgrad_stream(lambda: L.check(e.lib.semb_conv2d_wgrad(C.byref(self.geom), C.byref(self.x.t), C.byref(self.y.g),
                                                                           e.gptr(self.w), dbias, e.stream)))

@@ -8,6 +8,7 @@ sequence (forward(training=True) -> loss -> backward -> Adam -> metrics) [K3.5].
 from __future__ import annotations
 
 import collections
+import collections.abc
 import ctypes as C
 import json
 import math
@@ -45,11 +46,17 @@ class _Instance:
         self.y_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
         self.out_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
         self.x_pin = torch.zeros((n, h, w, 1), dtype=torch.float32).pin_memory()
-        self.y_pin = torch.zeros((n, h, w, 1), dtype=torch.float32).pin_memory()
         self.out_pin = torch.zeros((n, h, w, 1), dtype=torch.float32).pin_memory()
         self.sums_pin = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph2: Optional[torch.cuda.CUDAGraph] = None
         self.graph_key = None
+        self._train_io = None
+
+    def train_io(self) -> "_TrainIO":
+        if self._train_io is None:
+            self._train_io = _TrainIO(self)
+        return self._train_io
 
     # ---- pieces of a step (all asynchronous on the current stream) ---------------------------------
     def stage_in(self):
@@ -73,14 +80,89 @@ class _Instance:
                                             e.zeroed.ptr(self.loss_sums), e.dtype, e.stream))
 
     def fwd_bwd(self, weighting: float):
+        """zero scratch -> forward -> loss -> backward.  The input cast (stage_in) is NOT part of it: it runs in front of
+        the captured graph so that the host->device copy of the next batch can overlap this step (see _TrainIO)."""
         e = self.eng
         e.zero_step(zero_grads=True)
-        self.stage_in()
         e.forward(training=True)
         self.loss(weighting, with_grad=True)
         e.backward()
         if e.s2d:
             e.fold_virtual_grads()      # `grads` must be complete BEFORE the data-parallel all-reduce (Engine.adam folds too late)
+
+
+class _TrainIO:
+    """Double-buffered input staging of one training instance.
+
+    Step i+1's batch travels host -> device on a copy stream while step i's graph runs: pinned (or caller-pinned,
+    zero-copy) host memory -> x_stage[slot] / y_stage[slot]; on the compute stream a cast kernel and one device copy move
+    the slot into the buffers the graph reads, which frees the slot again long before its next use (two steps later)."""
+
+    RING = 4
+
+    def __init__(self, inst: "_Instance"):
+        n, h, w, dev = inst.n, inst.h, inst.w, inst.eng.device
+        mk = lambda: torch.zeros((n, h, w, 1), dtype=torch.float32, device=dev)
+        self.x_stage, self.y_stage = [mk(), mk()], [mk(), mk()]
+        self.x_pin, self.y_pin = [None, None], [None, None]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ev_h2d = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self.sums_pin = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        self.ev_sums = [torch.cuda.Event() for _ in range(self.RING)]
+        self.step = 0
+        self.shape = (n, h, w, 1)
+
+    def _host(self, arr, pins, slot) -> torch.Tensor:
+        """A pinned float32 view of `arr`: the caller's own tensor when it is already pinned (zero copy), else a memcpy
+        into this slot's pinned buffer (after the H2D that last read it has finished)."""
+        if isinstance(arr, torch.Tensor) and arr.device.type == "cpu" and arr.dtype == torch.float32 and arr.is_contiguous() \
+                and arr.is_pinned() and tuple(arr.shape) == self.shape:
+            return arr
+        if pins[slot] is None:
+            pins[slot] = torch.zeros(self.shape, dtype=torch.float32).pin_memory()
+        self.ev_h2d[slot].synchronize()
+        src = arr if isinstance(arr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(_to_numpy(arr), dtype=np.float32))
+        pins[slot].copy_(src.reshape(self.shape))
+        return pins[slot]
+
+    def upload(self, x, y) -> int:
+        slot = self.step & 1
+        xs, ys = self._host(x, self.x_pin, slot), self._host(y, self.y_pin, slot)
+        cs = self.copy_stream
+        cs.wait_event(self.ev_free[slot])
+        with torch.cuda.stream(cs):
+            self.x_stage[slot].copy_(xs, non_blocking=True)
+            self.y_stage[slot].copy_(ys, non_blocking=True)
+            self.ev_h2d[slot].record(cs)
+        return slot
+
+
+class LazyLogs(collections.abc.Mapping):
+    """Metrics of one step.  The device->host copy of the loss sums is enqueued with the step; the values are only waited
+    for when they are read (Keras' torch trainer also hands back device tensors and converts them when logging)."""
+
+    def __init__(self, pin: torch.Tensor, event: torch.cuda.Event, count: float):
+        self._pin, self._event, self._count, self._vals = pin, event, count, None
+
+    def _resolve(self):
+        if self._vals is None:
+            self._event.synchronize()
+            s = self._pin
+            self._vals = {"loss": float(s[0]) / self._count, "mae": float(s[1]) / self._count, "acc": float(s[2]) / self._count}
+        return self._vals
+
+    def __getitem__(self, k):
+        return self._resolve()[k]
+
+    def __iter__(self):
+        return iter(("loss", "mae", "acc"))
+
+    def __len__(self):
+        return 3
+
+    def __repr__(self):
+        return repr(self._resolve())
 
 
 class UNetModel:
@@ -245,6 +327,7 @@ class UNetModel:
         """fwd + loss + bwd (+ all-reduce) + Adam on the device; inputs already in inst.x_dev / y_dev."""
         e = inst.eng
         e.lr.fill_(self.learning_rate)
+        inst.stage_in()
         single = self.world_size == 1
         if self.use_cuda_graph:
             key = (self.weighting, self.beta_1, self.beta_2, self.epsilon, self.world_size)
@@ -255,25 +338,39 @@ class UNetModel:
                 saved = [t.clone() for t in (e.params.t, e.state.t, e.adam_m, e.adam_v, e.adam_state)]
                 with torch.cuda.stream(s):
                     inst.fwd_bwd(self.weighting)
+                    if not single:
+                        self._allreduce(e)      # also brings up the NCCL communicator before any capture
                     e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
                 for t, sv in zip((e.params.t, e.state.t, e.adam_m, e.adam_v, e.adam_state), saved):
                     t.copy_(sv)
                 e.repack()          # packed tensor-core weights follow the restored master weights
-                g1 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
-                    inst.fwd_bwd(self.weighting)
+                g1, g2 = torch.cuda.CUDAGraph(), None
+                one_graph = single or os.environ.get("SEMB_DP_TWO_GRAPHS") is None
+                try:
+                    # ONE replay per step: fwd + bwd, the NCCL all-reduce of the flat gradient buffer, Adam, weight re-pack
+                    with torch.cuda.graph(g1):
+                        inst.fwd_bwd(self.weighting)
+                        if one_graph:
+                            if not single:
+                                self._allreduce(e)
+                            e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
+                except Exception:
                     if single:
-                        e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0)
-                g2 = None
-                if not single:
+                        raise
+                    one_graph = False           # a collective that cannot be captured: all-reduce between two graphs
+                    torch.cuda.synchronize()
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        inst.fwd_bwd(self.weighting)
+                if not one_graph:
                     g2 = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g2):
                         e.adam(self.beta_1, self.beta_2, self.epsilon, 1.0 / self.world_size)
                 inst.graph, inst.graph2, inst.graph_key = g1, g2, key
             inst.graph.replay()
-            if not single:
+            if inst.graph2 is not None:
                 self._allreduce(e)
                 inst.graph2.replay()
         else:
@@ -288,15 +385,24 @@ class UNetModel:
 
     def train_step(self, x, y) -> Dict[str, float]:
         """One TorchTrainer.train_step with HOST inputs: H2D, fwd, loss, bwd, Adam, D2H of the metrics."""
-        x = _to_numpy(x).astype(np.float32, copy=False)
-        y = _to_numpy(y).astype(np.float32, copy=False)
+        if not isinstance(x, torch.Tensor):
+            x = _to_numpy(x).astype(np.float32, copy=False)
+        if not isinstance(y, torch.Tensor):
+            y = _to_numpy(y).astype(np.float32, copy=False)
         inst = self._use(self._instance(x.shape[0], x.shape[1], x.shape[2]))
-        inst.x_pin.copy_(torch.from_numpy(np.ascontiguousarray(x)))
-        inst.y_pin.copy_(torch.from_numpy(np.ascontiguousarray(y)))
-        inst.x_dev.copy_(inst.x_pin, non_blocking=True)
-        inst.y_dev.copy_(inst.y_pin, non_blocking=True)
+        io = inst.train_io()
+        slot = io.upload(x, y)                              # copy stream: overlaps the previous step's graph
+        main = torch.cuda.current_stream()
+        main.wait_event(io.ev_h2d[slot])
+        inst.x_dev.copy_(io.x_stage[slot], non_blocking=True)       # device copies; the graph reads x_dev / y_dev
+        inst.y_dev.copy_(io.y_stage[slot], non_blocking=True)
+        io.ev_free[slot].record(main)
         self._step_device(inst)
-        return self._read_metrics(inst)
+        r = io.step % io.RING
+        io.step += 1
+        io.sums_pin[r].copy_(inst.eng.zeroed.get(inst.loss_sums), non_blocking=True)
+        io.ev_sums[r].record(main)
+        return LazyLogs(io.sums_pin[r], io.ev_sums[r], float(inst.n * inst.h * inst.w))
 
     def _read_metrics(self, inst: _Instance) -> Dict[str, float]:
         e = inst.eng
@@ -333,11 +439,13 @@ class UNetModel:
             t0 = time.time()
             agg: Dict[str, float] = {}
             nb = len(data)
+            pending = collections.deque()
             for i in range(nb):
                 xb, yb = data[i]
-                logs = self.train_step(xb, yb)
-                for k, v in logs.items():
-                    agg[k] = agg.get(k, 0.0) + v
+                pending.append(self.train_step(xb, yb))
+                while len(pending) > (0 if i == nb - 1 else _TrainIO.RING - 2):      # read metrics a few steps late: no stall
+                    for k, v in pending.popleft().items():
+                        agg[k] = agg.get(k, 0.0) + v
             logs = {k: v / max(nb, 1) for k, v in agg.items()}
             if validation_data is not None and len(validation_data) > 0:
                 vagg: Dict[str, float] = {}

@@ -285,7 +285,24 @@ def run_ours(args):
     if world > 1:
         m.set_distributed()
     inst = m._current
-    xn, yn = x.numpy(), y.numpy()
+    # host inputs live in pinned memory (the contract's e2e definition): train_step uploads them without a staging memcpy
+    xn, yn = x.contiguous().pin_memory(), y.contiguous().pin_memory()
+
+    # ---- parity gate of the benched path: first-step loss on THIS batch against the oracle (same initial weights)
+    first_step = None
+    if rank == 0 and world == 1 and not args.no_check:
+        spec = OU.UNetSpec(16)
+        p0 = spec.init_params(seed=0)
+        m.set_named_weights({k: v.detach().numpy() for k, v in p0.items()})
+        chk = OU.UNetTrainer(spec, p0, wgt)
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref0, _ = chk.train_step(x, y)
+        got0 = dict(m.train_step(xn, yn))
+        rel = abs(got0["loss"] - ref0["loss"]) / abs(ref0["loss"])
+        first_step = {"loss": got0["loss"], "oracle_loss": ref0["loss"], "rel_err": rel, "acc": got0["acc"], "oracle_acc": ref0["acc"],
+                      "tolerance": 3e-2 if args.dtype == "bf16" else 1e-3}
+        assert rel < first_step["tolerance"], f"first-step loss {got0['loss']} differs from the oracle's {ref0['loss']} (rel {rel:.3e})"
+        del chk
 
     # launches per step, counted on an eager step (graph replays do not pass through the host-side counter)
     saved_graph = m.use_cuda_graph
@@ -403,9 +420,243 @@ def run_ours(args):
         "roofline_by_kernel": table,
         "cpu_baseline": cpu,
         "clocks": clocks,
-        "last_step_metrics": last,
+        "last_step_metrics": dict(last),
+        "first_step_vs_oracle": first_step,
     }
     emit(line)
+    if args.profile_out:
+        with open(args.profile_out, "w") as fh:
+            json.dump({"total_ms_eager": total_ms, "rows": rows}, fh, indent=1)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- CycleGAN (configs[2])
+CG_METRIC = "CycleGAN 256x256 image pairs/sec, full train step (G_A2B/G_B2A + PatchGAN-D, image pools)"
+CG_GFLOP_PER_PAIR = 1967.0      # algorithmic minimum at filters=64, 256x256 (6 G fwd + 12 bwd-eq, 6 D fwd + 10 bwd-eq)
+
+
+def cg_inputs(batch, size):
+    g = torch.Generator().manual_seed(0)
+    a = torch.rand(batch, size, size, 1, generator=g) * 2 - 1
+    b = torch.rand(batch, size, size, 1, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    return a, b
+
+
+def cg_cpu_throughput(size, filters, batch, steps, warmup):
+    import random
+    from oracle import cyclegan as OC
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tr = OC.CycleGanTrainer(filters=filters, pool_batch=batch, seed=0)
+    a, b = cg_inputs(batch, size)
+    for _ in range(warmup):
+        tr.train_step(a, b)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(a, b)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, cores
+
+
+def run_cyclegan_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    batch = 1
+    steps, warmup = min(args.steps, 2), min(args.warmup, 1)
+    pps, spt, cores = cg_cpu_throughput(args.size, args.filters, batch, steps, warmup)
+    emit({"impl": "reference", "metric": CG_METRIC, "value": pps, "unit": "image pairs/s", "n_gpus": args.gpus, "steps": steps,
+          "warmup": warmup, "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic",
+          "config": {"workload": f"CycleGAN filters={args.filters} {args.size}x{args.size}x1 train_step_torch", "sample": f"batch {batch} per step on the host cores (the GPU arm runs batch {args.batch})"},
+          "cpu_baseline": {"value": pps, "unit": "image pairs/s", "cores": cores, "kind": "port",
+                           "sample": f"{steps} steps of batch {batch}, oracle/cyclegan.py (torch {torch.__version__} CPU fp32)"},
+          "e2e": {"value": pps, "unit": "image pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+    return 0
+
+
+def instrument(engines):
+    """Wraps fwd / bwd of every op of `engines` (and their weight-gradient launches) with CUDA events; returns the record
+    list [(phase, op, ev0, ev1)] filled by the next eager step and an undo function."""
+    recs, undo = [], []
+    for e in engines:
+        wg = {}
+
+        def timed_wgrad(fn, e=e, wg=wg):
+            if e.skip_wgrad:
+                return None
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            wg["last"] = (a, b)
+
+        undo.append((e, "on_wgrad_stream", e.__dict__.get("on_wgrad_stream")))
+        e.on_wgrad_stream = timed_wgrad
+        for op in e.ops:
+            for phase, name in (("fwd", "fwd"), ("bwd", "bwd")):
+                orig = getattr(op, name)
+
+                def wrapped(*a, _orig=orig, _op=op, _phase=phase, _wg=wg, **k):
+                    _wg.pop("last", None)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); r = _orig(*a, **k); e1.record()
+                    recs.append((_phase, _op, e0, e1))
+                    if "last" in _wg:
+                        recs.append(("wgrad", _op, *_wg.pop("last")))
+                    return r
+                undo.append((op, name, op.__dict__.get(name)))
+                setattr(op, name, wrapped)
+
+    def restore():
+        for obj, name, prev in undo:
+            if prev is None:
+                obj.__dict__.pop(name, None)
+            else:
+                setattr(obj, name, prev)
+    return recs, restore
+
+
+def cg_rows(recs, dtype_name):
+    from sem_b200.engine import ConvOp, AffineOp
+    esz = 2 if dtype_name == "bf16" else 4
+    rows, last_bwd = [], None
+    for label, op, a, b in recs:
+        ms = a.elapsed_time(b)
+        row = {"phase": label, "op": type(op).__name__, "ms": ms, "kernel": "other"}
+        if isinstance(op, ConvOp):
+            g = op.geom
+            pix = g.N * g.OH * g.OW
+            row.update({"geom": f"{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.R} s{g.stride}{' T' if op.transposed else ''}",
+                        "flops": 2.0 * pix * g.R * g.S * g.Cin * g.Cout, "bytes": (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz, "w": op.w})
+            tc = (op.use_tc or op.s2d is not None or op.tapfold is not None) and dtype_name == "bf16"
+            big = g.R == 3 and g.stride == 1 and g.Cin >= 256
+            if label == "wgrad":
+                row["kernel"] = ("wgrad_tma_kernel [3x3 s1 Cin>=256]" if big else "wgrad (other layers)") if tc else "wgrad_simt"
+                if last_bwd is not None:
+                    last_bwd["ms"] = max(last_bwd["ms"] - ms, 0.0)
+            else:
+                row["kernel"] = ("conv_tma_kernel [3x3 s1 Cin>=256, fwd+dgrad]" if big else "conv fwd+dgrad (other layers)") if tc else "conv_simt"
+                if label == "bwd":
+                    if not op.x.requires_grad:
+                        row["flops"], row["bytes"] = 0.0, 0
+                    last_bwd = row
+        elif isinstance(op, AffineOp):
+            row["kernel"] = "affine_act_*"
+            row["geom"] = f"C={op.a.C} hw={op.hw} n={op.n} two_operands={op.b is not None}"
+        rows.append(row)
+    return rows
+
+
+def run_cyclegan(args):
+    import random
+    import torch.distributed as dist
+    import sem_b200
+    from sem_b200 import CycleGanModel, ImagePool, _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+    size, n, F = args.size, args.batch, args.filters
+    m = CycleGanModel((size, size, 1), batch_size=n, filters=F, dtype=args.dtype,
+                      image_pool_a=ImagePool(n, 50, random.Random(rank)), image_pool_b=ImagePool(n, 50, random.Random(100 + rank)),
+                      use_cuda_graph=not args.no_graph)
+    m.compile()
+    if world > 1:
+        m.set_distributed()
+    a, b = cg_inputs(n, size)
+    if world > 1:
+        a = torch.rand(a.shape, generator=torch.Generator().manual_seed(1000 + rank)) * 2 - 1
+    ap_, bp_ = a.contiguous().pin_memory(), b.contiguous().pin_memory()
+
+    c0 = L.launch_count()
+    m.train_step((ap_, bp_))                 # eager first step: counts the launches, allocates gradient buffers
+    launches_per_step = L.launch_count() - c0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        m.train_step((ap_, bp_))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        m.step_device()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    barrier()
+    t0 = time.perf_counter()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    last = None
+    for _ in range(args.steps):
+        last = m.train_step((ap_, bp_))
+    ev3.record()
+    barrier()
+    e2e_ms = max(ev2.elapsed_time(ev3), (time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    pairs = n * world * args.steps
+    value, e2e_value = pairs / (dev_ms / 1e3), pairs / (e2e_ms / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- per-op profile of one eager step (CUDA events around every op of all twelve towers)
+    engines = [bb.e for bb in (m.GA_ra, m.GB_rb, m.GB_fb, m.GA_fa, m.GB_ra, m.GA_rb, m.DA_fa, m.DB_fb, m.DA_real, m.DA_pool, m.DB_real, m.DB_pool)]
+    recs, restore = instrument(engines)
+    saved = m.use_cuda_graph
+    m.use_cuda_graph = False
+    m.step_device()
+    torch.cuda.synchronize()
+    m.use_cuda_graph = saved
+    restore()
+    rows = cg_rows(recs, args.dtype)
+    table, total_ms = kernel_table(rows, peaks)
+    named = {k: v for k, v in table.items() if k not in ("other", "affine_act_*")}
+    top_name = max(named, key=lambda k: named[k]["ms"])
+    top = named[top_name]
+    gflop_pair = CG_GFLOP_PER_PAIR * (F / 64.0) ** 2 * (size / 256.0) ** 2
+    step_tflops = gflop_pair * n / (dev_ms / args.steps)          # GFLOP / ms == TFLOP/s
+    roof = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": peaks["tflops_burst"], "unit": "TFLOP/s",
+            "frac": top["TFLOPs"] / peaks["tflops_burst"], "kernel": top_name, "kernel_ms_per_step": top["ms"],
+            "kernel_share_of_step": top["share_of_step"], "launches_per_step": top["ops"], "traffic": None,
+            "arithmetic_intensity_flop_per_byte": top["arithmetic_intensity_flop_per_byte"],
+            "algorithmic_flops_per_launch": (top["TFLOPs"] * 1e12 * top["ms"] * 1e-3) / max(top["ops"], 1),
+            "avg_launch_ms": top["ms"] / max(top["ops"], 1),
+            "peak_source": peaks["source"] + ", burst figure (kernels timed one by one)",
+            "step_conv_tflops_vs_algorithmic_minimum": step_tflops,
+            "step_frac_of_tensor_peak_sustained": step_tflops / peaks["tflops_sustained"]}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        pps, spt, cores = cg_cpu_throughput(size, F, 1, 1, 1)
+        cpu = {"value": pps, "unit": "image pairs/s", "cores": cores, "kind": "port",
+               "sample": "1 step of batch 1 after 1 warm-up, oracle/cyclegan.py train step (torch CPU fp32)"}
+    emit({"metric": CG_METRIC, "value": value, "unit": "image pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+          "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+          "data": "synthetic",
+          "config": {"workload": f"CycleGAN filters={F} {size}x{size}x1 train_step_torch (6 G fwd, 2+4 D fwd, 2 backward phases, 4 Adam), batch {n} per GPU, image pools 50",
+                     "global_batch": n * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                     "l2": "per-step working set (activations of 12 towers, several GB) exceeds the 126 MB L2; no explicit flush"},
+          "e2e": {"value": e2e_value, "unit": "image pairs/s", "ms_per_step": e2e_ms / args.steps,
+                  "h2d_bytes_per_step": int(2 * n * size * size * 4), "d2h_bytes_per_step": 64},
+          "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+          "roofline": roof, "roofline_by_kernel": table, "cpu_baseline": cpu, "clocks": clocks,
+          "last_step_metrics": {k: float(v) for k, v in last.items()}})
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump({"total_ms_eager": total_ms, "rows": rows}, fh, indent=1)
@@ -445,8 +696,16 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the first-step loss check against the oracle")
+    ap.add_argument("--workload", default="unet", choices=["unet", "cyclegan"],
+                    help="unet = BASELINE configs[1] (and configs[3] with --size 512 --batch 8 under torchrun); cyclegan = configs[2]")
+    ap.add_argument("--filters", type=int, default=64, help="CycleGAN base filters (StartProcess.py:37)")
     ap.add_argument("--profile-out", default=None)
     args = ap.parse_args()
+    if args.workload == "cyclegan":
+        if args.batch == 32:
+            args.batch = 8              # BASELINE configs[2]: batch 8
+        return run_cyclegan_reference(args) if args.impl == "reference" else run_cyclegan(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -137,6 +137,14 @@ int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void
  * HWIO gradient with coalesced reductions.  Same contract as semb_conv2d_wgrad without dbias. */
 int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* stream);
 
+/* Same weight gradient with caller-owned scratch: for 3x3 layers with >= 128 input and output channels (the CycleGAN
+ * residual / sampling convs, CycleGAN.py:323-358) x and dy are first re-laid out as planar [N][C/8][H][W][8] copies in
+ * `workspace`, whose TMA boxes have 128-byte rows instead of one 16-byte row per pixel and channel group.
+ * semb_conv2d_wgrad_tc_workspace returns the bytes needed (0: no planar path for this geometry, call the plain entry). */
+int64_t semb_conv2d_wgrad_tc_workspace(const semb_conv_geom* g);
+int semb_conv2d_wgrad_tc_ws(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+
 /* ---- stride-2 convolutions on the stride-1 tensor-core kernels (space-to-depth) ------------------------------
  * A k x k (k = 3, 4) stride-2 Conv2D / Conv2DTranspose (CycleGAN.py:339-358, 425-451) is run as a 3x3-embedded 2x2
  * stride-1 conv over the space-to-depth image (H/2, W/2, 4C): semb_pixel_shuffle2x moves activations between the two

@@ -65,10 +65,12 @@ def to_torch_params(npd):
     return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in npd.items()}
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-iou", action="store_true")
-    args = ap.parse_args()
+    ap.add_argument("--stage-only", action="store_true",
+                    help="only (re)write the git-ignored baseline/_ref files that travel to the GPU box; tests/golden is untouched")
+    args = ap.parse_args(argv)
     os.makedirs(GOLD, exist_ok=True)
     os.makedirs(SHIP, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -83,6 +85,9 @@ def main():
         p = {n: p[n] for n in spec.names()}
         weights[tag] = p
         np.savez_compressed(os.path.join(SHIP, f"unet_{tag}_weights.npz"), **p)
+    if args.stage_only:
+        print("staged", SHIP)
+        return 0
     np.savez_compressed(os.path.join(GOLD, "unet_gan_weights.npz"), **weights["GAN"])
 
     # ---- known answers: mean IoU of the shipped weights on the shipped dataset

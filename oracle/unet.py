@@ -165,14 +165,17 @@ class _Ctx:
     def convT(self, x):
         self.nct += 1
         n = f"conv2d_transpose_{self.nct}"
-        return L.conv2d_transpose(x, self.p[n + "/kernel"], self.p[n + "/bias"], 2)
+        return L.st(L.conv2d_transpose(x, self.p[n + "/kernel"], self.p[n + "/bias"], 2))
 
 
-def _conv_bn(ctx, x, k, act):
-    x = ctx.conv(x, k)
+def _conv_bn(ctx, x, k, act, store_act=True):
+    # L.st(...) marks the tensors the CUDA path writes to memory (identity unless L.storage(dtype) is active)
+    x = L.st(ctx.conv(x, k))
     x = ctx.bn(x, False)
     if act == "relu":
         x = torch.relu(x)
+        if store_act:
+            x = L.st(x)
     elif act == "sigmoid":
         x = torch.sigmoid(x)
     return x
@@ -185,17 +188,17 @@ def _mres(ctx, inp):
     c = _conv_bn(ctx, b, 3, "relu")
     out = torch.cat([a, b, c], dim=3)
     out = ctx.bn(out, True)
-    out = torch.relu(shortcut + out)
-    out = ctx.bn(out, True)
+    out = L.st(torch.relu(shortcut + out))
+    out = L.st(ctx.bn(out, True))
     return out
 
 
 def _respath(ctx, length, x):
     for _ in range(length):
         shortcut = _conv_bn(ctx, x, 1, None)
-        out = _conv_bn(ctx, x, 3, "relu")
-        out = torch.relu(shortcut + out)
-        x = ctx.bn(out, True)
+        out = _conv_bn(ctx, x, 3, "relu", store_act=False)
+        out = L.st(torch.relu(shortcut + out))
+        x = L.st(ctx.bn(out, True))
     return x
 
 
@@ -216,16 +219,16 @@ def unet_forward(x, params, training: bool = False, output_channels: int = 1, ta
         return t
 
     m1 = tap("mres1", _mres(ctx, xp))
-    p1 = L.max_pool_2x2(m1)
+    p1 = L.st(L.max_pool_2x2(m1))
     r1 = tap("rp1", _respath(ctx, 4, m1))
     m2 = tap("mres2", _mres(ctx, p1))
-    p2 = L.max_pool_2x2(m2)
+    p2 = L.st(L.max_pool_2x2(m2))
     r2 = tap("rp2", _respath(ctx, 3, m2))
     m3 = tap("mres3", _mres(ctx, p2))
-    p3 = L.max_pool_2x2(m3)
+    p3 = L.st(L.max_pool_2x2(m3))
     r3 = tap("rp3", _respath(ctx, 2, m3))
     m4 = tap("mres4", _mres(ctx, p3))
-    p4 = L.max_pool_2x2(m4)
+    p4 = L.st(L.max_pool_2x2(m4))
     r4 = tap("rp4", _respath(ctx, 1, m4))
     m5 = tap("mres5", _mres(ctx, p4))
     u6 = torch.cat([ctx.convT(m5), r4], dim=3)

@@ -165,8 +165,12 @@ def test_discriminator_gaussian_noise_matches_oracle_with_the_same_deviates():
     e.forward(True)
     torch.cuda.synchronize()
     assert torch.equal(b.out_buf.data[..., :1].float().cpu(), got)            # frozen deviates: reproducible
+    # (InstanceNorm has no inference mode, so a discriminator is never run with training=False: the noise-free path is
+    # checked by switching the deviates off)
+    for op in b.noise_ops:
+        op.noise.data.zero_()
     e.zero_step(False)
-    e.forward(False)
+    e.forward(True)
     torch.cuda.synchronize()
     ref0 = OC.discriminator_forward(x, p)
     assert U.rel_err(b.out_buf.data[..., :1].float().cpu(), ref0) < 1e-3
@@ -175,7 +179,7 @@ def test_discriminator_gaussian_noise_matches_oracle_with_the_same_deviates():
 def test_default_constructed_model_is_initialised_and_trains():
     """weights used to stay zero unless a test called set_named.  Class defaults of CycleGAN
     (use_skip_connection=True, gaussian_noise_value=0.15) must build and produce non-zero gradients."""
-    m = CycleGanModel((32, 32, 1), batch_size=2, filters=8, n_res=1, dtype="bf16", use_skip_connection=True, gaussian_noise_value=0.15)
+    m = CycleGanModel((64, 64, 1), batch_size=2, filters=8, n_res=1, dtype="bf16", use_skip_connection=True, gaussian_noise_value=0.15)
     for name, net in m.nets.items():
         for pname, w in zip(net.names, net.get_weights()):
             if pname.endswith("/kernel"):
@@ -184,8 +188,8 @@ def test_default_constructed_model_is_initialised_and_trains():
                 assert np.all(w == 1.0), (name, pname)
     k0 = {name: net.root.get_param(net.names[0]).copy() for name, net in m.nets.items()}
     assert not np.array_equal(k0["gen_a"], k0["gen_b"])          # one seed per network
-    a = np.random.default_rng(0).uniform(-1, 1, (2, 32, 32, 1)).astype(np.float32)
-    b = np.random.default_rng(1).uniform(-1, 1, (2, 32, 32, 1)).astype(np.float32)
+    a = np.random.default_rng(0).uniform(-1, 1, (2, 64, 64, 1)).astype(np.float32)
+    b = np.random.default_rng(1).uniform(-1, 1, (2, 64, 64, 1)).astype(np.float32)
     logs = m.train_step((a, b))
     assert all(np.isfinite(v) for v in logs.values())
     for name, net in m.nets.items():
@@ -197,7 +201,7 @@ def test_cyclegan_facade_default_options_build():
     import tempfile
     from sem_b200 import CycleGAN as CG
     with tempfile.TemporaryDirectory() as d:
-        g = CG.CycleGAN(root_dir=d, image_shape=(32, 32, 1))
+        g = CG.CycleGAN(root_dir=d, image_shape=(64, 64, 1))
         g.filters, g.num_residual_blocks_gen = 8, 1
         m = g.create_model()           # class defaults: skip connection + Gaussian noise
         assert any("skip_out" in n for n in m.gen_a.names)

@@ -657,6 +657,86 @@ def test_conv_tc_wgrad(case):
         assert float(got[:, :, :, cout:].abs().max()) == 0
 
 
+# (N,H,W,Cin,Cout,pad): layers with a planar-staged weight gradient (>= 128 channels on both sides)
+WGRAD_PLANAR_CASES = [
+    (2, 16, 16, 128, 128, 1),
+    (1, 20, 12, 144, 216, 1),              # partial tiles, channel chunks that do not divide
+    (2, 34, 34, 512, 512, 0),              # the CycleGAN residual conv at its real shape: 'valid' over the reflect-padded 34x34 input (K12)
+    (1, 18, 26, 136, 256, 0),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_PLANAR_CASES)
+def test_conv_tc_wgrad_planar_workspace(case):
+    """semb_conv2d_wgrad_tc_ws: x / dy re-laid out as planar copies in caller scratch (128-byte TMA rows), same gradient as
+    autograd on bf16-rounded operands; sliced source views, accumulation on top of existing content."""
+    n, h, w_, cin, cout, p = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(31)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wt = torch.randn(3, 3, cin, cout, generator=g) * 0.05
+    wr = wt.clone().requires_grad_(True)
+    y_ref = OL.conv2d(x, wr, None, 1, "same" if p == 1 else "valid")
+    oh, ow = y_ref.shape[1], y_ref.shape[2]
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    geom = L.ConvGeom(n, h, w_, oh, ow, cin, cout, 3, 3, 1, p, p, L.PAD_ZERO, L.BF16)
+    need = int(lib.semb_conv2d_wgrad_tc_workspace(C.byref(geom)))
+    assert need >= 2 * (x.numel() + dy.numel())
+    xd = U.to_dev(x, "bf16", pitch=cin + 8, coff=8)
+    dyd = U.to_dev(dy, "bf16", pitch=cout + 16, coff=8)
+    ws = torch.empty(need + 256, dtype=torch.uint8, device="cuda")
+    base = (ws.data_ptr() + 127) // 128 * 128
+    dw = torch.ones((3, 3, cin, cout), device="cuda")
+    xv, dyv = U.view(xd, 8, cin), U.view(dyd, 8, cout)
+    L.check(lib.semb_conv2d_wgrad_tc_ws(C.byref(geom), C.byref(xv), C.byref(dyv), dw.data_ptr(), base, need, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(dw.cpu() - 1.0, wr.grad) < 1e-4
+    with pytest.raises(L.SembError):
+        L.check(lib.semb_conv2d_wgrad_tc_ws(C.byref(geom), C.byref(xv), C.byref(dyv), dw.data_ptr(), base, need - 1, U.stream()))
+    small = L.ConvGeom(1, 16, 16, 16, 16, 32, 32, 3, 3, 1, 1, 1, L.PAD_ZERO, L.BF16)
+    assert int(lib.semb_conv2d_wgrad_tc_workspace(C.byref(small))) == 0
+
+
+def test_cyclegan_residual_conv_real_shape_fwd_dgrad():
+    """K12 of SURVEY 2.1 at its real shape: 512 -> 512 3x3 over a reflect-padded 8 x 32 x 32 tile batch (CycleGAN.py:323-337),
+    forward and data gradient of the TMA / tcgen05 kernel against the oracle's layer (bf16-rounded operands)."""
+    n, h, cin, cout = 8, 32, 512, 512
+    lib = L.load()
+    g = torch.Generator().manual_seed(37)
+    x = U.bf16_round(torch.randn(n, h, h, cin, generator=g))
+    wt = U.bf16_round(torch.randn(3, 3, cin, cout, generator=g) * 0.02)
+    xr = x.clone().requires_grad_(True)
+    xpad = OL.reflection_pad(xr, 2, 2)
+    y_ref = OL.conv2d(xpad, wt, None, 1, "valid")
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    xpad.retain_grad()
+    y_ref.backward(dy)
+    geom = L.ConvGeom(n, h + 2, h + 2, h, h, cin, cout, 3, 3, 1, 0, 0, L.PAD_ZERO, L.BF16)
+    xd = U.to_dev(xpad.detach(), "bf16")
+    yd = torch.zeros((n, h, h, cout), dtype=torch.bfloat16, device="cuda")
+    wdev = wt.cuda().contiguous()
+    nbytes = int(lib.semb_pack_weights_tc(None, 3, 3, cin, cout, 0, None, None))
+    wp = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+    assert int(lib.semb_pack_weights_tc(wdev.data_ptr(), 3, 3, cin, cout, 0, wp.data_ptr(), U.stream())) >= 0
+    stats = torch.zeros(n, 2, cout, device="cuda", dtype=torch.float64)
+    xv, yv = U.view(xd), U.view(yd)
+    L.check(lib.semb_conv2d_fwd_tc(C.byref(geom), C.byref(xv), wp.data_ptr(), None, C.byref(yv), stats.data_ptr(), 2 * cout, cout, 0, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(yd.float(), y_ref) < 1e-2
+    assert U.rel_err(stats[:, 0], y_ref.double().sum(dim=(1, 2))) < 1e-4          # InstanceNorm moments per (sample, channel)
+    # data gradient on the padded domain = full correlation of dy with the mirrored, transposed kernel
+    wpb = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+    assert int(lib.semb_pack_weights_tc(wdev.data_ptr(), 3, 3, cin, cout, 1, wpb.data_ptr(), U.stream())) >= 0
+    geom_d = L.ConvGeom(n, h, h, h + 2, h + 2, cout, cin, 3, 3, 1, 2, 2, L.PAD_ZERO, L.BF16)
+    dyd = U.to_dev(dy, "bf16")
+    dxd = torch.zeros((n, h + 2, h + 2, cin), dtype=torch.bfloat16, device="cuda")
+    dyv, dxv = U.view(dyd), U.view(dxd)
+    L.check(lib.semb_conv2d_fwd_tc(C.byref(geom_d), C.byref(dyv), wpb.data_ptr(), None, C.byref(dxv), None, 0, 0, 0, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(dxd.float(), xpad.grad) < 1e-2
+
+
 # ---- stride-2 convs on the stride-1 tensor-core kernels (space-to-depth) ---------------------------------------------
 # (n, h, w, cin, cout, k, (pad_t, pad_l), transposed)
 S2D_CASES = [
@@ -670,7 +750,7 @@ S2D_CASES = [
 @pytest.mark.parametrize("case", S2D_CASES)
 def test_strided_conv_space_to_depth(case):
     """ConvOp in space-to-depth mode (forward, data gradient, weight gradient folded back into the Keras-layout gradient)
-    against torch on bf16-rounded operands."""
+    against the oracle's layers (oracle/layers.py) on bf16-rounded operands."""
     import numpy as np
     import torch.nn.functional as F
     from sem_b200.engine import ConvOp, Engine, ParamSpec
@@ -682,8 +762,9 @@ def test_strided_conv_space_to_depth(case):
         x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
         wt = U.bf16_round(torch.randn(k, k, cin, cout, generator=g) * 0.1)          # Keras HWIO
         xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
-        xp = F.pad(xr.permute(0, 3, 1, 2), (pl, 2 * ow + k, pt, 2 * oh + k))          # generous trailing zeros, cropped by the output size
-        y_ref = F.conv2d(xp, wr.permute(3, 2, 0, 1), stride=2)[:, :, :oh, :ow].permute(0, 2, 3, 1)
+        # the oracle's Keras rules (oracle/layers.py: asymmetric 'same' padding for stride 2)
+        y_ref = OL.conv2d(xr, wr, None, 2, "same" if k == 3 else "valid")
+        assert tuple(y_ref.shape[1:3]) == (oh, ow)
         in_hw, out_hw, lw, pw = (h, w_), (oh, ow), (k, k, cin, cout), (k, k, cpi, cpo)
         maps = {2: np.arange(cin), 3: np.arange(cout)}
     else:
@@ -691,7 +772,7 @@ def test_strided_conv_space_to_depth(case):
         x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
         wt = U.bf16_round(torch.randn(k, k, cout, cin, generator=g) * 0.1)          # Keras Conv2DTranspose kernel (kh,kw,Cout,Cin)
         xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
-        y_ref = F.conv_transpose2d(xr.permute(0, 3, 1, 2), wr.permute(3, 2, 0, 1), stride=2, padding=1, output_padding=1).permute(0, 2, 3, 1)
+        y_ref = OL.conv2d_transpose(xr, wr, None, 2)       # Keras Conv2DTranspose 'same' 
         in_hw, out_hw, lw, pw = (h, w_), (oh, ow), (k, k, cout, cin), (k, k, cpo, cpi)
         maps = {2: np.arange(cout), 3: np.arange(cin)}
     dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
@@ -768,5 +849,57 @@ def test_conv7x7_tap_folding(case):
     torch.cuda.synchronize()
     assert U.rel_err(xb.grad_tensor()[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
     assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 1e-3
+    if has_bias:
+        assert U.rel_err(torch.from_numpy(e.get_grad("w/bias")), br.grad) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(2, 30, 30, 64, True), (1, 13, 17, 24, True), (2, 12, 12, 512, False)])
+def test_patchgan_output_conv_tap_folding(case):
+    """The PatchGAN output conv (4x4, stride 1, 'valid', one output channel, bias; CycleGAN.py:448) through ConvOp's
+    tap-folded tensor-core path (per-tap 1x1 conv on the un-padded input + shift-and-add) against the oracle."""
+    import numpy as np
+    from sem_b200.engine import ConvOp, Engine, ParamSpec
+    n, h, w_, cin, has_bias = case
+    k, cout = 4, 1
+    g = torch.Generator().manual_seed(29)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wt = U.bf16_round(torch.randn(k, k, cin, cout, generator=g) * 0.05)
+    bias = torch.randn(cout, generator=g) if has_bias else None
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True) if has_bias else None
+    y_ref = OL.conv2d(xr, wr, br, 1, "valid")
+    oh, ow = h - 3, w_ - 3
+    assert tuple(y_ref.shape[1:3]) == (oh, ow)
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    cpi, cpo = U.pad8(cin), 8
+    e = Engine(n, "bf16")
+    xb = e.new_buf(h, w_, cpi, "x")
+    yb = e.new_buf(oh, ow, cpo, "y")
+    e.add_param(ParamSpec("w/kernel", "conv_kernel", (k, k, cin, cout), (k, k, cpi, cpo), {2: np.arange(cin), 3: np.arange(cout)}, True,
+                          "glorot", (1, 1)))
+    if has_bias:
+        e.add_param(ParamSpec("w/bias", "vector", (cout,), (cpo,), {0: np.arange(cout)}, True, "zeros"))
+    op = e.add_op(ConvOp(e, xb.view(), yb.view(), (h, w_), (oh, ow), "w/kernel", "w/bias" if has_bias else None, k, 1, (0, 0),
+                         L.PAD_ZERO, False))
+    assert op.tapfold is not None and op.tf_valid
+    e.finalize()
+    e.set_param("w/kernel", wt.numpy())
+    if has_bias:
+        e.set_param("w/bias", bias.numpy())
+    xb.data[..., :cin] = x.cuda().to(torch.bfloat16)
+    e.zero_step(zero_grads=True)
+    e.forward(True)
+    torch.cuda.synchronize()
+    assert U.rel_err(yb.data[..., :cout].float(), y_ref) < 1e-2
+    assert float(yb.data[..., cout:].abs().max()) == 0
+    yb.grad_tensor()[..., :cout] = dy.cuda().to(torch.bfloat16)
+    xb.grad_tensor().fill_(1.0)
+    op.acc_x = 1
+    e.backward()
+    e.fold_virtual_grads()
+    torch.cuda.synchronize()
+    assert U.rel_err(xb.grad_tensor()[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
+    assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 2e-3
     if has_bias:
         assert U.rel_err(torch.from_numpy(e.get_grad("w/bias")), br.grad) < 1e-3

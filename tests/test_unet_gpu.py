@@ -187,3 +187,156 @@ def test_loss_decreases_over_steps_bf16():
     m.compile(weighting=wgt)
     losses = [m.train_step(x.numpy(), y.numpy())["loss"] for _ in range(30)]
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+# ---- round 2: the benched configuration itself, and the dataset-level IoU ----------------------------------------------
+REPORT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+SHIP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _report(name, obj):
+    os.makedirs(REPORT_DIR, exist_ok=True)
+    with open(os.path.join(REPORT_DIR, name), "w") as fh:
+        json.dump(obj, fh, indent=1)
+
+
+def _bench_batch(kind, n=32):
+    """32 tiles of 256x256: 'random' = BASELINE configs[1] synthetic inputs; 'real' = crops of the reference's SEM images
+    with their manual masks (a problem whose gradient is signal, not noise)."""
+    if kind == "random":
+        return OU.synthetic_batch(n, 256, 256)
+    with np.load(os.path.join(SHIP, "sem_dataset.npz")) as z:
+        imgs, masks = z["images"], np.unpackbits(z["masks"], axis=-1).astype(bool)
+    rng = np.random.default_rng(0)
+    xs, ys = [], []
+    for i in range(n):
+        r, c = int(rng.integers(0, imgs.shape[1] - 256)), int(rng.integers(0, imgs.shape[2] - 256))
+        a = imgs[i % imgs.shape[0]][r:r + 256, c:c + 256].astype(np.float32)
+        xs.append((a - a.min()) / max(float((a - a.min()).max()), 1.0))
+        ys.append(masks[i % imgs.shape[0]][r:r + 256, c:c + 256].astype(np.float32))
+    x, y = torch.from_numpy(np.stack(xs))[..., None], torch.from_numpy(np.stack(ys))[..., None]
+    return x, y, float((y == 0).sum() / (y == 1).sum())
+
+
+def _grad_agreement(ref, got, floor):
+    out = {}
+    for name, r in ref.items():
+        r = r.float()
+        if float(r.abs().max()) < floor:
+            continue            # analytically-zero gradients (betas in front of a batch-statistics BN): rounding noise only
+        g = got[name].float()
+        out[name] = (float((r * g).sum() / (r.norm() * g.norm()).clamp_min(1e-30)), float((r - g).abs().max() / r.abs().max()))
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(SHIP, "sem_dataset.npz")), reason="dataset slice not staged")
+@pytest.mark.parametrize("kind", ["real", "random"])
+def test_train_step_at_the_bench_config_every_gradient(kind):
+    """BASELINE configs[1] itself -- 256x256, batch 32: 8192 pixel tiles per launch, ring wrap-around over thousands of
+    tiles, K-chunk weight streaming at depth -- one train step, every gradient tensor against the oracle (fp32, evaluated
+    on the same bf16-rounded weights and inputs).  No ensemble; tolerances per tensor:
+
+      fp32 storage : cosine >= 0.9995 and max error <= 5 % of max|ref| (measured 0.99991 / 3.4 %: the residue is ReLU /
+                     max-pool decisions at |x| ~ 1e-7, see test_train_step_matches_oracle_f32)
+      bf16 storage : loss within 1e-3; per tensor  1 - cos <= 3 * (1 - cos_emulated) + 2e-3, where cos_emulated is what
+                     the ORACLE itself loses when it rounds activations and gradients to bf16 at the tensor boundaries
+                     the CUDA path stores (oracle.layers.storage) -- i.e. the GPU may drift from the fp32 path no more
+                     than three times what bf16 storage costs any implementation on this very problem.  With random
+                     labels that cost is large (the gradient is a near-cancelling sum over 2 M pixels: median cosine of
+                     the emulation ~0.8); on real SEM crops it is small (median 0.999).
+    All per-tensor numbers are written to gpurun_out/grad_report_<kind>.json."""
+    from oracle import layers as OL
+    n = 32
+    spec = OU.UNetSpec(16)
+    p0 = {k: U.bf16_round(v) if k.endswith("/kernel") else v for k, v in spec.init_params(seed=0).items()}
+    x, y, wgt = _bench_batch(kind, n)
+    x = U.bf16_round(x)
+    torch.set_num_threads(os.cpu_count() or 1)
+    tr = OU.UNetTrainer(spec, p0, wgt)
+    logs_ref, _ = tr.train_step(x, y)
+    with OL.storage(torch.bfloat16):
+        tre = OU.UNetTrainer(spec, p0, wgt)
+        logs_emu, _ = tre.train_step(x, y)
+    gmax = max(float(g.abs().max()) for g in tr.last_grads.values())
+    emu = _grad_agreement(tr.last_grads, tre.last_grads, 1e-3 * gmax)
+    report = {"config": f"UNet 256x256 batch {n}, one train step, {kind} data", "oracle_loss": logs_ref["loss"],
+              "oracle_bf16_emulated_loss": logs_emu["loss"], "modes": {}}
+    for dtype in ("f32", "bf16"):
+        m = UNetModel((256, 256, 1), 16, dtype=dtype, batch_size=n, use_cuda_graph=(dtype == "bf16"))
+        m.set_named_weights(_named_np(p0))
+        m.compile(weighting=wgt, learning_rate=1e-3)
+        logs = dict(m.train_step(x.numpy(), y.numpy()))
+        torch.cuda.synchronize()
+        e = m.engine
+        got = {name: torch.from_numpy(e.get_grad(name)) for name in spec.trainable_names()}
+        agr = _grad_agreement(tr.last_grads, got, 1e-3 * gmax)
+        rel_loss = abs(logs["loss"] - logs_ref["loss"]) / abs(logs_ref["loss"])
+        worst_cos = min(agr.items(), key=lambda kv: kv[1][0])
+        worst_err = max(agr.items(), key=lambda kv: kv[1][1])
+        report["modes"][dtype] = {"loss": logs["loss"], "rel_loss_err": rel_loss, "acc": logs["acc"], "oracle_acc": logs_ref["acc"],
+                                  "tensors": len(agr), "worst_cosine": [worst_cos[0], worst_cos[1][0]],
+                                  "worst_max_err": [worst_err[0], worst_err[1][1]],
+                                  "median_cosine": float(np.median([v[0] for v in agr.values()])),
+                                  "per_tensor": {k: {"cos": v[0], "max_err": v[1], "cos_bf16_emulated_oracle": emu[k][0]} for k, v in agr.items()}}
+        print(kind, dtype, "loss rel err", rel_loss, "worst cos", worst_cos, "worst err", worst_err, "median cos",
+              report["modes"][dtype]["median_cosine"], "emulated median cos", float(np.median([v[0] for v in emu.values()])))
+        _report(f"grad_report_{kind}.json", report)
+        assert len(agr) > 100
+        assert abs(logs["acc"] - logs_ref["acc"]) < 5e-3
+        if dtype == "f32":
+            assert rel_loss < 1e-4
+            assert worst_cos[1][0] >= 0.9995, worst_cos
+            assert worst_err[1][1] <= 0.05, worst_err
+        else:
+            assert rel_loss < 1e-3
+            bad = {k: (v[0], emu[k][0]) for k, v in agr.items() if (1.0 - v[0]) > 3.0 * (1.0 - emu[k][0]) + 2e-3}
+            assert not bad, bad
+        del m
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(SHIP, "sem_dataset.npz")), reason="dataset slice not staged (run __graft_entry__.build() where /root/reference exists)")
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_full_image_iou_on_the_reference_dataset(dtype, gan_weights):
+    """north_star: segmentation IoU on Datasets/ within +-0.01 of the reference path.  All 40 SEM images (rows 0:704,
+    whole image, per-image min-max) through the CUDA UNet with the reference-trained weights; whole-image IoU
+    (Calculate_Scores.py:69-70) against the manual masks, compared per image and in the mean with the oracle's known
+    answers (tests/golden/pb_known_answers.json); mask mismatches against the oracle's own masks are COUNTED on four
+    images and written to gpurun_out/iou_report_<dtype>.json (f32: must be 0)."""
+    from sem_b200 import Scores
+    ka = json.load(open(os.path.join(GOLD, "pb_known_answers.json")))["models"]["GAN"]
+    with np.load(os.path.join(SHIP, "sem_dataset.npz")) as z:
+        imgs, masks = z["images"], np.unpackbits(z["masks"], axis=-1).astype(bool)
+    m = UNetModel((imgs.shape[1], imgs.shape[2], 1), 16, dtype=dtype, batch_size=1)
+    m.set_named_weights(gan_weights)
+    ious, outs = [], {}
+    for i in range(imgs.shape[0]):
+        x = imgs[i].astype(np.float32)
+        x = (x - x.min()) / (x - x.min()).max()
+        yp = m(x[None, :, :, None], training=False).numpy()[0, :, :, 0]
+        ious.append(Scores.calculateWholeImageIoU(yp > 0.5, masks[i]))
+        if i in (0, 9, 17, 33):
+            outs[i] = (x, yp)
+    per_ref = ka["per_image_iou_0.5"]
+    d_img = float(np.max(np.abs(np.asarray(ious) - np.asarray(per_ref))))
+    d_mean = abs(float(np.mean(ious)) - ka["mean_iou"]["0.5"])
+    # mask mismatches against the oracle on four images
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in gan_weights.items()}
+    mism = {}
+    for i, (x, yp) in outs.items():
+        with torch.no_grad():
+            yo, _ = OU.unet_forward(torch.from_numpy(x)[None, :, :, None], P, training=False)
+        yo = yo[0, :, :, 0].numpy()
+        mism[str(i)] = {"mask_mismatches": int(((yp > 0.5) != (yo > 0.5)).sum()), "pixels": int(yo.size),
+                        "max_abs_err": float(np.abs(yp - yo).max())}
+    _report(f"iou_report_{dtype}.json", {"dtype": dtype, "mean_iou": float(np.mean(ious)), "oracle_mean_iou": ka["mean_iou"]["0.5"],
+                                         "max_per_image_iou_diff": d_img, "per_image_iou": [round(float(v), 6) for v in ious],
+                                         "mask_mismatches_vs_oracle": mism})
+    print(dtype, "mean IoU", float(np.mean(ious)), "oracle", ka["mean_iou"]["0.5"], "max per-image diff", d_img, mism)
+    assert d_mean < 0.01 and d_img < 0.01
+    if dtype == "f32":
+        assert d_img < 1e-3
+        assert all(v["mask_mismatches"] == 0 for v in mism.values()), mism
+    else:
+        assert all(v["mask_mismatches"] < 0.005 * v["pixels"] for v in mism.values()), mism
