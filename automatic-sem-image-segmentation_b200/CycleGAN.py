@@ -3,7 +3,7 @@
 Same attribute-style configuration and method names; `create_model()` returns `sem_b200.CycleGanModel` (networks and
 train step in hand-written CUDA).  Supported configuration = what StartProcess.py drives: no skip connection, no
 Gaussian noise in the discriminators, transposed-conv upsampling, MAE cycle / identity losses (other switches raise).
-Models are saved as `model.npz`; the per-epoch image mosaics of GANMonitor are not produced.
+Models are saved as `.keras`-style zip archives (keras_io.py).
 """
 from __future__ import annotations
 
@@ -140,23 +140,40 @@ class CycleGAN:
                     fh.write(";".join(["epoch"] + sorted(logs)) + "\n")
                 fh.write(";".join([str(epoch)] + [repr(logs[k]) for k in sorted(logs)]) + "\n")
             print(f"Epoch {epoch + 1}/{self.epochs} - " + " - ".join(f"{k}: {v:.4f}" for k, v in logs.items()), flush=True)
-            self.save(os.path.join(out_dir, f"checkpoints_{epoch + 1:03d}.npz"))
+            self.save(os.path.join(out_dir, f"checkpoints_{epoch + 1:03d}.keras"))
             self.data.on_epoch_end()
-        self.save(os.path.join(out_dir, "model.npz"))
+        self.save(os.path.join(out_dir, "model.keras"))
         return self.model
 
     def save(self, path):
-        arrs = {}
+        """One `.keras`-style zip per model (all four networks; keras_io), or a flat .npz for a path ending in .npz."""
+        arrs, order = {}, []
         for name, net in self.model.nets.items():
             for n, w in zip(net.names, net.get_weights()):
                 arrs[f"{name}/{n}"] = w
-        np.savez(path, **arrs)
+                order.append(f"{name}/{n}")
+        if path.endswith(".npz"):
+            np.savez(path, **arrs)
+            return
+        from . import keras_io
+        cfg = {"class": "CycleGanModel", "image_shape": list(self.image_shape), "filters": self.filters,
+               "use_skip_connection": self.use_skip_connection, "use_resize_convolution": self.use_resize_convolution,
+               "num_residual_blocks_gen": self.num_residual_blocks_gen, "format": "semb200-keras-1"}
+        keras_io.save_keras(path, cfg, arrs, order, rename=lambda s: s)
+
+    @staticmethod
+    def _read(path):
+        from . import keras_io
+        if keras_io.is_keras_archive(path):
+            return keras_io.load_keras(path, rename=lambda s: s)[1]
+        with np.load(path) as z:
+            return {k: z[k] for k in z.files}
 
     def load(self, path):
         self.model = self.model or self.create_model()
-        with np.load(path) as z:
-            for name, net in self.model.nets.items():
-                net.set_named({n: z[f"{name}/{n}"] for n in net.names})
+        z = self._read(path)
+        for name, net in self.model.nets.items():
+            net.set_named({n: z[f"{name}/{n}"] for n in net.names})
         return self.model
 
     def run_inference(self, files, output_directory, source_domain, model=None, tile_images=False, min_overlap=2,
@@ -168,12 +185,13 @@ class CycleGAN:
         weights_from = model if isinstance(model, str) else None
         if self.model is None and weights_from is None:
             newest = sorted(os.listdir(self.model_dir))[-1]
-            weights_from = os.path.join(self.model_dir, newest, "model.npz")
+            cand = [os.path.join(self.model_dir, newest, f) for f in ("model.keras", "model.npz")]
+            weights_from = next((c for c in cand if os.path.exists(c)), cand[0])
         cache = collections.OrderedDict()          # at most two generator instances alive (LRU): sizes vary per image
         named = None
         if weights_from is not None:
-            with np.load(weights_from) as z:
-                named = {k[len(which) + 1:]: z[k] for k in z.files if k.startswith(which + "/")}
+            z = self._read(weights_from)
+            named = {k[len(which) + 1:]: v for k, v in z.items() if k.startswith(which + "/")}
         for i in range(images.shape[0]):
             img = images[i]
             if which == "gen_a" and self.invert_images:

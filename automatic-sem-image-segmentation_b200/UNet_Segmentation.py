@@ -3,10 +3,11 @@
 Same class / method / attribute names and argument meaning as the reference (UNet :147-562, ImageDataset :21-101,
 DataLoader :104-122, DataSet :125-144); the Keras graph is replaced by `sem_b200.UNetModel` (hand-written CUDA behind
 the C ABI).  Differences a caller can observe:
-  * models are saved as `model.npz` (creation-order variables + JSON config) next to where the reference writes
-    `model.keras` -- the `.keras` container needs h5py, which is not available (SURVEY.md 8f N4);
+  * `model.keras` / `Checkpoint_Lowest_Loss.keras` are Keras-3 style zip archives whose weights store is the npz variant
+    (`model.weights.npz`; h5py is not available) and whose config.json is this package's own description (keras_io.py);
   * `run_inference(..., use_gpu=False)` still runs on the GPU: there is no CPU path in this package;
-  * `segment()` thresholds (Otsu) but does not split touching particles with a watershed.
+  * `segment()` (Otsu + distance-transform watershed with lines) is restated from scikit-image's published algorithms
+    (Measurements.py); scikit-image itself is not installable here.
 """
 from __future__ import annotations
 
@@ -19,7 +20,8 @@ from datetime import datetime
 import numpy as np
 from PIL import Image
 
-from . import HelperFunctions
+from . import HelperFunctions, keras_compat
+from .keras_compat import ReflectionPadding2D  # noqa: F401  (module-level class of the reference, :565-589)
 from .model import CSVLogger, LearningRateScheduler, ModelCheckpoint, UNetModel, load_model
 
 
@@ -152,10 +154,39 @@ class UNet:
         return self.learning_rate * (1 - epoch / float(self.epochs))
 
     # ---- model -----------------------------------------------------------------------------------------
+    # The reference's static layer functions (:401-503), same names / argument order, operating on symbolic tensors of
+    # keras_compat.Input(...): each call records engine ops.  Only what the MultiRes-UNet uses is accepted: square 1x1 / 3x3
+    # kernels, 'same' padding, stride 1 (2x2 stride 2 for the transposed conv).
     @staticmethod
-    def multi_res_unet(input_shape, output_channels=1, conv_filters=16, dtype="bf16", batch_size=1) -> UNetModel:
-        """MultiResUNet (reference :505-562) as an engine model; conv2d_bn / multi_res_block / res_path live in nets.py."""
-        return UNetModel(tuple(input_shape), conv_filters, output_channels, dtype=dtype, batch_size=batch_size)
+    def conv2d_bn(x, filters, num_row, num_col, padding="same", strides=(1, 1), activation="relu", name=None):
+        if num_row != num_col or num_row not in (1, 3) or padding != "same" or tuple(strides) != (1, 1):
+            raise NotImplementedError("conv2d_bn: the engine builds 1x1 / 3x3, 'same', stride-1 convolutions (what multi_res_unet uses)")
+        return keras_compat.builder_of(x).conv2d_bn(x, int(filters), int(num_row), activation)
+
+    @staticmethod
+    def trans_conv2d_bn(x, filters, num_row, num_col, padding="same", strides=(2, 2), name=None):
+        """Defined but never called by the reference's own graph (multi_res_unet uses a bare Conv2DTranspose, :542-551);
+        the BatchNormalization after a transposed conv has no fused kernel here."""
+        raise NotImplementedError("trans_conv2d_bn is unused by multi_res_unet (UNet_Segmentation.py:542-551) and not built")
+
+    @staticmethod
+    def multi_res_block(u, inp, alpha=1.67):
+        return keras_compat.builder_of(inp).multi_res_block(int(u), inp, alpha=alpha)
+
+    @staticmethod
+    def res_path(filters, length, inp):
+        return keras_compat.builder_of(inp).res_path(int(filters), int(length), inp)
+
+    @staticmethod
+    def multi_res_unet(inputs, output_channels=1, conv_filters=16, dtype=None, batch_size=None) -> UNetModel:
+        """MultiResUNet (reference :505-562).  `inputs`: keras_compat.Input(shape=(H, W, 1), batch_size=, dtype=) like the
+        reference's `keras.layers.Input`, or a plain (H, W, 1) shape tuple (then dtype / batch_size may be given here)."""
+        if isinstance(inputs, keras_compat.T):
+            e = inputs.view.buf.eng
+            shape, dtype, batch_size = (inputs.h, inputs.w, inputs.layout.logical), dtype or e.dtype_name, batch_size or e.N
+        else:
+            shape = tuple(inputs)
+        return UNetModel(shape, conv_filters, output_channels, dtype=dtype or "bf16", batch_size=batch_size or 1)
 
     def create_model(self):
         """weighting = #zeros/#ones over the training masks (:364-376); Adam(lr) + weighted BCE (:379-395)."""
@@ -187,7 +218,7 @@ class UNet:
         self.training_data = self.load_images("train")
         self.validation_data = self.load_images("val")
         self.model = self.create_model()
-        callbacks = [ModelCheckpoint(os.path.join(out_dir, "Checkpoint_Lowest_Loss.npz"), monitor="loss", verbose=1, save_best_only=True, mode="min"),
+        callbacks = [ModelCheckpoint(os.path.join(out_dir, "Checkpoint_Lowest_Loss.keras"), monitor="loss", verbose=1, save_best_only=True, mode="min"),
                      CSVLogger(os.path.join(out_dir, "training_log.csv"), separator=";", append=True)]
         if self.lr_decay == "STEP_DECAY":
             callbacks.append(LearningRateScheduler(self.step_decay))
@@ -196,7 +227,7 @@ class UNet:
         print("Start training the model: " + str(datetime.now()))
         self.model.fit(self.training_data, batch_size=self.batch_size, epochs=self.epochs, verbose=1, callbacks=callbacks,
                        validation_data=self.validation_data)
-        path = os.path.join(out_dir, "model.npz")
+        path = os.path.join(out_dir, "model.keras")
         print("Saving model to: " + path)
         self.model.save(path)
         return self.model
@@ -206,7 +237,8 @@ class UNet:
         if self.model is None:
             if model is None:
                 newest = sorted(os.listdir(self.model_dir))[-1]
-                self.model = load_model(os.path.join(self.model_dir, newest, "model.npz"), dtype=self.dtype)
+                cand = [os.path.join(self.model_dir, newest, f) for f in ("model.keras", "model.npz")]
+                self.model = load_model(next((c for c in cand if os.path.exists(c)), cand[0]), dtype=self.dtype)
             elif isinstance(model, str):
                 self.model = load_model(model, dtype=self.dtype)
             else:
@@ -221,11 +253,10 @@ class UNet:
             img = images[i]
             if tile_images:
                 th, tw = self.image_shape[0], self.image_shape[1]
-                tiles = HelperFunctions.tile_image(img, tw, th, min_overlap=min_overlap)
-                # all tiles of an image go through the engine as ONE batch (the reference calls the model tile by tile)
-                pred = self.model.predict(tiles, batch_size=min(len(tiles), self.inference_batch_size))
-                out = HelperFunctions.stitch_image(pred, img.shape[1], img.shape[0], min_overlap=min_overlap,
-                                                   manage_overlap_mode=manage_overlap_mode)
+                # tile grid, batched forward and stitching all on the device (the reference tiles / stitches on the host and
+                # calls the model tile by tile, :338-340)
+                out = self.model.predict_tiled(img, tw, th, min_overlap=min_overlap, manage_overlap_mode=manage_overlap_mode,
+                                               batch_size=self.inference_batch_size)
             else:
                 out = self.model(img[None], training=False).numpy()[0]      # fully convolutional: any H, W
             out = out[:, :, 0].copy()

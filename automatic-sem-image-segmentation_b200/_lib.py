@@ -86,6 +86,8 @@ SIGNATURES = {
     "semb_pad_crop": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semb_pixel_shuffle2": (C.c_int, [_TP, _TP, _I, _I, _I, _P, _I, _I, _P]),
     "semb_pixel_shuffle2x": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "semb_tile_gather": (C.c_int, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
+    "semb_tile_stitch": (C.c_int, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P]),
     "semb_upsample2x": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _P]),
     "semb_s2d_weights": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "semb_fold_stats4": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),

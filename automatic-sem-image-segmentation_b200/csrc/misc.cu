@@ -497,6 +497,51 @@ __global__ void tapfold_weights_kernel(float* __restrict__ w, int taps, int T8, 
     }
 }
 
+// ---- overlapping tile grid of HelperFunctions.tile_image / stitch_image (:17-141) on the device --------------------------
+// Tiles are numbered x-major (k = ix * ny + iy) like the reference's loops; xs / ys are the tile offsets along each axis.
+// gather: tiles[k - k0][y][x] = img[ys[iy] + y][xs[ix] + x], zero outside the image.
+__global__ void tile_gather_kernel(const float* __restrict__ img, int H, int W, float* __restrict__ tiles, int th, int tw,
+                                   const int* __restrict__ xs, const int* __restrict__ ys, int ny, int k0, int count) {
+    const long long total = (long long)count * th * tw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % tw), y = (int)((i / tw) % th), k = k0 + (int)(i / ((long long)tw * th));
+        const int gx = xs[k / ny] + x, gy = ys[k % ny] + y;
+        tiles[i] = (gx < W && gy < H) ? img[(size_t)gy * W + gx] : 0.f;
+    }
+}
+
+// stitch: one thread per output pixel walks the tiles in the reference's order.  mode 0: maximum (with the zero the
+// reference's output buffer starts from), mode 1: average over the covering tiles, mode 2: every tile contributes its
+// centre (half of the overlap cropped on each inner side); where two crops still meet, the later tile wins like the
+// reference's sequential assignment.
+__global__ void tile_stitch_kernel(const float* __restrict__ tiles, int th, int tw, float* __restrict__ out, int H, int W,
+                                   const int* __restrict__ xs, int nx, const int* __restrict__ ys, int ny, int mode, int ovx, int ovy) {
+    const long long total = (long long)H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)(i / W);
+        float acc = 0.f;
+        int cnt = 0;
+        for (int ix = 0; ix < nx; ++ix) {
+            const int ox = xs[ix];
+            int x_lo = ox, x_hi = min(ox + tw, W);
+            if (mode == 2) { x_lo = ox + (ix == 0 ? 0 : ovx); x_hi = min(ox + tw - (ix == nx - 1 ? 0 : ovx), W); }
+            if (x < x_lo || x >= x_hi) continue;
+            for (int iy = 0; iy < ny; ++iy) {
+                const int oy = ys[iy];
+                int y_lo = oy, y_hi = min(oy + th, H);
+                if (mode == 2) { y_lo = oy + (iy == 0 ? 0 : ovy); y_hi = min(oy + th - (iy == ny - 1 ? 0 : ovy), H); }
+                if (y < y_lo || y >= y_hi) continue;
+                const float v = tiles[((size_t)(ix * ny + iy) * th + (y - oy)) * tw + (x - ox)];
+                if (mode == 0) acc = fmaxf(acc, v);
+                else if (mode == 1) { acc += v; ++cnt; }
+                else acc = v;
+            }
+        }
+        // the reference divides by a uint8 count image: an uncovered pixel (cannot happen for a valid grid) would be 0/0
+        out[i] = mode == 1 ? acc / (float)cnt : acc;
+    }
+}
+
 static inline int grid_for(long long total, int block = 256) {
     long long b = cdivl(total, block);
     const long long cap = 148LL * 16;
@@ -628,6 +673,25 @@ extern "C" int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* d
 extern "C" int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
                                    const float* bias, int32_t dir, int32_t dtype, void* stream) {
     return semb_pixel_shuffle2x(src, dst, N, H, W, 2 * H, 2 * W, bias, dir, 0, dtype, stream);
+}
+
+extern "C" int semb_tile_gather(const float* img, int32_t H, int32_t W, float* tiles, int32_t th, int32_t tw, const int32_t* xs, int32_t nx,
+                                const int32_t* ys, int32_t ny, int32_t k0, int32_t count, void* stream) {
+    SEMB_REQUIRE(img && tiles && xs && ys && H > 0 && W > 0 && th > 0 && tw > 0 && nx > 0 && ny > 0 && k0 >= 0 && count > 0 &&
+                 k0 + count <= nx * ny, SEMB_ESHAPE, "tile_gather: bad arguments");
+    tile_gather_kernel<<<grid_for((long long)count * th * tw), 256, 0, as_stream(stream)>>>(img, H, W, tiles, th, tw, xs, ys, ny, k0, count);
+    return check_launch("tile_gather");
+}
+
+extern "C" int semb_tile_stitch(const float* tiles, int32_t th, int32_t tw, float* out, int32_t H, int32_t W, const int32_t* xs, int32_t nx,
+                                const int32_t* ys, int32_t ny, int32_t mode, void* stream) {
+    SEMB_REQUIRE(tiles && out && xs && ys && H > 0 && W > 0 && th > 0 && tw > 0 && nx > 0 && ny > 0 && mode >= 0 && mode <= 2, SEMB_ESHAPE,
+                 "tile_stitch: bad arguments");
+    // half of the overlap that mode 2 crops from each inner side (HelperFunctions.py:84-85)
+    const int ovx = nx > 1 ? (tw * nx - W) / (2 * (nx - 1)) : 0;
+    const int ovy = ny > 1 ? (th * ny - H) / (2 * (ny - 1)) : 0;
+    tile_stitch_kernel<<<grid_for((long long)H * W), 256, 0, as_stream(stream)>>>(tiles, th, tw, out, H, W, xs, nx, ys, ny, mode, ovx, ovy);
+    return check_launch("tile_stitch");
 }
 
 extern "C" int semb_upsample2x(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t dir,

@@ -305,6 +305,41 @@ class UNetModel:
             outs.append(self(chunk).numpy()[:m])
         return np.concatenate(outs, 0)
 
+    def predict_tiled(self, img, tile_w: int, tile_h: int, min_overlap: int = 2, manage_overlap_mode: int = 2, batch_size: int = 16):
+        """tile_image -> model -> stitch_image of the reference's inference loop (UNet_Segmentation.py:335-343) with the
+        image uploaded ONCE: the overlapping tiles are gathered on the device straight into the engine's input, run in
+        chunks of `batch_size` (the reference runs them one by one), and stitched on the device.  img: (H, W[, 1])."""
+        from . import HelperFunctions as HF
+        img = np.ascontiguousarray(_to_numpy(img), dtype=np.float32)
+        if img.ndim == 3:
+            img = img[:, :, 0]
+        H, W = img.shape
+        nx, xs = HF._grid(W, tile_w, min_overlap)
+        ny, ys = HF._grid(H, tile_h, min_overlap)
+        nt = nx * ny
+        bs = max(1, min(int(batch_size), nt))
+        inst = self._use(self._instance(bs, tile_h, tile_w))
+        e = inst.eng
+        dev = e.device
+        img_d = torch.from_numpy(img).to(dev, non_blocking=True)
+        xs_d = torch.tensor(xs, dtype=torch.int32, device=dev)
+        ys_d = torch.tensor(ys, dtype=torch.int32, device=dev)
+        pred = torch.zeros((nt, tile_h, tile_w), dtype=torch.float32, device=dev)
+        out = torch.empty((H, W), dtype=torch.float32, device=dev)
+        for k0 in range(0, nt, bs):
+            cnt = min(bs, nt - k0)
+            if cnt < bs:
+                inst.x_dev.zero_()          # the padded tail of the last chunk (samples are independent in inference mode)
+            L.check(e.lib.semb_tile_gather(img_d.data_ptr(), H, W, inst.x_dev.data_ptr(), tile_h, tile_w, xs_d.data_ptr(), nx,
+                                           ys_d.data_ptr(), ny, k0, cnt, e.stream))
+            inst.stage_in()
+            e.forward(training=False)
+            inst.stage_out()
+            pred[k0:k0 + cnt].copy_(inst.out_dev[:cnt, :, :, 0])
+        L.check(e.lib.semb_tile_stitch(pred.data_ptr(), tile_h, tile_w, out.data_ptr(), H, W, xs_d.data_ptr(), nx, ys_d.data_ptr(), ny,
+                                       int(manage_overlap_mode), e.stream))
+        return out.cpu().numpy()[:, :, None]
+
     # ---- training ------------------------------------------------------------------------------------
     def compile(self, weighting: float = 1.0, learning_rate: float = 1e-3, beta_1: float = 0.9, beta_2: float = 0.999,
                 epsilon: float = 1e-7):
@@ -471,20 +506,35 @@ class UNetModel:
 
     # ---- persistence ---------------------------------------------------------------------------------
     def save(self, path: str):
-        """Writes `<path>` as an .npz of creation-order variables plus a JSON config.  (The reference's
-        `.keras` zip needs h5py, which this image lacks -- SURVEY.md 8f N4.)"""
+        """`model.save(path)` (UNet_Segmentation.py:262,287): a Keras-3 style `.keras` zip (metadata.json, config.json,
+        model.weights.npz store with Keras layer paths; see keras_io) -- or, for a path ending in .npz, the flat archive of
+        round 1."""
         named = self.get_named_weights()
         cfg = {"class": "MultiResUNet", "input_shape": list(self.input_shape), "filters": self.filters,
-               "dtype": self.dtype, "weighting": self.weighting, "format": "semb200-npz-1"}
-        with open(path, "wb") as fh:
-            np.savez(fh, __config__=np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8), **named)
+               "dtype": self.dtype, "weighting": self.weighting, "format": "semb200-keras-1"}
+        if path.endswith(".npz"):
+            with open(path, "wb") as fh:
+                np.savez(fh, __config__=np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8), **named)
+            return
+        from . import keras_io
+        keras_io.save_keras(path, cfg, named, self.creation_names())
 
     @staticmethod
-    def load(path: str, dtype: Optional[str] = None, batch_size: int = 1) -> "UNetModel":
-        with np.load(path) as z:
-            cfg = json.loads(bytes(z["__config__"]).decode())
-            named = {k: z[k] for k in z.files if k != "__config__"}
-        m = UNetModel(tuple(cfg["input_shape"]), cfg["filters"], 1, dtype or cfg["dtype"], batch_size)
+    def load(path: str, dtype: Optional[str] = None, batch_size: int = 1, input_shape=None, filters: int = 16) -> "UNetModel":
+        """`.keras` (this package's writer), legacy `.npz`, or one of the reference's frozen `.pb` UNets
+        (ImageJ Plugin/SEM_Particle_Segmentation_Models; input_shape / filters must then be given, default 512x352x1 / 16)."""
+        from . import keras_io
+        if path.endswith(".pb"):
+            m = UNetModel(tuple(input_shape or (512, 352, 1)), filters, 1, dtype or "f32", batch_size)
+            m.set_named_weights(keras_io.read_pb_weights(path, m.creation_names()))
+            return m
+        if keras_io.is_keras_archive(path):
+            cfg, named = keras_io.load_keras(path)
+        else:
+            with np.load(path) as z:
+                cfg = json.loads(bytes(z["__config__"]).decode())
+                named = {k: z[k] for k in z.files if k != "__config__"}
+        m = UNetModel(tuple(input_shape or cfg["input_shape"]), cfg["filters"], 1, dtype or cfg["dtype"], batch_size)
         m.set_named_weights(named)
         m.weighting = cfg.get("weighting", 1.0)
         return m

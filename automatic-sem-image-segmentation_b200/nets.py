@@ -80,7 +80,8 @@ class T:
 
 
 class UNetBuilder:
-    def __init__(self, eng: Engine, h: int, w: int, filters: int = 16, in_channels: int = 1, output_channels: int = 1):
+    def __init__(self, eng: Engine, h: int, w: int, filters: int = 16, in_channels: int = 1, output_channels: int = 1,
+                 build: bool = True):
         if output_channels != 1:
             raise NotImplementedError("softmax head (output_channels>1) is not on the north-star path yet")
         self.e, self.h, self.w, self.filters = eng, h, w, filters
@@ -88,7 +89,36 @@ class UNetBuilder:
         self.nconv = self.nbn = self.nct = 0
         self.creation_names: List[str] = []
         self.taps: Dict[str, T] = {}
-        self._build(in_channels)
+        eng._builder = self          # the reference's static layer functions find their graph through the tensor's engine
+        self._anon = 0
+        if build:
+            self._build(in_channels)
+        else:
+            # functional use (UNet.conv2d_bn / multi_res_block / res_path called on keras_compat.Input): only the input exists
+            lin = Layout.simple(in_channels)
+            self.in_buf = eng.new_buf(h, w, lin.phys, "input", requires_grad=False)
+            self.input = T(self.in_buf.view(), h, w, lin, self.kg.layer("input", []))
+            self.out_buf = self.output = self.keras_output_layer = None
+
+    # ---- generic layer functions behind the reference's statics (UNet_Segmentation.py:401-449) -------------------------
+    def conv2d_bn(self, x: T, filters: int, k: int, activation: Optional[str]) -> T:
+        """Conv2D(k x k, same, no bias) -> BatchNormalization(scale=False) -> optional activation, materialised."""
+        act = {None: L.ACT_NONE, "relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID}[activation]
+        lay = Layout.simple(filters)
+        raw, bn = self.conv2d_bn_raw(x, lay, k)
+        klast = raw.klayer
+        if activation is not None:
+            klast = self.kg.layer("activation", [raw.klayer])
+        out = self.e.new_buf(x.h, x.w, lay.phys, f"conv{self.nconv}_out")
+        self.e.add_op(AffineOp(self.e, x.h * x.w, raw.view, bn, None, None, out.view(), act))
+        return T(out.view(), x.h, x.w, lay, klast)
+
+    def anon(self, prefix: str) -> str:
+        self._anon += 1
+        return f"{prefix}_{self._anon}"
+
+    def set_output(self, t: T):
+        self.output, self.out_buf, self.keras_output_layer = t, t.view.buf, t.klayer
 
     # ---- parameter helpers --------------------------------------------------------------------------
     def _add(self, spec: ParamSpec):
@@ -140,10 +170,11 @@ class UNetBuilder:
         e.add_op(norm)
         return T(out_view, x.h, x.w, lout, kbn), norm
 
-    def multi_res_block(self, u: int, inp: T, name: str) -> T:
+    def multi_res_block(self, u: int, inp: T, name: Optional[str] = None, alpha: float = 1.67) -> T:
         """UNet_Segmentation.py:451-474."""
         e = self.e
-        wdt = 1.67 * u
+        name = name or self.anon("mres")
+        wdt = alpha * u
         ca, cb, cc = int(wdt * 0.167), int(wdt * 0.333), int(wdt * 0.5)
         la, lb, lc = Layout.simple(ca), Layout.simple(cb), Layout.simple(cc)
         lcat = Layout.concat(la, lb, lc)
@@ -187,9 +218,10 @@ class UNetBuilder:
         self.taps[name] = t
         return t
 
-    def res_path(self, filters: int, length: int, inp: T, name: str, final_view: Optional[View] = None) -> T:
+    def res_path(self, filters: int, length: int, inp: T, name: Optional[str] = None, final_view: Optional[View] = None) -> T:
         """UNet_Segmentation.py:476-503.  The last unit writes into `final_view` (a slice of the decoder concat)."""
         e = self.e
+        name = name or self.anon("rp")
         lay = Layout.simple(filters)
         hw = inp.h * inp.w
         count = e.N * hw

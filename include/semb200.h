@@ -316,6 +316,17 @@ int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t 
 int semb_upsample2x(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t dir,
                     int32_t accumulate, int32_t dtype, void* stream);
 
+/* ---- tiled inference: HelperFunctions.tile_image / stitch_image (:17-141) as index arithmetic on the device ----------
+ * The reference cuts an image into overlapping tiles on the host, calls the model tile by tile and stitches on the host
+ * (UNet_Segmentation.py:335-343).  Here the image is uploaded once; tiles are numbered x-major (k = ix*ny + iy), xs[nx] /
+ * ys[ny] are the per-axis tile offsets (device int32 arrays computed by the host from the reference's grid rule).
+ * gather: tiles[k-k0] (fp32, th x tw, one channel) for k in [k0, k0+count), zero beyond the image edge.
+ * stitch: all nx*ny predicted tiles -> out (H x W fp32); mode 0 maximum, 1 average, 2 centre crop (manage_overlap_mode). */
+int semb_tile_gather(const float* img, int32_t H, int32_t W, float* tiles, int32_t th, int32_t tw, const int32_t* xs, int32_t nx,
+                     const int32_t* ys, int32_t ny, int32_t k0, int32_t count, void* stream);
+int semb_tile_stitch(const float* tiles, int32_t th, int32_t tw, float* out, int32_t H, int32_t W, const int32_t* xs, int32_t nx,
+                     const int32_t* ys, int32_t ny, int32_t mode, void* stream);
+
 /* ---- losses ------------------------------------------------------------------------------ */
 
 /* weighted_bce (UNet_Segmentation.py:379-384) + the 'mae' and 'acc' metrics (:395) + d(loss)/d(p).

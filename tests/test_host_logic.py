@@ -182,3 +182,32 @@ def test_cyclegan_builders_options_create_the_reference_variables():
     assert len(b.noise_ops) == 4 and b.creation_names == [n for n, _, _ in OC.discriminator_spec(16)]
     with pytest.raises(ValueError):
         GeneratorBuilder(Engine(1, "bf16", dry=True), 36, 36, 8, n_res=1, use_skip_connection=True)
+
+
+def test_keras_archive_roundtrip_and_pb_reader(tmp_path):
+    """keras_io: `.keras` zip (metadata.json, config.json, model.weights.npz with Keras layer paths) round trip, and the
+    product's own frozen-graph reader against the oracle's (when the reference tree is present)."""
+    import zipfile
+    from sem_b200 import keras_io
+    got = [keras_io.keras_layer_name(n) for n in ("conv2d_1", "conv2d_2", "batch_normalization_85", "stem")]
+    assert got == ["conv2d", "conv2d_1", "batch_normalization_84", "stem"]
+    order = ["conv2d_1/kernel", "batch_normalization_1/beta", "batch_normalization_1/moving_mean", "conv2d_transpose_1/kernel",
+             "conv2d_transpose_1/bias"]
+    rng = np.random.default_rng(0)
+    named = {n: rng.standard_normal((3, 2)).astype(np.float32) for n in order}
+    p = str(tmp_path / "model.keras")
+    keras_io.save_keras(p, {"class": "MultiResUNet", "filters": 16}, named, order)
+    with zipfile.ZipFile(p) as z:
+        assert set(z.namelist()) == {"metadata.json", "config.json", "model.weights.npz"}
+    with np.load(__import__("io").BytesIO(zipfile.ZipFile(p).read("model.weights.npz")), allow_pickle=True) as w:
+        assert set(w.files) == {"layers/conv2d/vars", "layers/batch_normalization/vars", "layers/conv2d_transpose/vars"}
+        assert list(w["layers/batch_normalization/vars"].item().keys()) == ["0", "1"]
+    cfg, back = keras_io.load_keras(p)
+    assert cfg["filters"] == 16 and all(np.array_equal(back[n], named[n]) for n in order)
+    pb = "/root/reference/ImageJ Plugin/SEM_Particle_Segmentation_Models/TiO2_UNet_Masks_GAN.pb"
+    if os.path.exists(pb):
+        from oracle import pb_reader
+        spec = OU.UNetSpec(16)
+        ours = keras_io.read_pb_weights(pb, spec.names())
+        ref = pb_reader.unet_params_from_pb(pb)
+        assert all(np.array_equal(ours[n], ref[n]) for n in spec.names())

@@ -340,3 +340,58 @@ def test_full_image_iou_on_the_reference_dataset(dtype, gan_weights):
         assert all(v["mask_mismatches"] == 0 for v in mism.values()), mism
     else:
         assert all(v["mask_mismatches"] < 0.005 * v["pixels"] for v in mism.values()), mism
+
+
+def test_predict_tiled_equals_host_tiling(gan_weights):
+    """UNetModel.predict_tiled (device gather -> batched forward -> device stitch) == tile_image -> predict -> stitch_image."""
+    from sem_b200 import HelperFunctions as HF
+    with np.load(os.path.join(GOLD, "sem_crops.npz")) as z:
+        c = z["crops"].astype(np.float32)
+    img = np.concatenate([np.concatenate([c[0], c[1]], 1), np.concatenate([c[2], c[3]], 1)], 0)[:450, :500]
+    img = ((img - img.min()) / (img.max() - img.min()))[:, :, None]
+    m = UNetModel((128, 128, 1), 16, dtype="f32", batch_size=8)
+    m.set_named_weights(gan_weights)
+    for mode in (2, 1, 0):
+        got = m.predict_tiled(img, 128, 128, min_overlap=2, manage_overlap_mode=mode, batch_size=8)
+        tiles = HF.tile_image(img, 128, 128, min_overlap=2)
+        ref = HF.stitch_image(m.predict(tiles, batch_size=8), img.shape[1], img.shape[0], min_overlap=2, manage_overlap_mode=mode)
+        assert got.shape == ref.shape and np.abs(got - ref).max() < 1e-6, mode
+
+
+def test_reference_static_layer_functions_build_a_running_graph():
+    """UNet.multi_res_block / res_path / conv2d_bn / ReflectionPadding2D called like the reference calls them (on a symbolic
+    Input), wrapped in keras_compat.Model: forward in training mode against the same composition of the oracle's blocks."""
+    from sem_b200 import UNet_Segmentation as US, keras_compat as K
+    n, h, w = 2, 30, 26
+    inputs = K.Input(shape=(h, w, 1), batch_size=n, dtype="f32")
+    x = K.ReflectionPadding2D(padding=(6, 2))(inputs)            # -> 32 x 32
+    x = US.UNet.multi_res_block(16, x)
+    x = US.UNet.res_path(16, 2, x)
+    y = US.UNet.conv2d_bn(x, 1, 1, 1, activation="sigmoid")
+    assert y.shape == (None, 32, 32, 1)
+    model = K.Model(inputs, y)
+    e = model.eng
+    g = torch.Generator().manual_seed(5)
+    params = {}
+    for name in model.b.creation_names:
+        shp = e.specs[name].logical_shape
+        if name.endswith("/moving_variance"):
+            t = torch.rand(shp, generator=g) + 0.5
+        elif name.endswith("/kernel"):
+            t = torch.randn(shp, generator=g) * 0.3
+        else:
+            t = torch.randn(shp, generator=g) * 0.2 + (1.0 if name.endswith("/gamma") else 0.0)
+        params[name] = t
+        e.set_param(name, t.numpy())
+    xin = torch.rand(n, h, w, 1, generator=g)
+    got = model(xin.numpy(), training=True)
+    from oracle import layers as OL
+    ctx = OU._Ctx(params, True, {})
+    r = OL.reflection_pad(xin, 6, 2)
+    r = OU._mres(ctx, r)
+    r = OU._respath(ctx, 2, r)
+    r = OU._conv_bn(ctx, r, 1, "sigmoid")
+    assert U.rel_err(got, r) < 1e-3
+    assert len(model.get_weights()) == len(model.b.creation_names) and model.count_params() == sum(v.numel() for v in params.values())
+    with pytest.raises(NotImplementedError):
+        US.UNet.conv2d_bn(x, 8, 5, 5)
