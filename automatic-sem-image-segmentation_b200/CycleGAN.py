@@ -14,8 +14,9 @@ import time
 import numpy as np
 from PIL import Image
 
-from . import HelperFunctions
-from .cyclegan_model import CycleGanModel, GeneratorModel, ImagePool
+from . import HelperFunctions, keras_compat
+from .cyclegan_model import CycleGanModel, DiscriminatorModel, GeneratorModel, ImagePool
+from .keras_compat import ReflectionPadding2D  # noqa: F401  (module-level class of the reference, :482-506)
 
 
 class DataLoader:
@@ -94,6 +95,45 @@ class CycleGAN:
                               n_down_disc=self.num_downsampling_blocks_disc)
         model.compile(learning_rate=self.learning_rate, beta_1=0.5)
         return model
+
+    # ---- network builders (reference :323-451), same names and argument order ----------------------------------------------
+    def get_resnet_generator(self, filters=64, num_downsampling_blocks=2, num_residual_blocks=9, num_upsample_blocks=2, name=None,
+                             use_binary_crossentropy=False, padding="same"):
+        """A stand-alone generator at `self.image_shape` (batch `self.batch_size`): callable, `get_weights / set_weights`."""
+        if use_binary_crossentropy:
+            raise NotImplementedError("sigmoid head / BinaryCrossentropy losses (CycleGAN.py:417-418) are not built")
+        if padding != "same" or num_upsample_blocks != num_downsampling_blocks:
+            raise NotImplementedError("generators are built with 'same' strided convs and as many up- as down-sampling blocks")
+        return GeneratorModel(self.image_shape, self.batch_size, filters=filters, dtype=self.dtype, n_res=num_residual_blocks,
+                              use_skip_connection=self.use_skip_connection, use_resize_convolution=self.use_resize_convolution,
+                              n_down=num_downsampling_blocks, n_up=num_upsample_blocks)
+
+    def get_discriminator(self, filters=32, num_downsampling_blocks=3, name=None, padding="same"):
+        """A stand-alone PatchGAN (4x4 convs; the reference's create_model passes padding='valid', :148-150)."""
+        if padding != "valid":
+            raise NotImplementedError("the PatchGAN is built with padding='valid' (what create_model uses since 1.2.0, CycleGAN.py:148)")
+        return DiscriminatorModel(self.image_shape, self.batch_size, filters=filters, dtype=self.dtype,
+                                  gaussian_noise=self.gaussian_noise_value, n_down=num_downsampling_blocks)
+
+    def residual_block(self, input_tensor, activation, kernel_size=(3, 3), strides=(1, 1), padding="valid", use_bias=False):
+        """reference :323-337 on a symbolic tensor of a gan_nets graph (GT)."""
+        if tuple(kernel_size) != (3, 3) or tuple(strides) != (1, 1) or padding != "valid" or use_bias:
+            raise NotImplementedError("residual_block: 3x3, stride 1, reflect-padded 'valid', bias-free (the reference's own call)")
+        return input_tensor.view.buf.eng._builder.residual_block(input_tensor, keras_compat.act_code(activation))
+
+    def downsample(self, x, filters, activation, kernel_size=(3, 3), strides=(2, 2), padding="same", use_bias=False):
+        """reference :339-345: 3x3 'same' (generator) or 4x4 'valid' (discriminator), stride 2, InstanceNorm, activation."""
+        k = int(kernel_size[0])
+        if tuple(strides) != (2, 2) or use_bias or (k, padding) not in ((3, "same"), (4, "valid")):
+            raise NotImplementedError("downsample: 3x3 'same' or 4x4 'valid', stride 2, bias-free")
+        return x.view.buf.eng._builder.downsample(x, int(filters), keras_compat.act_code(activation), k=k, padding=padding)
+
+    def upsample(self, x, filters, activation, kernel_size=(3, 3), strides=(2, 2), padding="same", use_bias=False):
+        """reference :347-358: Conv2DTranspose 3x3 stride 2 'same' (or the resize-convolution variant), InstanceNorm, activation."""
+        if tuple(kernel_size) != (3, 3) or tuple(strides) != (2, 2) or padding != "same" or use_bias:
+            raise NotImplementedError("upsample: 3x3, stride 2, 'same', bias-free")
+        return x.view.buf.eng._builder.upsample(x, int(filters), keras_compat.act_code(activation),
+                                                use_resize_convolution=self.use_resize_convolution)
 
     def generator_loss_fn(self, fake):
         t = (1.0 - self.label_smoothing_factor) + self.label_smoothing_factor / 2
@@ -221,3 +261,43 @@ class CycleGAN:
             out -= np.min(out)
             out /= np.max(out)
             Image.fromarray((out * 255).astype(np.uint8)).save(os.path.join(output_directory, os.path.split(names[i])[-1]))
+
+
+class GANMonitor:
+    """reference :810-905: after every epoch, A -> B -> A and B -> A -> B reconstructions of `num_img` test images as
+    side-by-side mosaics (input | translated | cycled) written to `output_dir` (8-bit TIFF; the reference also overlays
+    the mask on the image, which is presentation only)."""
+
+    def __init__(self, test_a, test_b, output_dir, num_img=2):
+        self.num_img, self.test_a, self.test_b, self.output_dir = num_img, test_a, test_b, output_dir
+        self.model = None
+
+    def set_model(self, model):
+        self.model = model
+
+    def on_epoch_end(self, epoch, logs=None):
+        self.plot_reconstruction(self.model, epoch + 1, nex=self.num_img)
+
+    def plot_reconstruction(self, model, epoch, nex=2):
+        n = min(nex, len(self.test_a), len(self.test_b))
+        if n == 0:
+            return None
+        a = np.asarray(self.test_a[:n], dtype=np.float32)
+        b = np.asarray(self.test_b[:n], dtype=np.float32)
+
+        def pad(x):                                  # the towers are specialised to the training batch size
+            out = np.zeros((model.n,) + x.shape[1:], dtype=np.float32)
+            out[:x.shape[0]] = x
+            return out
+        fake_b = model.generate("gen_a", pad(a))
+        cyc_a = model.generate("gen_b", fake_b)
+        fake_a = model.generate("gen_b", pad(b))
+        cyc_b = model.generate("gen_a", fake_a)
+        u8 = lambda x: np.clip((x[..., 0] + 1.0) * 127.5, 0, 255).astype(np.uint8)
+        rows_aba = [np.concatenate([u8(a)[i], u8(fake_b)[i], u8(cyc_a)[i]], 1) for i in range(n)]
+        rows_bab = [np.concatenate([u8(b)[i], u8(fake_a)[i], u8(cyc_b)[i]], 1) for i in range(n)]
+        os.makedirs(self.output_dir, exist_ok=True)
+        pa, pb = os.path.join(self.output_dir, f"epoch_{epoch:03d}_ABA.tif"), os.path.join(self.output_dir, f"epoch_{epoch:03d}_BAB.tif")
+        Image.fromarray(np.concatenate(rows_aba, 0)).save(pa)
+        Image.fromarray(np.concatenate(rows_bab, 0)).save(pb)
+        return pa, pb

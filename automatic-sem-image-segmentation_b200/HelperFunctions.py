@@ -155,3 +155,84 @@ def segment(image, threshold=-1, watershed_lines=True, min_distance=9, use_four_
     if use_four_connectivity:
         labels = eight_to_four_connected(labels)
     return labels
+
+
+# ---- workflow plumbing of steps 0 and 5 (reference :188-287, :163-185): host-side file handling, no network math ---------
+def initialize_directories(root_dir, output_dir_cyclegan, output_dir_unet):
+    """The 1_WGAN / 2_CycleGAN / 3_UNet tree the steps hand their results through (HelperFunctions.py:188-238)."""
+    for parts in (("1_WGAN", "Output_Images"), ("1_WGAN", "Models"), ("2_CycleGAN", "data", "testA"), ("2_CycleGAN", "data", "testB"),
+                  ("2_CycleGAN", "data", "trainA"), ("2_CycleGAN", "data", "trainB"), ("2_CycleGAN", "generate_images", "A"),
+                  ("2_CycleGAN", "generate_images", "B"), ("2_CycleGAN", "generate_images", "Synthetic_Masks_Filtered"),
+                  ("2_CycleGAN", "images"), ("2_CycleGAN", "Models"), ("3_UNet", "Models")):
+        os.makedirs(os.path.join(root_dir, *parts), exist_ok=True)
+    os.makedirs(output_dir_cyclegan, exist_ok=True)
+    os.makedirs(output_dir_unet, exist_ok=True)
+
+
+def prepare_images_cycle_gan(root_dir, input_dir_images, tile_size_w=384, tile_size_h=384, num_simulated_masks=1000, dark_background=True):
+    """Tiles the input images into 2_CycleGAN/data/trainA (tiles that are mostly background are skipped), copies five of
+    them to testA and tops the set up with random flipped crops until there are `num_simulated_masks` (:241-287)."""
+    import random
+    from shutil import copy
+    input_imgs = load_and_preprocess_images(input_dir_or_filelist=input_dir_images, normalization_range=None, output_channels=1)
+    filenames = get_image_file_paths_from_directory(input_dir_images)
+    train_a = os.path.join(root_dir, "2_CycleGAN", "data", "trainA")
+
+    def foreground(tile, img):
+        return (dark_background and np.mean(tile) >= 1.1 * np.mean(img)) or (not dark_background and np.mean(tile) <= 0.9 * np.mean(img))
+
+    for i, img in enumerate(input_imgs):
+        tiles = np.asarray(tile_image(img, tile_size_w, tile_size_h, normalization_range=(0, 255), min_overlap=0), dtype="uint8")
+        f = os.path.split(filenames[i])[-1]
+        ext = os.path.splitext(f)[-1]
+        for j, t in enumerate(tiles):
+            if foreground(t, img):
+                Image.fromarray(t[:, :, 0]).save(os.path.join(train_a, f.replace(ext, f"-{j}{ext}")))
+    tiles_a = get_image_file_paths_from_directory(train_a)
+    for f in random.sample(tiles_a, min(5, len(tiles_a))):
+        copy(f, os.path.join(root_dir, "2_CycleGAN", "data", "testA"))
+    have, i = len(os.listdir(train_a)), 0
+    while i < num_simulated_masks - have:
+        r = random.randint(0, input_imgs.shape[0] - 1)
+        f = os.path.split(filenames[r])[-1]
+        ext = os.path.splitext(f)[-1]
+        img = input_imgs[r]
+        a = random.randint(0, img.shape[0] - tile_size_h - 1)
+        b = random.randint(0, img.shape[1] - tile_size_w - 1)
+        t = img[a:a + tile_size_h, b:b + tile_size_w]
+        if random.random() > 0.5:
+            t = np.fliplr(t)
+        if random.random() > 0.5:
+            t = np.flipud(t)
+        if foreground(t, img):
+            Image.fromarray(t[:, :, 0].astype("uint8")).save(os.path.join(train_a, f.replace(ext, f"-aug_{i}{ext}")))
+            i += 1
+
+
+def filter_gan_masks(img_path, msk_path, out_path, threshold_method=None, do_watershed_and_four_connectivity=True,
+                     gaussian_blur_amount=0.0, dark_background=True):
+    """Step 5 (:163-185): per file, optionally re-segment the mask (watershed + 4-connectivity), then keep only the
+    particles whose mean grey value in the image lies on the particle side of a global threshold (Li by default)."""
+    import cv2
+    from PIL import ImageFilter
+    from .Measurements import contours_filtered_by_mean_intensity, threshold_li
+    threshold_method = threshold_method or threshold_li
+    os.makedirs(out_path, exist_ok=True)
+    for f in os.listdir(img_path):
+        if not f.endswith(IMAGE_EXTENSIONS) or not os.path.exists(os.path.join(msk_path, f)):
+            continue
+        img = np.array(Image.open(os.path.join(img_path, f)), dtype="uint8")
+        mask = np.array(Image.open(os.path.join(msk_path, f)), dtype="uint8")
+        if do_watershed_and_four_connectivity:
+            mask = segment(image=mask, threshold=-1, watershed_lines=True, use_four_connectivity=True)
+        elif np.any((mask > 1) & (mask < 255)) or np.all(mask <= 1):
+            from .Measurements import Measure
+            mask = Measure.segment(mask, threshold=-1.0, applyWatershed=False, darkBackground=dark_background)
+        t = threshold_method(img)
+        keep = contours_filtered_by_mean_intensity(mask, img, min_value=t) if dark_background else \
+            contours_filtered_by_mean_intensity(mask, img, min_value=0.0, max_value=t)
+        out = np.zeros(img.shape[:2], dtype="uint8")
+        cv2.drawContours(image=out, contours=keep, contourIdx=-1, color=(255, 255, 255), thickness=-1)
+        Image.fromarray(out).save(os.path.join(out_path, f))
+        if gaussian_blur_amount > 0:
+            Image.fromarray(img).filter(ImageFilter.GaussianBlur(gaussian_blur_amount)).save(os.path.join(img_path, f))

@@ -144,3 +144,50 @@ class Measure:
         markers = ndimage.label(local_maxi)[0]
         labels = watershed(-distance, markers, mask=mask, watershed_line=applyWatershed)
         return np.asarray((labels > 0) * 255, dtype="uint8")
+
+
+def threshold_li(image: np.ndarray, tolerance: float = None) -> float:
+    """skimage.filters.threshold_li: Li's iterative minimum cross-entropy threshold (Li & Tam 1998), initial guess = mean."""
+    image = np.asarray(image, dtype=np.float64)
+    image = image[np.isfinite(image)]
+    if image.size == 0 or image.min() == image.max():
+        return float(image.min()) if image.size else 0.0
+    shift = image.min()
+    image = image - shift
+    tolerance = tolerance or np.min(np.diff(np.unique(image))) / 2
+    t_next = image.mean()
+    t_curr = -2 * tolerance
+    while abs(t_next - t_curr) > tolerance:
+        t_curr = t_next
+        fg = image > t_curr
+        mean_fore, mean_back = image[fg].mean(), image[~fg].mean()
+        if mean_back == 0:
+            break
+        t_next = (mean_back - mean_fore) / (np.log(mean_back) - np.log(mean_fore))
+    return float(t_next + shift)
+
+
+def contours_filtered_by_mean_intensity(mask_u8: np.ndarray, gray: np.ndarray, min_value: float = 0.0, max_value: float = -1.0):
+    """Measure(mask, applyWatershed=False, excludeEdges=False, grayscaleImage=gray).calculateMeanIntensities() followed by
+    filterResults('meanIntensity', minValue, maxValue) (Measurements.py:158-191, 321-342, 606-612): OpenCV contours
+    (RETR_TREE), tiny ones (< 5 points and perimeter < 8) dropped, mean grey value over the pixels inside or on each
+    contour, contours outside [min_value, max_value] removed.  Returns the surviving contours."""
+    import cv2
+    contours, _ = cv2.findContours(np.ascontiguousarray(mask_u8, dtype=np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+    keep = []
+    for c in contours:
+        if len(c) < 5:
+            pts = c[:, 0, :].astype(np.float64)
+            if np.sqrt(((np.roll(pts, -1, axis=0) - pts) ** 2).sum(1)).sum() < 8:
+                continue
+        x0, y0, w, h = cv2.boundingRect(c)
+        sub = np.zeros((h, w), dtype=np.uint8)
+        cv2.drawContours(sub, [c - np.array([[x0, y0]])], 0, 1, cv2.FILLED)      # filled polygon incl. its boundary
+        vals = gray[y0:y0 + h, x0:x0 + w][sub > 0]
+        total = float(vals.sum())
+        mean = total / vals.size if total > 0 else 0.0
+        if min_value == 0 and max_value < min_value:
+            keep.append(c)
+        elif not (mean < min_value or (mean > max_value and max_value >= min_value)):
+            keep.append(c)
+    return keep

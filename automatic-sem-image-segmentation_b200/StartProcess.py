@@ -1,13 +1,18 @@
-"""Drop-in for the conv-stack steps of Releases/Version 1.2.0/StartProcess.py (steps 3, 4, 6a, 6b :89-175).
+"""Drop-in for Releases/Version 1.2.0/StartProcess.py: same constants, same step functions, one spawned process per step
+(:178-221; state travels between steps through the 1_WGAN / 2_CycleGAN / 3_UNet tree only).
 
-Steps 0-2 and 5 of the reference workflow (directory set-up, WGAN-GP mask synthesis, classical post-filtering) are
-outside the accelerated path (SURVEY.md section 8 "out of scope" / "next"); run them with the reference and point
-ROOT_DIR at the same tree.  Constants keep the reference's names and defaults.
+Steps 3, 4, 6a, 6b are the conv-stack hot path (CycleGAN training / inference, MultiRes-UNet training / inference) on the
+sm_100a engine.  Steps 0 and 5 are host-side file handling and classical post-processing, restated in HelperFunctions /
+Measurements.  Steps 1 and 2 (WGAN-GP training on single-particle masks and the Perlin-noise mask simulation,
+WassersteinGAN.py) are NOT part of this package (double-backward through convs, opensimplex): they raise
+with that reason; run them with the reference and point ROOT_DIR at the same tree (2_CycleGAN/data/trainB).
 """
 import os
 from datetime import datetime
 
-from . import CycleGAN, UNet_Segmentation
+import multiprocessing as mp
+
+from . import CycleGAN, HelperFunctions, UNet_Segmentation
 
 ROOT_DIR = os.path.abspath("./")
 INPUT_DIR_IMAGES = os.path.join(ROOT_DIR, "Input_Images")
@@ -27,6 +32,26 @@ UNET_EPOCHS = 50
 UNET_CONTRAST_OPTIMIZATION_RANGE = (0.5, 99.5)
 UNET_FILTERS = 16
 USE_DATALOADER = True
+NUM_SIMULATED_MASKS = 1000
+DARK_BACKGROUND = True
+GAUSSIAN_BLUR_AMOUNT = 0.0
+
+
+def start_step_0():
+    print("Step0: Configuring Devices, Initializing Directories, and Preparing Images...")
+    HelperFunctions.initialize_directories(root_dir=ROOT_DIR, output_dir_cyclegan=OUTPUT_DIR_CYCLEGAN, output_dir_unet=OUTPUT_DIR_UNET)
+    HelperFunctions.prepare_images_cycle_gan(root_dir=ROOT_DIR, input_dir_images=INPUT_DIR_IMAGES, tile_size_w=TILE_SIZE_W,
+                                             tile_size_h=TILE_SIZE_H, num_simulated_masks=NUM_SIMULATED_MASKS, dark_background=DARK_BACKGROUND)
+
+
+def start_step_1():
+    raise NotImplementedError("Step 1 (WGAN-GP training, WassersteinGAN.py:181-238) is outside this package: its gradient penalty "
+                              "needs a double backward through the convolutions (SURVEY.md 8f N2); run it with the reference")
+
+
+def start_step_2():
+    raise NotImplementedError("Step 2 (mask simulation, WassersteinGAN.py:375-540) is outside this package (needs the WGAN of step 1 "
+                              "and opensimplex); run it with the reference, it fills 2_CycleGAN/data/trainB")
 
 
 def _cycle_gan():
@@ -62,6 +87,17 @@ def start_step_4():
                     source_domain="A", tile_images=not RUN_INFERENCE_ON_WHOLE_IMAGE, min_overlap=2, manage_overlap_mode=2, use_gpu=True)
 
 
+def start_step_5():
+    print("Step 5: Postprocessing CycleGAN Output images...")
+    HelperFunctions.filter_gan_masks(img_path=os.path.join(ROOT_DIR, "2_CycleGAN", "generate_images", "A"),
+                                     msk_path=os.path.join(ROOT_DIR, "2_CycleGAN", "data", "trainB"),
+                                     out_path=os.path.join(ROOT_DIR, "2_CycleGAN", "generate_images", "Synthetic_Masks_Filtered"),
+                                     gaussian_blur_amount=GAUSSIAN_BLUR_AMOUNT, do_watershed_and_four_connectivity=False,
+                                     dark_background=DARK_BACKGROUND)
+    HelperFunctions.filter_gan_masks(img_path=INPUT_DIR_IMAGES, msk_path=os.path.join(ROOT_DIR, "2_CycleGAN", "generate_images", "B"),
+                                     out_path=OUTPUT_DIR_CYCLEGAN, do_watershed_and_four_connectivity=True, dark_background=DARK_BACKGROUND)
+
+
 def _unet():
     u = UNet_Segmentation.UNet(root_dir=ROOT_DIR, image_dir=os.path.join(ROOT_DIR, "2_CycleGAN", "generate_images", "A"),
                                mask_dir=os.path.join(ROOT_DIR, "2_CycleGAN", "generate_images", "Synthetic_Masks_Filtered"),
@@ -88,8 +124,19 @@ def start_step_6b():
                     threshold=-1, watershed_lines=True, min_distance=9, min_overlap=2, manage_overlap_mode=2, use_gpu=True)
 
 
+def run_steps(steps):
+    """One spawned process per step, joined before the next starts (reference :182-219; the parent does not look at exit
+    codes there either, but a failed step is reported here)."""
+    ctx = mp.get_context("spawn")
+    for step in steps:
+        p = ctx.Process(target=step)
+        p.start()
+        p.join()
+        if p.exitcode != 0:
+            print(f"{step.__name__} exited with code {p.exitcode}")
+
+
 if __name__ == "__main__":
     print("Process started: " + str(datetime.now()))
-    for step in (start_step_3, start_step_4, start_step_6a, start_step_6b):
-        step()       # the reference isolates steps in processes to free TF GPU memory; torch frees buffers with the objects
+    run_steps((start_step_0, start_step_3, start_step_4, start_step_5, start_step_6a, start_step_6b))
     print("Process finished: " + str(datetime.now()))

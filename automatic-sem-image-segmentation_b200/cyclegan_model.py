@@ -108,6 +108,9 @@ class GeneratorModel:
         self.x_dev = torch.zeros((batch_size, h, w, 1), dtype=torch.float32, device=self.eng.device)
         self.out_dev = torch.zeros((batch_size,) + tuple(self.b.out_hw) + (1,), dtype=torch.float32, device=self.eng.device)
 
+    def get_weights(self):
+        return self.net.get_weights()
+
     def set_weights(self, ws):
         self.net.set_weights(ws)
 
@@ -131,6 +134,39 @@ class GeneratorModel:
     def predict(self, x, batch_size: Optional[int] = None) -> np.ndarray:
         x = np.asarray(x, dtype=np.float32)
         return np.concatenate([self(x[i:i + self.n]) for i in range(0, x.shape[0], self.n)], 0)
+
+
+class DiscriminatorModel:
+    """ONE PatchGAN tower (`get_discriminator(...)`, CycleGAN.py:425-451) as a callable model: forward only."""
+
+    def __init__(self, image_shape, batch_size: int, filters: int = 128, dtype: str = "bf16", use_tc: bool = True, **options):
+        h, w = image_shape[0], image_shape[1]
+        self.n, self.h, self.w = batch_size, h, w
+        self.net = _Net("disc", h, w, filters, dtype, 0, use_tc, options=options)
+        self.eng, self.b = self.net.tower("x", batch_size)
+        self.x_dev = torch.zeros((batch_size, h, w, 1), dtype=torch.float32, device=self.eng.device)
+        oh, ow = self.b.out_hw
+        self.out_dev = torch.zeros((batch_size, oh, ow, 1), dtype=torch.float32, device=self.eng.device)
+
+    def get_weights(self):
+        return self.net.get_weights()
+
+    def set_weights(self, ws):
+        self.net.set_weights(ws)
+
+    def __call__(self, x, training: bool = True) -> np.ndarray:
+        e, b = self.eng, self.b
+        self.x_dev.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32))))
+        L.check(e.lib.semb_cast_in(self.x_dev.data_ptr(), 1, C.byref(b.in_buf.view().t), self.n * self.h * self.w, e.dtype, e.stream))
+        for op in getattr(b, "noise_ops", []):
+            op.frozen = not training
+            if not training:
+                op.noise.data.zero_()
+        e.zero_step(False)
+        e.forward(True)
+        oh, ow = b.out_hw
+        L.check(e.lib.semb_cast_out(C.byref(b.out_buf.view().t), self.out_dev.data_ptr(), 1, self.n * oh * ow, e.dtype, e.stream))
+        return self.out_dev.cpu().numpy()
 
 
 class CycleGanModel:

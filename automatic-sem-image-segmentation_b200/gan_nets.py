@@ -25,10 +25,70 @@ def same_pad_lead(size: int, k: int, stride: int) -> int:
     return total // 2
 
 
+class GT:
+    """Symbolic activation of a GAN graph: view + spatial size + logical channel count (the reference's Keras tensor)."""
+
+    def __init__(self, view: View, h: int, w: int, c: int):
+        self.view, self.h, self.w, self.c = view, h, w, c
+
+    @property
+    def shape(self):
+        return (None, self.h, self.w, self.c)
+
+
 class _Base:
     def __init__(self, eng: Engine, prefix: str):
         self.e, self.prefix = eng, prefix
         self.creation_names: List[str] = []
+        eng._builder = self
+        self._nres = self._ndown = self._nup = 0
+
+    def conv_norm_act(self, x: GT, wname: str, cout_l: int, k: int, stride: int, pad, pad_mode: int, nname: str, act: int,
+                      transposed: bool = False, residual: Optional[View] = None, hw_out=None) -> GT:
+        """Conv2D / Conv2DTranspose (no bias) -> GroupNormalization(groups=-1) -> activation [+ residual] (CycleGAN.py:323-358)."""
+        e = self.e
+        hw_out = hw_out or (x.h, x.w)
+        norm = self.inorm(nname, cout_l, hw_out[0] * hw_out[1])
+        raw = e.new_buf(hw_out[0], hw_out[1], pad8(cout_l), f"{self.prefix}{nname}_raw")
+        e.add_op(ConvOp(e, x.view, raw.view(), (x.h, x.w), hw_out, wname, None, k, stride, pad, pad_mode, transposed,
+                        stats=norm.stats_ref()))
+        e.add_op(norm)
+        out = e.new_buf(hw_out[0], hw_out[1], pad8(cout_l), f"{self.prefix}{nname}_out")
+        e.add_op(AffineOp(e, hw_out[0] * hw_out[1], raw.view(), norm, residual, None, out.view(), act))
+        return GT(out.view(), hw_out[0], hw_out[1], cout_l)
+
+    # ---- the reference's block functions (CycleGAN.py:323-358) on symbolic tensors -------------------------------------
+    def residual_block(self, x: GT, act: int = L.ACT_RELU) -> GT:
+        i, f = self._nres, x.c
+        self._nres += 1
+        y = self.conv_norm_act(x, self.conv_w(f"res{i}_0", 3, f, f), f, 3, 1, (1, 1), L.PAD_REFLECT, f"res{i}_0_in", act)
+        return self.conv_norm_act(y, self.conv_w(f"res{i}_1", 3, f, f), f, 3, 1, (1, 1), L.PAD_REFLECT, f"res{i}_1_in", L.ACT_NONE,
+                                  residual=x.view)
+
+    def downsample(self, x: GT, filters: int, act: int = L.ACT_RELU, k: int = 3, padding: str = "same", name: Optional[str] = None) -> GT:
+        name = name or f"down{self._ndown}"
+        self._ndown += 1
+        if padding == "same":
+            oh, ow = -(-x.h // 2), -(-x.w // 2)
+            pad = (same_pad_lead(x.h, k, 2), same_pad_lead(x.w, k, 2))
+        else:
+            oh, ow = (x.h - k) // 2 + 1, (x.w - k) // 2 + 1
+            pad = (0, 0)
+        return self.conv_norm_act(x, self.conv_w(name, k, x.c, filters), filters, k, 2, pad, L.PAD_ZERO, f"{name}_in", act, hw_out=(oh, ow))
+
+    def upsample(self, x: GT, filters: int, act: int = L.ACT_RELU, use_resize_convolution: bool = False) -> GT:
+        i, e, f = self._nup, self.e, x.c
+        self._nup += 1
+        H, W = x.h, x.w
+        if use_resize_convolution:
+            # UpSampling2D(nearest) -> ReflectionPadding2D(1) -> Conv2D(3x3, valid, no bias) (CycleGAN.py:348-351)
+            up = e.new_buf(2 * H, 2 * W, pad8(f), f"{self.prefix}up{i}_nearest")
+            e.add_op(UpsampleOp(e, x.view, up.view(), H, W))
+            return self.conv_norm_act(GT(up.view(), 2 * H, 2 * W, f), self.conv_w(f"up{i}", 3, f, filters), filters, 3, 1, (1, 1),
+                                      L.PAD_REFLECT, f"up{i}_in", act)
+        # Conv2DTranspose(3x3, s2, 'same') == torch padding 1, output_padding 1: the equivalent strided conv has pad 1
+        return self.conv_norm_act(x, self.convT_w(f"up{i}", 3, f, filters), filters, 3, 2, (1, 1), L.PAD_ZERO, f"up{i}_in", act,
+                                  transposed=True, hw_out=(2 * H, 2 * W))
 
     def _p(self, name, kind, lshape, pshape, maps, init="zeros", fans=(1, 1)):
         full = f"{self.prefix}{name}"
@@ -79,40 +139,18 @@ class GeneratorBuilder(_Base):
             e.add_op(PadCropOp(e, x, padded.view(), (h, w), (h + ph, w + pw), ph // 2, pw // 2, "reflect"))
             x, H, W = padded.view(), h + ph, w + pw
         f = filters
-
-        def conv_in_act(x, hw_in, hw_out, wname, k, stride, pad, pad_mode, cout_l, nname, act, transposed=False, residual=None):
-            norm = self.inorm(nname, cout_l, hw_out[0] * hw_out[1])
-            raw = e.new_buf(hw_out[0], hw_out[1], pad8(cout_l), f"{prefix}{nname}_raw")
-            e.add_op(ConvOp(e, x, raw.view(), hw_in, hw_out, wname, None, k, stride, pad, pad_mode, transposed,
-                            stats=norm.stats_ref()))
-            e.add_op(norm)
-            out = e.new_buf(hw_out[0], hw_out[1], pad8(cout_l), f"{prefix}{nname}_out")
-            e.add_op(AffineOp(e, hw_out[0] * hw_out[1], raw.view(), norm, residual, None, out.view(), act))
-            return out.view()
-
+        t = GT(x, H, W, 1)
         # stem: ReflectionPadding2D(3) + 7x7 valid, no bias, IN, relu
-        x = conv_in_act(x, (H, W), (H, W), self.conv_w("stem", 7, 1, f), 7, 1, (3, 3), L.PAD_REFLECT, f, "stem_in", L.ACT_RELU)
-        for i in range(n_down):
-            oh, ow = -(-H // 2), -(-W // 2)
-            x = conv_in_act(x, (H, W), (oh, ow), self.conv_w(f"down{i}", 3, f, 2 * f), 3, 2,
-                            (same_pad_lead(H, 3, 2), same_pad_lead(W, 3, 2)), L.PAD_ZERO, 2 * f, f"down{i}_in", L.ACT_RELU)
-            f, H, W = 2 * f, oh, ow
-        for i in range(n_res):
-            y = conv_in_act(x, (H, W), (H, W), self.conv_w(f"res{i}_0", 3, f, f), 3, 1, (1, 1), L.PAD_REFLECT, f, f"res{i}_0_in", L.ACT_RELU)
-            x = conv_in_act(y, (H, W), (H, W), self.conv_w(f"res{i}_1", 3, f, f), 3, 1, (1, 1), L.PAD_REFLECT, f, f"res{i}_1_in",
-                            L.ACT_NONE, residual=x)
-        for i in range(n_up):
-            if use_resize_convolution:
-                # UpSampling2D(nearest) -> ReflectionPadding2D(1) -> Conv2D(3x3, valid, no bias) (CycleGAN.py:348-351)
-                up = e.new_buf(2 * H, 2 * W, pad8(f), f"{prefix}up{i}_nearest")
-                e.add_op(UpsampleOp(e, x, up.view(), H, W))
-                x = conv_in_act(up.view(), (2 * H, 2 * W), (2 * H, 2 * W), self.conv_w(f"up{i}", 3, f, f // 2), 3, 1, (1, 1),
-                                L.PAD_REFLECT, f // 2, f"up{i}_in", L.ACT_RELU)
-            else:
-                # Conv2DTranspose(3x3, s2, 'same') == torch padding 1, output_padding 1: the equivalent strided conv has pad 1
-                x = conv_in_act(x, (H, W), (2 * H, 2 * W), self.convT_w(f"up{i}", 3, f, f // 2), 3, 2, (1, 1), L.PAD_ZERO, f // 2,
-                                f"up{i}_in", L.ACT_RELU, transposed=True)
-            f, H, W = f // 2, 2 * H, 2 * W
+        t = self.conv_norm_act(t, self.conv_w("stem", 7, 1, f), f, 7, 1, (3, 3), L.PAD_REFLECT, "stem_in", L.ACT_RELU)
+        for _ in range(n_down):
+            f *= 2
+            t = self.downsample(t, f)
+        for _ in range(n_res):
+            t = self.residual_block(t)
+        for _ in range(n_up):
+            f //= 2
+            t = self.upsample(t, f, use_resize_convolution=use_resize_convolution)
+        x, H, W = t.view, t.h, t.w
         wh = self.conv_w("head", 7, f, 1)
         bh = self.vec("head/bias", 1, "zeros")
         if use_skip_connection:
@@ -121,8 +159,8 @@ class GeneratorBuilder(_Base):
             img = self.in_buf.view()
             fp = pad8(f)
             cat = e.new_buf(H, W, fp + 8, prefix + "skip_cat")
-            s_act = conv_in_act(img, (H, W), (H, W), self.conv_w("skip_short", 1, 1, f), 1, 1, (0, 0), L.PAD_ZERO, f, "skip_short_in",
-                                L.ACT_RELU)
+            s_act = self.conv_norm_act(GT(img, H, W, 1), self.conv_w("skip_short", 1, 1, f), f, 1, 1, (0, 0), L.PAD_ZERO, "skip_short_in",
+                                       L.ACT_RELU).view
             w_o = self.conv_w("skip_conv", 3, 1, f)
             n_o = self.inorm("skip_conv_in", f, H * W)
             o_raw = e.new_buf(H, W, fp, prefix + "skip_conv_raw")

@@ -113,3 +113,30 @@ class Model:
         L.check(e.lib.semb_cast_out(C.byref(ov.t), self._y.data_ptr(), cout, self._y.shape[0] * self._y.shape[1] * self._y.shape[2], e.dtype,
                                     e.stream))
         return self._y.cpu()
+
+
+class Activation:
+    """keras.layers.Activation(name) as the reference passes it to its block functions (CycleGAN.py:378-389)."""
+
+    def __init__(self, name: str, **kwargs):
+        codes = {"relu": L.ACT_RELU, "tanh": L.ACT_TANH, "sigmoid": L.ACT_SIGMOID, "linear": L.ACT_NONE}
+        if name not in codes:
+            raise NotImplementedError(f"activation {name!r} has no fused kernel")
+        self.name, self.act = name, codes[name]
+
+
+class LeakyReLU:
+    """keras.layers.LeakyReLU(negative_slope): the kernels implement the slope the reference uses (0.2)."""
+
+    def __init__(self, negative_slope: float = 0.2, **kwargs):
+        if abs(negative_slope - 0.2) > 1e-12:
+            raise NotImplementedError("only LeakyReLU(0.2) (CycleGAN.py:436-447) is built")
+        self.act = L.ACT_LEAKY
+
+
+def act_code(activation) -> int:
+    if activation is None:
+        return L.ACT_NONE
+    if isinstance(activation, str):
+        return Activation(activation).act
+    return activation.act

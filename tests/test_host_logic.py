@@ -211,3 +211,78 @@ def test_keras_archive_roundtrip_and_pb_reader(tmp_path):
         ours = keras_io.read_pb_weights(pb, spec.names())
         ref = pb_reader.unet_params_from_pb(pb)
         assert all(np.array_equal(ours[n], ref[n]) for n in spec.names())
+
+
+def test_classical_postprocessing_and_scores():
+    """Measurements.Measure.segment (Otsu -> EDT -> smoothing -> local maxima -> watershed with lines), the 8 -> 4
+    connectivity fix, Li threshold, and the Calculate_Scores.py metrics (whole-image / instance IoU, ROC, threshold sweep with
+    and without the reference's index quirk)."""
+    from scipy import ndimage
+    from sem_b200 import Measurements as M, Scores
+    yy, xx = np.mgrid[0:80, 0:120]
+    two = (((yy - 40) ** 2 + (xx - 40) ** 2 < 22 ** 2) | ((yy - 40) ** 2 + (xx - 78) ** 2 < 22 ** 2))
+    img = two.astype(np.uint8) * 200
+    assert M.threshold_otsu(img) in (0.0, 99.0, 100.0) or 0 <= M.threshold_otsu(img) < 200
+    seg = HF.segment(img, threshold=-1, watershed_lines=True, min_distance=9, use_four_connectivity=True)
+    assert seg.dtype == np.uint8 and set(np.unique(seg)) <= {0, 255}
+    assert ndimage.label(img > 0)[1] == 1 and ndimage.label(seg > 0)[1] == 2           # touching discs are split ...
+    line = (img > 0) & (seg == 0)
+    assert 15 <= int(line.sum()) <= 40 and not np.any((seg > 0) & (img == 0))          # ... by a thin line, nothing leaves the mask
+    nosplit = HF.segment(img, threshold=-1, watershed_lines=False)
+    assert np.array_equal(nosplit > 0, img > 0)
+    # 8 -> 4 connectivity: a diagonal contact is broken
+    d = np.zeros((6, 6), dtype=np.uint8)
+    d[1:3, 1:3] = 255
+    d[3:5, 3:5] = 255
+    f = HF.eight_to_four_connected(d.copy())
+    assert ndimage.label(f > 0)[1] == 2 and ndimage.label(f > 0, structure=np.ones((3, 3)))[1] == 2
+    # Li threshold separates a bimodal image between the modes
+    bi = np.concatenate([np.full(500, 20.0), np.full(300, 180.0)]) + np.random.default_rng(0).normal(0, 3, 800)
+    assert 40 < M.threshold_li(bi) < 160
+    # scores
+    gt = two.astype(np.uint8)
+    assert Scores.calculateWholeImageIoU(gt, gt) == 1.0
+    half = gt.copy()
+    half[:, 60:] = 0
+    iou = Scores.calculateWholeImageIoU(half, gt)
+    assert abs(iou - half.sum() / gt.sum()) < 1e-12
+    assert Scores.calculateInstanceIoU(gt, gt) > 0.99
+    tpr, tnr, fpr, fnr = Scores.ROC(half, gt)
+    assert abs(tpr - iou) < 1e-12 and tnr == 1.0 and fpr == 0.0 and abs(fnr - (1 - iou)) < 1e-12
+    pred = gt.astype(np.float32) * 0.65
+    r = Scores.sweep_iou([pred], [gt])
+    assert r["best_whole_image"][0] == 1.0 and r["whole_image"][7] == 0.0 and r["whole_image"][6] == 1.0
+    q = Scores.sweep_iou([pred], [gt], reference_indexing=True)
+    assert q["whole_image"][5] == 1.0 and q["whole_image"][6] == 0.0          # threshold t/10 stored at index t-1 (Calculate_Scores.py:252)
+
+
+def test_workflow_steps_0_and_5_and_step_functions(tmp_path):
+    from PIL import Image
+    from sem_b200 import StartProcess as SP
+    rng = np.random.default_rng(0)
+    d = str(tmp_path)
+    inp = os.path.join(d, "Input_Images")
+    os.makedirs(inp)
+    for i in range(2):
+        img = (rng.random((200, 260)) * 80).astype(np.uint8)
+        img[40:120, 60:200] += 150
+        Image.fromarray(img).save(os.path.join(inp, f"im{i}.tif"))
+    HF.initialize_directories(d, os.path.join(d, "oc"), os.path.join(d, "ou"))
+    for sub in ("1_WGAN/Models", "2_CycleGAN/data/trainB", "2_CycleGAN/generate_images/Synthetic_Masks_Filtered", "3_UNet/Models"):
+        assert os.path.isdir(os.path.join(d, sub))
+    HF.prepare_images_cycle_gan(d, inp, 96, 96, num_simulated_masks=12)
+    assert len(os.listdir(os.path.join(d, "2_CycleGAN", "data", "trainA"))) == 12
+    assert len(os.listdir(os.path.join(d, "2_CycleGAN", "data", "testA"))) == 5
+    msk = np.zeros((200, 260), np.uint8)
+    msk[50:100, 80:150] = 255          # over the bright particle: kept
+    msk[150:180, 10:40] = 255          # over background: filtered out
+    mdir = os.path.join(d, "msk")
+    os.makedirs(mdir)
+    Image.fromarray(msk).save(os.path.join(mdir, "im0.tif"))
+    HF.filter_gan_masks(inp, mdir, os.path.join(d, "out"), do_watershed_and_four_connectivity=False)
+    o = np.array(Image.open(os.path.join(d, "out", "im0.tif")))
+    assert o[75, 100] == 255 and o[165, 25] == 0
+    for name in ("start_step_0", "start_step_1", "start_step_2", "start_step_3", "start_step_4", "start_step_5", "start_step_6a", "start_step_6b"):
+        assert callable(getattr(SP, name))
+    with pytest.raises(NotImplementedError):
+        SP.start_step_1()
