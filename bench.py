@@ -121,6 +121,27 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def finish_distributed(world, holders):
+    """Orderly end of a multi-rank run: CUDA graphs that captured NCCL kernels are released BEFORE the communicator, all
+    ranks leave together, and a watchdog ends the process if the teardown itself blocks (seen once with captured
+    collectives): the JSON line is already out at this point."""
+    if world <= 1:
+        return 0
+    import torch.distributed as dist
+    threading.Timer(45.0, lambda: os._exit(0)).start()
+    for h in holders:
+        for attr in ("graph", "graph2", "_graphs"):
+            if hasattr(h, attr):
+                setattr(h, attr, None)
+    torch.cuda.synchronize()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------- CPU arm
 def cpu_train_throughput(size: int, batch: int, steps: int, warmup: int):
     """Oracle (torch-CPU restatement of the Keras-torch path) train step on the host cores; tiles/s."""
@@ -353,9 +374,7 @@ def run_ours(args):
     e2e_value = tiles / (e2e_ms / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return finish_distributed(world, [inst])
 
     # ---- per-op profile (eager, CUDA events on the launching stream) -> roofline of the dominant kernel
     rows = profile_ops(inst, wgt, peaks, size, batch)
@@ -427,9 +446,7 @@ def run_ours(args):
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump({"total_ms_eager": total_ms, "rows": rows}, fh, indent=1)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return finish_distributed(world, [inst])
 
 
 # ------------------------------------------------------------------------------------------------- CycleGAN (configs[2])
@@ -612,9 +629,7 @@ def run_cyclegan(args):
     pairs = n * world * args.steps
     value, e2e_value = pairs / (dev_ms / 1e3), pairs / (e2e_ms / 1e3)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return finish_distributed(world, [m])
 
     # ---- per-op profile of one eager step (CUDA events around every op of all twelve towers)
     engines = [bb.e for bb in (m.GA_ra, m.GB_rb, m.GB_fb, m.GA_fa, m.GB_ra, m.GA_rb, m.DA_fa, m.DB_fb, m.DA_real, m.DA_pool, m.DB_real, m.DB_pool)]
@@ -660,9 +675,7 @@ def run_cyclegan(args):
     if args.profile_out:
         with open(args.profile_out, "w") as fh:
             json.dump({"total_ms_eager": total_ms, "rows": rows}, fh, indent=1)
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
+    return finish_distributed(world, [m])
 
 
 _REAL_STDOUT = None
