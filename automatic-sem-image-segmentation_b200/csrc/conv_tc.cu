@@ -808,23 +808,6 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     return check_launch("conv_tc");
 }
 
-extern "C" int semb_conv2d_dgrad_tc_bnsums(const semb_conv_geom* g, const semb_tensor* dy, const void* w_packed, const semb_tensor* dx,
-                                           int32_t accumulate, const semb_bn_bwd_sums* bs, void* stream) {
-    SEMB_REQUIRE(g && dy && dx && w_packed && bs, SEMB_ESHAPE, "dgrad_tc_bnsums: null argument");
-    SEMB_REQUIRE(g->dtype == SEMB_BF16 && g->pad_mode == SEMB_PAD_ZERO, SEMB_ESHAPE, "dgrad_tc_bnsums: bf16 storage, zero padding only");
-    SEMB_REQUIRE(g->stride == 1 && ((g->R == 1 && g->S == 1) || (g->R == 3 && g->S == 3)), SEMB_ESHAPE,
-                 "dgrad_tc_bnsums: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
-    SEMB_REQUIRE(view_ok(dy) && view_ok(dx) && dy->C == g->Cin && dx->C == g->Cout, SEMB_EALIGN, "dgrad_tc_bnsums: bad tensor views");
-    SEMB_REQUIRE(g->N > 0 && g->OH > 0 && g->OW > 0 && g->pad_t >= 0 && g->pad_l >= 0 && g->pad_t < g->R + TILE_H && g->pad_l < g->S + TILE_W,
-                 SEMB_ESHAPE, "dgrad_tc_bnsums: bad geometry");
-    SEMB_REQUIRE(view_ok(&bs->z) && bs->scale && bs->shift && bs->mean && bs->sums && bs->c0 >= 0 && (bs->c0 % 8) == 0 &&
-                 bs->c0 + bs->z.C <= g->Cout && (bs->act == SEMB_ACT_NONE || bs->act == SEMB_ACT_RELU) && bs->cstride >= bs->z.C,
-                 SEMB_ESHAPE, "dgrad_tc_bnsums: bad normalisation record");
-    // the kernel indexes the sums by OUTPUT channel: shift the base so that channel c0 lands on sums[0]
-    double* base = reinterpret_cast<double*>(bs->sums) - bs->c0;
-    return conv_tma_launch(g, dy, w_packed, nullptr, dx, base, 0, bs->cstride, accumulate, stream, bs);
-}
-
 extern "C" int64_t semb_conv2d_wgrad_tc_workspace(const semb_conv_geom* g) {
     if (!g || g->dtype != SEMB_BF16 || g->stride != 1 || g->R != 3 || g->S != 3 || g->pad_mode != SEMB_PAD_ZERO || g->pad_t > 2 || g->pad_l > 2)
         return 0;

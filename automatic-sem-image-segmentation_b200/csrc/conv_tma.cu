@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
             asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
             for (int i = etid; i < NC; i += 128) {
                 const int c = c_begin + i;
-                if (c < a.Cout && (!a.bs_z || (c >= a.bs_c0 && c < a.bs_c1))) {
+                if (c < a.Cout) {
                     const float t1 = ((part[i] + part[NC + i]) + part[2 * NC + i]) + part[3 * NC + i];
                     const float t2 = ((part[4 * NC + i] + part[5 * NC + i]) + part[6 * NC + i]) + part[7 * NC + i];
                     double* st = a.stats + (size_t)n * a.stats_nstride + c;
@@ -263,8 +263,6 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
-                const bf16* zp = a.bs_z ? a.bs_z + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.bs_pitch + a.bs_coff - a.bs_c0
-                                        : nullptr;
                 mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
 #pragma unroll
@@ -282,32 +280,19 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
                         }
-                        if (a.accumulate && pvalid && cvalid) {
-                            float o[8];
-                            Vec8<bf16>::load(yp + c, o);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] += o[i];
-                        }
                         if (a.stats && pvalid && !(a.dbg & 8)) {
-                            if (a.bs_z) {
-                                if (c >= a.bs_c0 && c < a.bs_c1) {
-                                    float z[8];
-                                    Vec8<bf16>::load(zp + c, z);
-                                    const int pc = c - a.bs_c0;
 #pragma unroll
-                                    for (int i = 0; i < 8; ++i) {
-                                        const float u = fmaf(z[i], a.bs_scale[pc + i], a.bs_shift[pc + i]);
-                                        const float gq = a.bs_act == SEMB_ACT_RELU ? (u > 0.f ? v[i] : 0.f) : v[i];
-                                        s1[c + i] += gq;
-                                        s2[c + i] = fmaf(gq, z[i] - a.bs_mean[pc + i], s2[c + i]);
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) { s1[c + i] += v[i]; s2[c + i] = fmaf(v[i], v[i], s2[c + i]); }
-                            }
+                            for (int i = 0; i < 8; ++i) { s1[c + i] += v[i]; s2[c + i] = fmaf(v[i], v[i], s2[c + i]); }
                         }
-                        if (pvalid && cvalid && !(a.dbg & 4)) Vec8<bf16>::store(yp + c, v);
+                        if (pvalid && cvalid && !(a.dbg & 4)) {
+                            if (a.accumulate) {
+                                float o[8];
+                                Vec8<bf16>::load(yp + c, o);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] += o[i];
+                            }
+                            Vec8<bf16>::store(yp + c, v);
+                        }
                     }
                 }
                 tc_fence_before();
@@ -325,8 +310,6 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
-                const bf16* zp = a.bs_z ? a.bs_z + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.bs_pitch + a.bs_coff - a.bs_c0
-                                        : nullptr;
                 mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
                 for (int g = 0; g < NC / 8; ++g) {
@@ -338,38 +321,25 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
                     }
-                    if (a.accumulate && pvalid && cvalid) {
-                        float o[8];
-                        Vec8<bf16>::load(yp + c, o);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] += o[i];
-                    }
-                    if (a.stats && (!a.bs_z || (c >= a.bs_c0 && c < a.bs_c1))) {      // warp-uniform condition
+                    if (a.stats) {
                         float w[16];
-                        if (a.bs_z) {
-                            float z[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) z[i] = 0.f;
-                            if (pvalid) Vec8<bf16>::load(zp + c, z);
-                            const int pc = c - a.bs_c0;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float u = fmaf(z[i], a.bs_scale[pc + i], a.bs_shift[pc + i]);
-                                const float gq = !pvalid ? 0.f : (a.bs_act == SEMB_ACT_RELU ? (u > 0.f ? v[i] : 0.f) : v[i]);
-                                w[i] = gq;
-                                w[8 + i] = gq * (z[i] - a.bs_mean[pc + i]);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) { w[i] = pvalid ? v[i] : 0.f; w[8 + i] = w[i] * w[i]; }
-                        }
+                        for (int i = 0; i < 8; ++i) { w[i] = pvalid ? v[i] : 0.f; w[8 + i] = w[i] * w[i]; }
                         warp_reduce16(w, lane);
                         if ((lane & 1) == 0) {
                             const int idx = lane >> 1;                       // 0..7 sums, 8..15 squares
                             part[((idx >> 3) * 4 + wq) * NC + g * 8 + (idx & 7)] += w[0];
                         }
                     }
-                    if (pvalid && cvalid && !(a.dbg & 4)) Vec8<bf16>::store(yp + c, v);
+                    if (pvalid && cvalid && !(a.dbg & 4)) {
+                        if (a.accumulate) {
+                            float o[8];
+                            Vec8<bf16>::load(yp + c, o);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] += o[i];
+                        }
+                        Vec8<bf16>::store(yp + c, v);
+                    }
                 }
                 tc_fence_before();
                 mbar_arrive(empty_u32);
@@ -400,15 +370,9 @@ static EncodeTiledFn encode_tiled() {
 
 // Called by semb_conv2d_fwd_tc (conv_tc.cu) after argument validation, for SEMB_PAD_ZERO geometries.
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
-                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream,
-                    const semb_bn_bwd_sums* bs) {
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream) {
     TmArgs A{};
     TcArgs& a = A.t;
-    if (bs) {
-        a.bs_z = reinterpret_cast<const bf16*>(bs->z.ptr); a.bs_pitch = bs->z.pitch; a.bs_coff = bs->z.coff;
-        a.bs_scale = bs->scale; a.bs_shift = bs->shift; a.bs_mean = bs->mean;
-        a.bs_act = bs->act; a.bs_c0 = bs->c0; a.bs_c1 = bs->c0 + bs->z.C;
-    }
     a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
     a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
     a.x = reinterpret_cast<const bf16*>(x->ptr); a.x_pitch = x->pitch; a.x_coff = x->coff;

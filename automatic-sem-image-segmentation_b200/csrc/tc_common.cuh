@@ -179,12 +179,6 @@ struct TcArgs {
     int plane_bytes, halo_h, halo_w;
     int stages, b_resident, a_bytes, b_bytes, stage_bytes;
     int dbg;      // SEMB_TC_DEBUG ablation bits (profiling only): 1 no A loads, 2 no MMAs, 4 no stores, 8 no moments
-    // Data-gradient launches that are the LAST writer of d(y) for a normalisation layer y = act(BN(z)) also produce that
-    // layer's backward sums in the epilogue (bs_z != NULL): stats[0][c] += sum g, stats[1][c] += sum g * (z - mean) with
-    // g = d(y) * act'(z * scale + shift), for output channels [bs_c0, bs_c1); parameter arrays are indexed by c - bs_c0.
-    const bf16* bs_z; int bs_pitch, bs_coff;
-    const float *bs_scale, *bs_shift, *bs_mean;
-    int bs_act, bs_c0, bs_c1;
 };
 
 // Walks the tiles t = first + i*stride of an (N, tiles_y, tiles_x) grid without integer divisions in the loop.
@@ -225,8 +219,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // conv_tma.cu: TMA-staged variant of the forward / data-gradient conv for zero-padded geometries
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
-                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream,
-                    const semb_bn_bwd_sums* bs = nullptr);
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream);
 
 // wgrad_tma.cu: TMA-staged weight gradient of the zero-padded 3x3 layers
 int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace, void* stream);

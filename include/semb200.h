@@ -132,27 +132,6 @@ int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void
                        const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                        int32_t accumulate, void* stream);
 
-/* Data gradient (semb_conv2d_fwd_tc contract with x:=dy, y:=dx on the flipped weight pack) that ALSO produces the
- * BatchNormalization backward sums of the layer whose output gradient it completes.  For y = act(BN(z)) (conv2d_bn,
- * UNet_Segmentation.py:421-425; the block-level BatchNormalization layers :470-473,:494-502) autograd needs
- * sum g and sum g*xhat over the batch with g = d(y) * act'(.) before it can form d(z).  When this launch is the last
- * writer of d(y) (accumulate = 1 on top of the other consumers' contributions), its epilogue has the total d(y) in
- * registers: it reads z once and accumulates sums[0][c] += g, sums[1][c] += g * (z - mean) (fp64, NOT yet multiplied by
- * invstd) for the dx channels [c0, c0 + z.C), which removes the separate reduction pass over d(y) and z. */
-typedef struct semb_bn_bwd_sums {
-    semb_tensor z;          /* pre-normalisation tensor of the layer, same pixel grid as dx; z.C channels */
-    const float* scale;     /* per channel of z: scale, shift of the normalisation (u = z*scale + shift), batch mean */
-    const float* shift;
-    const float* mean;
-    int32_t act;            /* SEMB_ACT_NONE or SEMB_ACT_RELU */
-    int32_t c0;             /* first dx channel the layer's output occupies (multiple of 8) */
-    void* sums;             /* double [2][cstride], zeroed by the caller before the step */
-    int32_t cstride;
-} semb_bn_bwd_sums;
-
-int semb_conv2d_dgrad_tc_bnsums(const semb_conv_geom* g, const semb_tensor* dy, const void* w_packed, const semb_tensor* dx,
-                                int32_t accumulate, const semb_bn_bwd_sums* bs, void* stream);
-
 /* Weight gradient of the same layers on tcgen05: D[co][ci] per tap, K = output pixels (split over CTAs), both
  * operands read as MN-major UMMA operands from the NHWC channel-group planes; accumulates (+=) into the fp32
  * HWIO gradient with coalesced reductions.  Same contract as semb_conv2d_wgrad without dbias. */
