@@ -808,6 +808,21 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     return check_launch("conv_tc");
 }
 
+extern "C" int semb_conv2d_fwd_tc_f32(const semb_conv_geom* g, const semb_tensor* x3, const void* w_packed, const float* bias,
+                                      const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
+                                      int32_t accumulate, void* stream) {
+    SEMB_REQUIRE(g && x3 && y && w_packed, SEMB_ESHAPE, "conv_tc_f32: null argument");
+    SEMB_REQUIRE(g->dtype == SEMB_BF16 && g->pad_mode == SEMB_PAD_ZERO, SEMB_ESHAPE, "conv_tc_f32: geometry must describe the bf16 split operand, zero padding");
+    SEMB_REQUIRE(g->stride == 1 && ((g->R == 1 && g->S == 1) || (g->R == 3 && g->S == 3)), SEMB_ESHAPE,
+                 "conv_tc_f32: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
+    SEMB_REQUIRE(view_ok(x3) && x3->C == g->Cin, SEMB_EALIGN, "conv_tc_f32: bad operand view");
+    SEMB_REQUIRE(y->ptr && y->C == g->Cout && (y->C % 8) == 0 && (y->pitch % 8) == 0 && (y->coff % 8) == 0 && y->coff + y->C <= y->pitch &&
+                 (reinterpret_cast<uintptr_t>(y->ptr) % 32) == 0, SEMB_EALIGN, "conv_tc_f32: bad fp32 output view");
+    SEMB_REQUIRE(g->N > 0 && g->OH > 0 && g->OW > 0 && g->pad_t >= 0 && g->pad_l >= 0 && g->pad_t < g->R + TILE_H && g->pad_l < g->S + TILE_W,
+                 SEMB_ESHAPE, "conv_tc_f32: bad geometry");
+    return conv_tma_launch(g, x3, w_packed, bias, y, stats, stats_nstride, stats_cstride, accumulate, stream, 1);
+}
+
 extern "C" int64_t semb_conv2d_wgrad_tc_workspace(const semb_conv_geom* g) {
     if (!g || g->dtype != SEMB_BF16 || g->stride != 1 || g->R != 3 || g->S != 3 || g->pad_mode != SEMB_PAD_ZERO || g->pad_t > 2 || g->pad_l > 2)
         return 0;

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
+                float* ypf = reinterpret_cast<float*>(a.y) + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
                 mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
 #pragma unroll
@@ -287,11 +288,11 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                         if (pvalid && cvalid && !(a.dbg & 4)) {
                             if (a.accumulate) {
                                 float o[8];
-                                Vec8<bf16>::load(yp + c, o);
+                                if (a.out_f32) Vec8<float>::load(ypf + c, o); else Vec8<bf16>::load(yp + c, o);
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[i] += o[i];
                             }
-                            Vec8<bf16>::store(yp + c, v);
+                            if (a.out_f32) Vec8<float>::store(ypf + c, v); else Vec8<bf16>::store(yp + c, v);
                         }
                     }
                 }
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
+                float* ypf = reinterpret_cast<float*>(a.y) + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
                 mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
                 for (int g = 0; g < NC / 8; ++g) {
@@ -334,11 +336,11 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                     if (pvalid && cvalid && !(a.dbg & 4)) {
                         if (a.accumulate) {
                             float o[8];
-                            Vec8<bf16>::load(yp + c, o);
+                            if (a.out_f32) Vec8<float>::load(ypf + c, o); else Vec8<bf16>::load(yp + c, o);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) v[i] += o[i];
                         }
-                        Vec8<bf16>::store(yp + c, v);
+                        if (a.out_f32) Vec8<float>::store(ypf + c, v); else Vec8<bf16>::store(yp + c, v);
                     }
                 }
                 tc_fence_before();
@@ -370,9 +372,10 @@ static EncodeTiledFn encode_tiled() {
 
 // Called by semb_conv2d_fwd_tc (conv_tc.cu) after argument validation, for SEMB_PAD_ZERO geometries.
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
-                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream) {
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream, int out_f32) {
     TmArgs A{};
     TcArgs& a = A.t;
+    a.out_f32 = out_f32;
     a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
     a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
     a.x = reinterpret_cast<const bf16*>(x->ptr); a.x_pitch = x->pitch; a.x_coff = x->coff;

@@ -542,6 +542,65 @@ __global__ void tile_stitch_kernel(const float* __restrict__ tiles, int th, int 
     }
 }
 
+// ---- parity mode on the tensor cores: fp32 tensors as split bf16 operands ------------------------------------------------
+// x = xh + xm + xl exactly to 2^-24 |x| with xh = bf16(x), xm = bf16(x - xh), xl = bf16(x - xh - xm).
+// 3 terms: x*w ~ xh*wh + xl'*wh + xh*wl'   (two-way split, relative error ~2^-16: measured 1e-3 on the UNet's sigmoid map
+//          after 61 layers -- not enough for a bit-exact mask)
+// 6 terms: x*w ~ xh*wh + xh*wm + xm*wh + xh*wl + xl*wh + xm*wm   (all products above 2^-24: fp32-grade)
+// i.e. ONE tensor-core conv over the stacked operand [xh | xh | xm | xh | xl | xm] (6C channels) against the weights
+// [wh ; wm ; wh ; wl ; wh ; wm] stacked along the contraction axis, accumulated in fp32.  (3 terms: [xh | xl' | xh] . [wh ; wh ; wl'].)
+__device__ __forceinline__ void split3(float v, float& h, float& m, float& l) {
+    h = __bfloat162float(__float2bfloat16_rn(v));
+    const float r = v - h;
+    m = __bfloat162float(__float2bfloat16_rn(r));
+    l = r - m;
+}
+
+__global__ void split_bf16_kernel(PView src, PView dst, long long n_pixels, int C8, int C, int terms) {
+    const long long total = n_pixels * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const size_t px = (size_t)(i / C8);
+        float v[8], hi[8], mid[8], lo[8];
+        Vec8<float>::load(at<float>(src, px, c), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) split3(v[k], hi[k], mid[k], lo[k]);
+        if (terms == 3) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mid[k] = v[k] - hi[k];           // two-way split: the whole residual
+            Vec8<bf16>::store(at<bf16>(dst, px, c), hi);
+            Vec8<bf16>::store(at<bf16>(dst, px, C + c), mid);
+            Vec8<bf16>::store(at<bf16>(dst, px, 2 * C + c), hi);
+        } else {
+            Vec8<bf16>::store(at<bf16>(dst, px, c), hi);
+            Vec8<bf16>::store(at<bf16>(dst, px, C + c), hi);
+            Vec8<bf16>::store(at<bf16>(dst, px, 2 * C + c), mid);
+            Vec8<bf16>::store(at<bf16>(dst, px, 3 * C + c), hi);
+            Vec8<bf16>::store(at<bf16>(dst, px, 4 * C + c), lo);
+            Vec8<bf16>::store(at<bf16>(dst, px, 5 * C + c), mid);
+        }
+    }
+}
+
+// w (R,S,Cin,Cout) fp32 -> the stacked fp32 kernel the packer then rounds to bf16 (block values are chosen so that their
+// bf16 rounding is exactly wh / wm / wl).  axis 0: stacked along the input channels (forward); axis 1: along the output
+// channels (the flipped pack then contracts over them: data gradient).
+__global__ void split_weights_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, float* __restrict__ ws, int axis, int terms) {
+    const long long total = (long long)taps * Cin * Cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout), ci = (int)((i / Cout) % Cin), t = (int)(i / ((long long)Cout * Cin));
+        float h, m, l;
+        split3(w[i], h, m, l);
+        float blk[6];
+        if (terms == 3) { blk[0] = h; blk[1] = h; blk[2] = w[i] - h; }
+        else { blk[0] = h; blk[1] = m; blk[2] = h; blk[3] = l; blk[4] = h; blk[5] = m; }
+        for (int b = 0; b < terms; ++b) {
+            if (axis == 0) ws[((size_t)t * terms * Cin + (size_t)b * Cin + ci) * Cout + co] = blk[b];
+            else ws[((size_t)t * Cin + ci) * terms * Cout + (size_t)b * Cout + co] = blk[b];
+        }
+    }
+}
+
 static inline int grid_for(long long total, int block = 256) {
     long long b = cdivl(total, block);
     const long long cap = 148LL * 16;
@@ -673,6 +732,23 @@ extern "C" int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* d
 extern "C" int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t N, int32_t H, int32_t W,
                                    const float* bias, int32_t dir, int32_t dtype, void* stream) {
     return semb_pixel_shuffle2x(src, dst, N, H, W, 2 * H, 2 * W, bias, dir, 0, dtype, stream);
+}
+
+extern "C" int semb_split_bf16(const semb_tensor* src, const semb_tensor* dst, int64_t n_pixels, void* stream) {
+    SEMB_REQUIRE(src && dst && src->ptr && dst->ptr && n_pixels > 0 && src->C > 0 && (src->C % 8) == 0 &&
+                 (dst->C == 3 * src->C || dst->C == 6 * src->C) && (src->pitch % 8) == 0 && (src->coff % 8) == 0 && view_ok(dst), SEMB_ESHAPE,
+                 "split_bf16: dst must have 3x or 6x the channels of src");
+    const int C8 = src->C / 8;
+    split_bf16_kernel<<<grid_for(n_pixels * C8), 256, 0, as_stream(stream)>>>(pv(src), pv(dst), n_pixels, C8, src->C, dst->C / src->C);
+    return check_launch("split_bf16");
+}
+
+extern "C" int semb_split_weights(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout, float* ws, int32_t axis, int32_t terms,
+                                  void* stream) {
+    SEMB_REQUIRE(w && ws && R > 0 && S > 0 && Cin > 0 && Cout > 0 && (axis == 0 || axis == 1) && (terms == 3 || terms == 6), SEMB_ESHAPE,
+                 "split_weights: bad arguments");
+    split_weights_kernel<<<grid_for((long long)R * S * Cin * Cout), 256, 0, as_stream(stream)>>>(w, R * S, Cin, Cout, ws, axis, terms);
+    return check_launch("split_weights");
 }
 
 extern "C" int semb_tile_gather(const float* img, int32_t H, int32_t W, float* tiles, int32_t th, int32_t tw, const int32_t* xs, int32_t nx,

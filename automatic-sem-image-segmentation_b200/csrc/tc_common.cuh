@@ -179,6 +179,7 @@ struct TcArgs {
     int plane_bytes, halo_h, halo_w;
     int stages, b_resident, a_bytes, b_bytes, stage_bytes;
     int dbg;      // SEMB_TC_DEBUG ablation bits (profiling only): 1 no A loads, 2 no MMAs, 4 no stores, 8 no moments
+    int out_f32;  // y is an fp32 tensor (parity mode: bf16 x 3 split operands, fp32 results); y_pitch / y_coff count floats
 };
 
 // Walks the tiles t = first + i*stride of an (N, tiles_y, tiles_x) grid without integer divisions in the loop.
@@ -219,7 +220,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // conv_tma.cu: TMA-staged variant of the forward / data-gradient conv for zero-padded geometries
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
-                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream);
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream, int out_f32 = 0);
 
 // wgrad_tma.cu: TMA-staged weight gradient of the zero-padded 3x3 layers
 int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace, void* stream);

@@ -39,7 +39,7 @@ class _Instance:
         e = self.eng
         self.loss_sums = e.zeroed.add("loss/sums", 4)
         e.finalize()
-        if os.environ.get("SEMB_NO_WGRAD_STREAM") is None:
+        if os.environ.get("SEMB_NO_WGRAD_STREAM") is None and not e.tc_split:      # split-operand scratch is shared: one stream
             e.wgrad_stream = torch.cuda.Stream(device=e.device)
         self.n, self.h, self.w = n, h, w
         self.x_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)

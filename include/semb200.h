@@ -316,6 +316,25 @@ int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t 
 int semb_upsample2x(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t dir,
                     int32_t accumulate, int32_t dtype, void* stream);
 
+/* ---- parity mode on the tensor cores (fp32 storage, split bf16 operands) ----------------------------------------------
+ * north_star: "within 1e-3 relative fp32 (bit-exact for the argmax mask)" for an implicit GEMM on tcgen05.  An fp32 value
+ * is x = xh + xm + xl (three bf16 terms, exact to 2^-24); x*w ~ xh*wh + xh*wm + xm*wh + xh*wl + xl*wh + xm*wm keeps every
+ * product above 2^-24 (6 terms).  The 3-term variant (x = xh + xl', xh*wh + xl'*wh + xh*wl') is 2^-16-accurate: measured
+ * 1e-3 on the UNet's sigmoid map after 61 layers, i.e. NOT enough for a bit-exact mask; the engine uses 6 terms.
+ * semb_split_bf16: fp32 tensor (C channels) -> bf16 tensor with 6C channels [xh|xh|xm|xh|xl|xm] (or 3C: [xh|xl'|xh]).
+ * semb_split_weights: fp32 kernel (R,S,Cin,Cout) -> fp32 stacked kernel whose bf16 rounding (semb_pack_weights_tc) is
+ *   [wh;wm;wh;wl;wh;wm] (3 terms: [wh;wh;wl']) along the input channels (axis 0, forward) or the output channels (axis 1:
+ *   the flipped pack contracts over them, data gradient).
+ * semb_conv2d_fwd_tc_f32: semb_conv2d_fwd_tc on the split operand (g->Cin = terms*C, g->dtype = SEMB_BF16) with an fp32
+ *   result tensor y (pitch / coff in floats; accumulate adds to the fp32 content); moments come from the fp32 accumulators.
+ * The weight gradient of such a layer is `terms` calls of semb_conv2d_wgrad_tc on channel slices of the split x and dy. */
+int semb_split_bf16(const semb_tensor* src_f32, const semb_tensor* dst_bf16, int64_t n_pixels, void* stream);
+int semb_split_weights(const float* w, int32_t R, int32_t S, int32_t Cin, int32_t Cout, float* ws, int32_t axis, int32_t terms,
+                       void* stream);
+int semb_conv2d_fwd_tc_f32(const semb_conv_geom* g, const semb_tensor* x3, const void* w_packed, const float* bias,
+                           const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate,
+                           void* stream);
+
 /* ---- tiled inference: HelperFunctions.tile_image / stitch_image (:17-141) as index arithmetic on the device ----------
  * The reference cuts an image into overlapping tiles on the host, calls the model tile by tile and stitches on the host
  * (UNet_Segmentation.py:335-343).  Here the image is uploaded once; tiles are numbered x-major (k = ix*ny + iy), xs[nx] /
