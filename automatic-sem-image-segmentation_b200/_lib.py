@@ -33,7 +33,8 @@ class ConvGeom(C.Structure):
 
 class AffineDesc(C.Structure):
     """semb_affine_desc"""
-    _fields_ = [(n, C.c_int32) for n in ("N", "HW", "C", "dtype", "act", "actb", "mode_a", "mode_b", "aff_nstride")]
+    _fields_ = [(n, C.c_int32) for n in ("N", "HW", "C", "dtype", "act", "actb", "mode_a", "mode_b", "aff_nstride", "nseg_b")] + \
+               [("seg_c0", C.c_int32 * 3), ("seg_b", Tensor * 3), ("seg_db", Tensor * 3)]
 
 
 class NormFin(C.Structure):

@@ -59,7 +59,20 @@ struct AffArgs {
     float count_a, count_b;
     float *dgamma_a, *dbeta_a, *dgamma_b, *dbeta_b;
     unsigned int* barrier;
+    // b as a concatenation of up to three compact tensors (semb_affine_desc.nseg_b)
+    int nseg_b; int seg_c0[3]; View seg_b[3], seg_db[3];
 };
+
+// The view and the channel offset inside it that hold channel c of the b operand (resp. of its gradient).
+__device__ __forceinline__ View b_view(const AffArgs& p, int c, int& cc, bool grad) {
+    cc = c;
+    if (p.nseg_b == 0) return grad ? p.db : p.b;
+    int s = 0;
+    if (p.nseg_b > 1 && c >= p.seg_c0[1]) s = 1;
+    if (p.nseg_b > 2 && c >= p.seg_c0[2]) s = 2;
+    cc = c - p.seg_c0[s];
+    return grad ? p.seg_db[s] : p.seg_b[s];
+}
 
 __device__ __forceinline__ float act_bwd_from_u(float u, int act) {
     switch (act) {
@@ -165,6 +178,8 @@ __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p)
     const Lanes L(p.C);
     const int n = blockIdx.y;
     const int c = L.cg * 8;
+    int cb = c;
+    const View bv = b_view(p, c, cb, false);
     const long long pix0 = (long long)n * p.HW;
     const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
     const size_t aoff = (size_t)n * p.aff_nstride + c;
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p)
                 const int px = base + u * L.rows;
                 if (px < end) {
                     ra[u].load(vptr<T>(p.a, pix0 + px, c));
-                    if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+                    if (HAS_B) rb[u].load(vptr<T>(bv, pix0 + px, cb));
                 }
             }
 #pragma unroll
@@ -250,6 +265,8 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kern
     const Lanes L(p.C);
     const int n = blockIdx.y;
     const int c = L.cg * 8;
+    int cb = c;
+    const View bv = b_view(p, c, cb, false);
     const long long pix0 = (long long)n * p.HW;
     const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
     const size_t aoff = (size_t)n * p.aff_nstride + c;
@@ -277,7 +294,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kern
                 if (px < end) {
                     rg[u].load(vptr<T>(p.dy, pix0 + px, c));
                     ra[u].load(vptr<T>(p.a, pix0 + px, c));
-                    if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+                    if (HAS_B) rb[u].load(vptr<T>(bv, pix0 + px, cb));
                 }
             }
 #pragma unroll
@@ -342,6 +359,8 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
     if (!L.active) return;
     const int n = blockIdx.y;
     const int c = L.cg * 8;
+    int cb = c;
+    const View bv = b_view(p, c, cb, false);
     const long long pix0 = (long long)n * p.HW;
     const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
     const size_t aoff = (size_t)n * p.aff_nstride + c;
@@ -387,7 +406,9 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
             }
         }
     }
-    const bool wa = p.da.ptr != nullptr, wb = HAS_B && p.db.ptr != nullptr;
+    int cdb = c;
+    const View dbv = b_view(p, c, cdb, true);
+    const bool wa = p.da.ptr != nullptr, wb = HAS_B && dbv.ptr != nullptr;
     if (!wa && !wb) return;
 
     for (int base = begin + L.prow; base < end; base += L.rows * U) {
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
             if (px < end) {
                 rg[u].load(vptr<T>(p.dy, pix0 + px, c));
                 ra[u].load(vptr<T>(p.a, pix0 + px, c));
-                if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+                if (HAS_B) rb[u].load(vptr<T>(bv, pix0 + px, cb));
             }
         }
 #pragma unroll
@@ -431,7 +452,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
                     Vec8<T>::store(o, da);
                 }
                 if (wb) {
-                    T* o = vptr_mut<T>(p.db, pix0 + px, c);
+                    T* o = vptr_mut<T>(dbv, pix0 + px, cdb);
                     if (p.acc_b) {
                         float old[8];
                         Vec8<T>::load(o, old);
@@ -457,6 +478,8 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_fused_kerne
     const Lanes L(p.C);
     const int n = blockIdx.y;
     const int c = L.cg * 8;
+    int cb = c;
+    const View bv = b_view(p, c, cb, false);
     const long long pix0 = (long long)n * p.HW;
     const int begin = blockIdx.x * p.ppb, end = min(p.HW, begin + p.ppb);
     const size_t aoff = (size_t)n * p.aff_nstride + c;
@@ -485,7 +508,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_fused_kerne
                     if (px < end) {
                         rg[u].load(vptr<T>(p.dy, pix0 + px, c));
                         ra[u].load(vptr<T>(p.a, pix0 + px, c));
-                        if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+                        if (HAS_B) rb[u].load(vptr<T>(bv, pix0 + px, cb));
                     }
                 }
 #pragma unroll
@@ -588,7 +611,9 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_fused_kerne
             }
         }
     }
-    const bool wa = p.da.ptr != nullptr, wb = HAS_B && p.db.ptr != nullptr;
+    int cdb = c;
+    const View dbv = b_view(p, c, cdb, true);
+    const bool wa = p.da.ptr != nullptr, wb = HAS_B && dbv.ptr != nullptr;
     if (!wa && !wb) return;
     const int span = L.rows * U;
     const int niter = (end - begin - L.prow + span - 1) / span;      // iterations of this thread in pass 1
@@ -601,7 +626,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_fused_kerne
             if (px < end) {
                 rg[u].load(vptr<T>(p.dy, pix0 + px, c));
                 ra[u].load(vptr<T>(p.a, pix0 + px, c));
-                if (HAS_B) rb[u].load(vptr<T>(p.b, pix0 + px, c));
+                if (HAS_B) rb[u].load(vptr<T>(bv, pix0 + px, cb));
             }
         }
 #pragma unroll
@@ -634,7 +659,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_fused_kerne
                     Vec8<T>::store(o, da);
                 }
                 if (wb) {
-                    T* o = vptr_mut<T>(p.db, pix0 + px, c);
+                    T* o = vptr_mut<T>(dbv, pix0 + px, cdb);
                     if (p.acc_b) {
                         float old[8];
                         Vec8<T>::load(o, old);
@@ -708,11 +733,27 @@ static dim3 aff_grid(AffArgs& p, bool per_sample, int blocks_per_sm) {
     return dim3(cdiv(p.HW, p.ppb), p.N);
 }
 
+static void set_segments(AffArgs& p, const semb_affine_desc* d) {
+    p.nseg_b = d->nseg_b;
+    for (int s = 0; s < 3; ++s) {
+        p.seg_c0[s] = d->seg_c0[s];
+        p.seg_b[s] = View{d->seg_b[s].ptr, d->seg_b[s].pitch, d->seg_b[s].coff};
+        p.seg_db[s] = View{d->seg_db[s].ptr, d->seg_db[s].pitch, d->seg_db[s].coff};
+    }
+}
+
 static int check_aff(const semb_affine_desc* d) {
     SEMB_REQUIRE(d, SEMB_ESHAPE, "affine: null desc");
     SEMB_REQUIRE(d->N > 0 && d->HW > 0 && d->C > 0 && d->C % 8 == 0 && d->C <= 2048, SEMB_ESHAPE,
                  "affine: bad shape N=%d HW=%d C=%d", d->N, d->HW, d->C);
     SEMB_REQUIRE(d->dtype == SEMB_F32 || d->dtype == SEMB_BF16, SEMB_ESHAPE, "affine: bad dtype");
+    SEMB_REQUIRE(d->nseg_b >= 0 && d->nseg_b <= 3, SEMB_ESHAPE, "affine: at most three b segments");
+    for (int s = 0, c0 = 0; s < d->nseg_b; ++s) {
+        SEMB_REQUIRE(view_ok(&d->seg_b[s]) && d->seg_c0[s] == c0, SEMB_ESHAPE, "affine: b segments must be valid views that tile the channels in order");
+        c0 += d->seg_b[s].C;
+        SEMB_REQUIRE(s + 1 < d->nseg_b || c0 == d->C, SEMB_ESHAPE, "affine: b segments cover %d of %d channels", c0, d->C);
+        SEMB_REQUIRE(!d->seg_db[s].ptr || (view_ok(&d->seg_db[s]) && d->seg_db[s].C == d->seg_b[s].C), SEMB_ESHAPE, "affine: bad b gradient segment");
+    }
     return SEMB_OK;
 }
 
@@ -841,6 +882,7 @@ extern "C" int semb_affine_act_fwd(const semb_affine_desc* d, const semb_tensor*
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
+    set_segments(p, d);
     p.a = mkview(a); p.b = mkview(b); p.y = mkview(y);
     p.scale_a = scale_a; p.shift_a = shift_a; p.scale_b = scale_b; p.shift_b = shift_b;
     p.dstats = reinterpret_cast<double*>(stats); p.stats_nstride = stats_nstride; p.stats_cstride = stats_cstride;
@@ -867,6 +909,7 @@ extern "C" int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
+    set_segments(p, d);
     p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy);
     p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
@@ -898,6 +941,7 @@ extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_t
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
+    set_segments(p, d);
     p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
     p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a; p.c1_a = c1_a; p.c2_a = c2_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b; p.c1_b = c1_b; p.c2_b = c2_b;
@@ -923,6 +967,7 @@ extern "C" int semb_affine_act_fwd_fin(const semb_affine_desc* d, const semb_ten
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
+    set_segments(p, d);
     p.a = mkview(a); p.b = mkview(b); p.y = mkview(y);
     if (fin_a) { p.fa = *fin_a; p.scale_a = fin_a->scale; p.shift_a = fin_a->shift; }
     if (fin_b) { p.fb = *fin_b; p.scale_b = fin_b->scale; p.shift_b = fin_b->shift; }
@@ -954,6 +999,7 @@ extern "C" int semb_affine_act_bwd_apply_sums(const semb_affine_desc* d, const s
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
+    set_segments(p, d);
     p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
     p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
@@ -1008,6 +1054,7 @@ extern "C" int semb_affine_act_bwd_fused(const semb_affine_desc* d, const semb_t
     AffArgs p{};
     p.N = d->N; p.HW = d->HW; p.C = d->C; p.act = d->act; p.actb = d->actb; p.mode_a = d->mode_a; p.mode_b = d->mode_b;
     p.aff_nstride = d->aff_nstride;
+    set_segments(p, d);
     p.a = mkview(a); p.b = mkview(b); p.dy = mkview(dy); p.da = mkview(da); p.db = mkview(db);
     p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;

@@ -919,8 +919,34 @@ class NormOp(Op):
         return training or self.moving is None
 
 
+class SegView:
+    """The b operand of an AffineOp as a channel-wise concatenation of compact Views (no concat buffer): quacks like a
+    View where the kernels only need the total channel count (semb_affine_desc.nseg_b)."""
+
+    def __init__(self, segs: Sequence[View]):
+        assert 1 <= len(segs) <= 3
+        self.segs = list(segs)
+        self.C = sum(v.C for v in segs)
+        self.c0 = [sum(v.C for v in segs[:i]) for i in range(len(segs))]
+        self.requires_grad = any(v.requires_grad for v in segs)
+        self._t = self._g = None
+
+    @property
+    def t(self) -> L.Tensor:            # placeholder (valid view over the first segment's storage, never dereferenced)
+        if self._t is None:
+            self._t = L.Tensor(self.segs[0].buf.data.data_ptr(), self.C, self.C, 0)
+        return self._t
+
+    @property
+    def g(self) -> L.Tensor:
+        if self._g is None:
+            self._g = L.Tensor(self.segs[0].buf.grad_tensor().data_ptr(), self.C, self.C, 0)
+        return self._g
+
+
 class AffineOp(Op):
-    """y = act( A(a) + actb(B(b)) ) with A/B the affines of NormOps (or identity), optional moments of y."""
+    """y = act( A(a) + actb(B(b)) ) with A/B the affines of NormOps (or identity), optional moments of y.
+    `b` may be a SegView: the concatenation of up to three compact tensors (multi_res_block's `concatenate`)."""
 
     def __init__(self, eng: Engine, hw: int, a: View, norm_a: Optional[NormOp], b: Optional[View], norm_b: Optional[NormOp],
                  y: View, act: int, actb: int = L.ACT_NONE, stats_out: Optional[Tuple[str, int, int, int]] = None,
@@ -943,16 +969,33 @@ class AffineOp(Op):
     def plan_backward(self):
         if self.a.requires_grad:
             self.acc_a = plan_grad_write(self.a)
-        if self.b is not None and self.b.requires_grad:
+        if isinstance(self.b, SegView):
+            accs = {plan_grad_write(v) for v in self.b.segs if v.requires_grad}
+            assert len(accs) <= 1, "segments of one concatenation must all be first (or all later) gradient writers"
+            self.acc_b = accs.pop() if accs else 0
+        elif self.b is not None and self.b.requires_grad:
             self.acc_b = plan_grad_write(self.b)
 
     def _desc(self, training: bool) -> L.AffineDesc:
+        cache = self.__dict__.setdefault("_desc_cache", {})
+        d = cache.get(training)
+        if d is None:
+            d = cache[training] = self._make_desc(training)
+        return d
+
+    def _make_desc(self, training: bool) -> L.AffineDesc:
         def mode(norm):
             if norm is None:
                 return L.AFF_NONE
             return L.AFF_BATCH if norm.uses_batch_stats(training) else L.AFF_PLAIN
-        return L.AffineDesc(self.n, self.hw, self.a.C, self.eng.dtype, self.act, self.actb, mode(self.norm_a),
-                            mode(self.norm_b) if self.b is not None else L.AFF_NONE, self.aff_nstride)
+        d = L.AffineDesc(self.n, self.hw, self.a.C, self.eng.dtype, self.act, self.actb, mode(self.norm_a),
+                         mode(self.norm_b) if self.b is not None else L.AFF_NONE, self.aff_nstride)
+        if isinstance(self.b, SegView):
+            d.nseg_b = len(self.b.segs)
+            for i, v in enumerate(self.b.segs):
+                d.seg_c0[i] = self.b.c0[i]
+                d.seg_b[i] = v.t
+        return d
 
     def _p(self, norm: Optional[NormOp], key: str, coff: int) -> Optional[int]:
         return None if norm is None else norm.s(key) + 4 * coff
@@ -981,6 +1024,10 @@ class AffineOp(Op):
     def bwd(self):
         e = self.eng
         d = self._last_desc
+        if isinstance(self.b, SegView):
+            for i, v in enumerate(self.b.segs):
+                if v.requires_grad:
+                    d.seg_db[i] = v.g
         na, nb = self.norm_a, self.norm_b
         ca = self.coff_a
         bt = C.byref(self.b.t) if self.b is not None else None

@@ -202,6 +202,16 @@ typedef struct {
     int32_t act, actb;
     int32_t mode_a, mode_b;           /* SEMB_AFF_* */
     int32_t aff_nstride;              /* 0 = per-channel, else per-sample stride of scale/shift arrays */
+    /* Optional: the b operand as a CONCATENATION of up to three tensors along the channel axis (`concatenate([a, b, c])`
+     * of multi_res_block, UNet_Segmentation.py:469) without a concat buffer: segment s holds the channels
+     * [seg_c0[s], seg_c0[s] + seg_b[s].C) of b.  nseg_b = 0: b is the plain tensor argument.  When segments are given
+     * the `b` (and, in the backward kernels, `db`) arguments only need valid C; seg_db[s] receive the gradient slices
+     * (ptr NULL = not needed).  An 8-channel slice of a 32-channel concat buffer costs the full 64-byte DRAM sector per
+     * pixel; compact per-branch tensors do not. */
+    int32_t nseg_b;
+    int32_t seg_c0[3];
+    semb_tensor seg_b[3];
+    semb_tensor seg_db[3];
 } semb_affine_desc;
 
 int semb_affine_act_fwd(const semb_affine_desc* d,
