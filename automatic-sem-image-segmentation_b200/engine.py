@@ -622,7 +622,7 @@ class ConvOp(Op):
         # (a cheap copy next to a 512->512 conv) so that forward and weight gradient run the TMA kernels as zero-pad
         # "valid" convolutions over it; the data gradient already works on the padded domain (pad_buf above).
         self.x_pad = None
-        if self.use_tc and pad_mode == L.PAD_REFLECT and _os.environ.get("SEMB_NO_REFLECT_TMA") is None:
+        if self.use_tc and pad_mode == L.PAD_REFLECT:
             hp = max(h, (oh - 1) * stride + k)
             wp = max(wd, (ow - 1) * stride + k)
             self.x_pad = eng.new_buf(hp, wp, x.C, f"{w}_xpad", requires_grad=False, n=n)

@@ -125,9 +125,10 @@ int semb_pack_weights_tc_batch(const void* device_jobs, int32_t njobs, int32_t t
 
 /* Same contract as semb_conv2d_fwd for stride 1, R=S in {1,3}, bf16 storage: im2col-free implicit GEMM on
  * tcgen05.mma (M = 128 output pixels per CTA, N = Cout, K = taps x Cin) with the fp32 accumulator in TMEM.
- * The A operand is the NHWC halo tile staged once in shared memory; the nine taps are shifted UMMA
- * descriptors over that tile.  Zero or reflect padding.  UNet_Segmentation.py:421,465-468,490-499;
- * CycleGAN.py:327,333. */
+ * The A operand is the NHWC halo tile staged once in shared memory by the TMA unit; the nine taps are shifted UMMA
+ * descriptors over that tile.  Zero padding only (the TMA's out-of-bounds fill): the reflect-padded residual convs of
+ * CycleGAN.py:326-333 run as pad 0 ('valid') over an input materialised with semb_pad_crop.
+ * UNet_Segmentation.py:421,465-468,490-499; CycleGAN.py:327,333. */
 int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
                        const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                        int32_t accumulate, void* stream);

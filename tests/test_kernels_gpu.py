@@ -563,9 +563,15 @@ def test_conv_tc_fwd_and_dgrad(case):
     dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
     y_ref.backward(dy)
     cpi, cpo = U.pad8(cin), U.pad8(cout)
-    pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
-    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, pm, L.BF16)
     xd = U.to_dev(x, "bf16", pitch=cpi + 8, coff=8)
+    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, L.PAD_ZERO, L.BF16)
+    if pad_mode == "reflect":
+        # what the engine does for CycleGAN's residual convs: materialise the reflection padding, then a 'valid' conv
+        xpad = torch.zeros((n, h + 2 * p, w_ + 2 * p, cpi + 8), dtype=torch.bfloat16, device="cuda")
+        sv, dv = U.view(xd, 8, cpi), U.view(xpad, 8, cpi)
+        L.check(lib.semb_pad_crop(C.byref(sv), C.byref(dv), n, h, w_, h + 2 * p, w_ + 2 * p, p, p, 0, L.BF16, 0, U.stream()))
+        xd = xpad
+        geom = L.ConvGeom(n, h + 2 * p, w_ + 2 * p, h, w_, cpi, cpo, k, k, 1, 0, 0, L.PAD_ZERO, L.BF16)
     yd = torch.zeros((n, h, w_, cpo + 16), dtype=torch.bfloat16, device="cuda")
     wd, bd = U.pad_w(wt), U.pad_v(bias)
     nbytes = lib.semb_pack_weights_tc(None, k, k, cpi, cpo, 0, None, None)
@@ -641,9 +647,14 @@ def test_conv_tc_wgrad(case):
     dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
     y_ref.backward(dy)
     cpi, cpo = U.pad8(cin), U.pad8(cout)
-    pm = L.PAD_REFLECT if pad_mode == "reflect" else L.PAD_ZERO
-    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, pm, L.BF16)
+    geom = L.ConvGeom(n, h, w_, h, w_, cpi, cpo, k, k, 1, p, p, L.PAD_ZERO, L.BF16)
     xd = U.to_dev(x, "bf16", pitch=cpi + 8, coff=8)
+    if pad_mode == "reflect":
+        xpad = torch.zeros((n, h + 2 * p, w_ + 2 * p, cpi + 8), dtype=torch.bfloat16, device="cuda")
+        sv, dv = U.view(xd, 8, cpi), U.view(xpad, 8, cpi)
+        L.check(lib.semb_pad_crop(C.byref(sv), C.byref(dv), n, h, w_, h + 2 * p, w_ + 2 * p, p, p, 0, L.BF16, 0, U.stream()))
+        xd = xpad
+        geom = L.ConvGeom(n, h + 2 * p, w_ + 2 * p, h, w_, cpi, cpo, k, k, 1, 0, 0, L.PAD_ZERO, L.BF16)
     dyd = U.to_dev(dy, "bf16", pitch=cpo + 8, coff=0)
     dw = torch.ones((k, k, cpi, cpo), device="cuda")          # accumulates on top of existing content
     xv, dyv = U.view(xd, 8, cpi), U.view(dyd, 0, cpo)
