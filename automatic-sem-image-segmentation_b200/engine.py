@@ -656,6 +656,8 @@ class ConvOp(Op):
                 else:
                     self.geom_d = L.ConvGeom(n, oh, ow, self.pad_hw[0], self.pad_hw[1], cout, cin, k, k, 1, k - 1, k - 1,
                                              L.PAD_ZERO, eng.dtype)
+                    # (Tiling the batch as ONE tall image with zero separator rows -- 85 instead of 120 tiles for 8 x 34 x 34 -- was
+                    # measured in round 2: no gain, 170 CTAs still need two waves of the 148 SMs; removed.)
 
     def plan_backward(self):
         if self.x.requires_grad:

@@ -952,3 +952,41 @@ def test_device_tile_gather_and_stitch_match_the_host_grid(case):
             assert np.abs(o - ref).max() < 1e-6, mode
         else:
             assert np.array_equal(o, ref), (mode, int((o != ref).sum()))
+
+
+@pytest.mark.parametrize("case", [(3, 20, 20, 16, 24), (8, 32, 32, 128, 128), (1, 16, 24, 40, 8)])
+def test_reflect_padded_conv_op_bf16(case):
+    """ConvOp for ReflectionPadding2D(1) + 3x3 'valid' (CycleGAN.py:326-333) in bf16: materialised padding, TMA forward,
+    data gradient on the padded domain, reflect fold, weight gradient (planar-staged for >= 128 channels) -- against the
+    oracle."""
+    import numpy as np
+    from sem_b200.engine import ConvOp, Engine, ParamSpec
+    n, h, w_, cin, cout = case
+    g = torch.Generator().manual_seed(41)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wt = U.bf16_round(torch.randn(3, 3, cin, cout, generator=g) * 0.05)
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    y_ref = OL.conv2d(OL.reflection_pad(xr, 2, 2), wr, None, 1, "valid")
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    e = Engine(n, "bf16")
+    xb = e.new_buf(h, w_, cin, "x")
+    yb = e.new_buf(h, w_, cout, "y")
+    e.add_param(ParamSpec("w/kernel", "conv_kernel", (3, 3, cin, cout), (3, 3, cin, cout), {2: np.arange(cin), 3: np.arange(cout)}, True,
+                          "glorot", (1, 1)))
+    op = e.add_op(ConvOp(e, xb.view(), yb.view(), (h, w_), (h, w_), "w/kernel", None, 3, 1, (1, 1), L.PAD_REFLECT, False))
+    e.finalize()
+    assert op.x_pad is not None and op.pad_buf is not None
+    e.set_param("w/kernel", wt.numpy())
+    xb.data.copy_(x.cuda().to(torch.bfloat16))
+    e.zero_step(zero_grads=True)
+    e.forward(True)
+    torch.cuda.synchronize()
+    assert U.rel_err(yb.data.float(), y_ref) < 1e-2
+    yb.grad_tensor().copy_(dy.cuda().to(torch.bfloat16))
+    xb.grad_tensor().fill_(1.0)
+    op.acc_x = 1
+    e.backward()
+    torch.cuda.synchronize()
+    assert U.rel_err(xb.grad_tensor().float().cpu() - 1.0, xr.grad) < 2e-2
+    assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 1e-3
