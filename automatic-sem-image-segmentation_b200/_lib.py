@@ -94,6 +94,7 @@ SIGNATURES = {
     "semb_tile_stitch": (C.c_int, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P]),
     "semb_upsample2x": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _P]),
     "semb_s2d_weights": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "semb_merge_weights": (C.c_int, [_P, _P, _I, _I, _I, _P, _I, _P]),
     "semb_fold_stats4": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "semb_tap_patch": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _P, _I, _I, _P]),
     "semb_tapfold_weights": (C.c_int, [_P, _I, _I, _I, _P, _I, _I, _P]),

@@ -412,6 +412,29 @@ __global__ void s2d_weights_kernel(float* __restrict__ w, int k, int pt, int pl,
     }
 }
 
+// res_path unit (UNet_Segmentation.py:490-499): the 3x3 conv and the 1x1 shortcut conv read the same tensor, so they run as
+// ONE 3x3 conv with Ca + Cs outputs: w3[r][s][ci][0:Ca] = wa[r][s][ci][:], w3[1][1][ci][Ca:] = ws[ci][:], zero on the other
+// taps of the shortcut columns (N = 16 -> 32 costs the tensor pipe nothing at these widths; one launch, one read of the
+// input, one data gradient without a read-modify-write of dx).  dir 0 writes w3 from the masters, dir 1 ADDS the gradient
+// of w3 into the two master gradients (the off-centre shortcut taps of dw3 are dropped: those weights do not exist).
+__global__ void merge_weights_kernel(float* __restrict__ wa, float* __restrict__ ws, int Cin, int Ca, int Cs, float* __restrict__ w3, int dir) {
+    const int Ct = Ca + Cs;
+    const long long total = 9LL * Cin * Ct;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Ct);
+        const long long t = i / Ct;
+        const int ci = (int)(t % Cin), tap = (int)(t / Cin);
+        if (co < Ca) {
+            float* m = wa + ((size_t)tap * Cin + ci) * Ca + co;
+            if (dir == 0) w3[i] = *m; else *m += w3[i];
+        } else {
+            float* m = ws + (size_t)ci * Cs + (co - Ca);
+            if (dir == 0) w3[i] = tap == 4 ? *m : 0.f;
+            else if (tap == 4) *m += w3[i];
+        }
+    }
+}
+
 // stats[g][k][c] += sum_q temp[g][k][q*C + c]: moments of a depth-to-space output from the moments of its 4C-channel source
 __global__ void fold_stats4_kernel(const double* __restrict__ temp, double* __restrict__ stats, int groups, int C, int stats_nstride,
                                    int stats_cstride) {
@@ -779,6 +802,13 @@ extern "C" int semb_upsample2x(const semb_tensor* small, const semb_tensor* big,
     if (dtype == SEMB_BF16) upsample2x_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, C8, dir, acc);
     else upsample2x_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, C8, dir, acc);
     return check_launch("upsample2x");
+}
+
+extern "C" int semb_merge_weights(float* wa, float* ws, int32_t Cin, int32_t Ca, int32_t Cs, float* w3, int32_t dir, void* stream) {
+    SEMB_REQUIRE(wa && ws && w3 && Cin > 0 && Ca > 0 && Cs > 0 && (dir == 0 || dir == 1), SEMB_ESHAPE, "merge_weights: bad arguments");
+    const long long total = 9LL * Cin * (Ca + Cs);
+    merge_weights_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(wa, ws, Cin, Ca, Cs, w3, dir);
+    return check_launch("merge_weights");
 }
 
 extern "C" int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t Cin, int32_t Cout, float* w3, int32_t dir,

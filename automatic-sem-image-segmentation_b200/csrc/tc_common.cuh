@@ -20,7 +20,8 @@ static inline TcPlan tc_plan(int Cin, int Cout, int taps) {
     p.NC = ((c16 + p.nchunks - 1) / p.nchunks + 15) / 16 * 16;
     const int cin16 = (Cin + 15) / 16 * 16;
     int kc = 64;
-    while (kc > 16 && (size_t)taps * kc * p.NC * 2 + (size_t)kc * 362 > 96 * 1024) kc >>= 1;
+    static const size_t stage_budget = [] { const char* e = getenv("SEMB_TC_STAGE_KB"); const int v = e ? atoi(e) : 96; return (size_t)(v >= 16 && v <= 200 ? v : 96) * 1024; }();
+    while (kc > 16 && (size_t)taps * kc * p.NC * 2 + (size_t)kc * 362 > stage_budget) kc >>= 1;
     if (kc > cin16) kc = cin16 <= 16 ? 16 : (cin16 <= 32 ? 32 : 64);
     p.KC = kc;
     p.kchunks = (Cin + kc - 1) / kc;

@@ -274,6 +274,15 @@ class Engine:
             if nbytes < 0:
                 L.check(nbytes)
             pk["buf"] = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device=self.device)
+        recs = [r for r in self.s2d.values() if r["dw3"] is not None]
+        if recs and not self.dry:
+            flat = torch.zeros(sum(r["dw3"].numel() for r in recs), dtype=torch.float32, device=self.device)
+            o = 0
+            for r in recs:
+                n = r["dw3"].numel()
+                r["dw3"], r["flat"] = flat[o:o + n], True
+                o += n
+            self._vgrad_flat = flat
         self.finalized = True
 
     def s2d_weight(self, w: str, k: int, pt: int, pl: int, cin: int, cout: int) -> dict:
@@ -284,6 +293,21 @@ class Engine:
         if rec is None:
             n = 9 * 4 * cin * cout
             rec = {"kind": "s2d", "w": w, "k": k, "pt": pt, "pl": pl, "cin": cin, "cout": cout, "key": f"{w}/s2d{pt}{pl}",
+                   "w3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None,
+                   "dw3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None}
+            root.s2d[key] = rec
+            root._pack_dirty = True
+        return rec
+
+    def merge_weight(self, wa: str, ws: str, cin: int, ca: int, cs: int) -> dict:
+        """Virtual fp32 kernel w3 (3,3,cin,ca+cs) = [3x3 kernel `wa` | 1x1 kernel `ws` on the centre tap] (semb_merge_weights) and
+        the buffer its gradient is reduced into before it is folded into the two Keras-layout gradients."""
+        root = self.share or self
+        key = (wa, "merge", ws)
+        rec = root.s2d.get(key)
+        if rec is None:
+            n = 9 * cin * (ca + cs)
+            rec = {"kind": "merge", "w": wa, "w2": ws, "k": 3, "cin": cin, "ca": ca, "cs": cs, "cout": ca + cs, "key": f"{wa}/merge",
                    "w3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None,
                    "dw3": torch.zeros(n, dtype=torch.float32, device=self.device) if not self.dry else None}
             root.s2d[key] = rec
@@ -329,7 +353,10 @@ class Engine:
         return rec
 
     def _virtual_weight_kernel(self, rec: dict, master_ptr: int, virt_ptr: int, direction: int):
-        if rec["kind"] == "split3":
+        if rec["kind"] == "merge":
+            second = self.gptr(rec["w2"]) if direction else self.params.ptr(rec["w2"])      # weights (0) or gradients (1) of the shortcut
+            L.check(self.lib.semb_merge_weights(master_ptr, second, rec["cin"], rec["ca"], rec["cs"], virt_ptr, direction, self.stream))
+        elif rec["kind"] == "split3":
             assert direction == 0       # gradients of the split-operand convs go straight to the master gradient
             L.check(self.lib.semb_split_weights(master_ptr, rec["k"], rec["k"], rec["cin"], rec["cout"], virt_ptr, rec["axis"], rec["terms"],
                                                 self.stream))
@@ -345,8 +372,18 @@ class Engine:
         assert self.share is None
         st = self.stream
         L.check(self.lib.semb_fill_f32(self.grads.data_ptr(), self.grads.numel(), 0.0, st))
+        self._zero_virtual_grads()
+        self._vgrads_folded = False
+
+    def _zero_virtual_grads(self):
+        """The gradients of the virtual kernels live in ONE flat buffer (one fill); records created after finalize() keep
+        their own tensors."""
+        st = self.stream
+        flat = self.__dict__.get("_vgrad_flat")
+        if flat is not None:
+            L.check(self.lib.semb_fill_f32(flat.data_ptr(), flat.numel(), 0.0, st))
         for rec in self.s2d.values():
-            if rec["dw3"] is not None:
+            if rec["dw3"] is not None and not rec.get("flat"):
                 L.check(self.lib.semb_fill_f32(rec["dw3"].data_ptr(), rec["dw3"].numel(), 0.0, st))
 
     def fold_virtual_grads(self):
@@ -357,7 +394,8 @@ class Engine:
             if rec["dw3"] is None:
                 continue
             self._virtual_weight_kernel(rec, self.gptr(rec["w"]), rec["dw3"].data_ptr(), 1)
-            L.check(self.lib.semb_fill_f32(rec["dw3"].data_ptr(), rec["dw3"].numel(), 0.0, st))
+        self._zero_virtual_grads()
+        self._vgrads_folded = True
 
     def tc_pack(self, w: str, R: int, S: int, cin: int, cout: int, flip: int, vw: Optional[dict] = None) -> dict:
         for pk in self.tc_packs:
@@ -474,6 +512,7 @@ class Engine:
             op.fwd(training)
 
     def backward(self):
+        (self.share or self)._vgrads_folded = False      # new gradients of the virtual kernels are about to be produced
         for op in reversed(self.ops):
             op.bwd()
         if self.wgrad_stream is not None:
@@ -492,8 +531,8 @@ class Engine:
             fn()
 
     def adam(self, beta1: float, beta2: float, eps: float, gscale: float = 1.0):
-        if self.s2d:
-            self.fold_virtual_grads()       # no-op when the caller already folded (dw3 is zero again)
+        if self.s2d and not self.__dict__.get("_vgrads_folded", False):
+            self.fold_virtual_grads()       # skipped when the caller already folded (before its all-reduce)
         L.check(self.lib.semb_adam_step(self.params.t.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
                                         self.adam_v.data_ptr(), self.params.t.numel(), self.lr.data_ptr(),
                                         beta1, beta2, eps, gscale, self.adam_state.data_ptr(), self.stream))
@@ -857,6 +896,47 @@ class ConvOp(Op):
                                               C.byref(self.x.g), None, 0, 0, self.acc_x, e.stream))
 
 
+class PairConvOp(ConvOp):
+    """res_path unit (UNet_Segmentation.py:490-499): `Conv2D(3x3)` and the 1x1 shortcut `Conv2D` of the SAME input as ONE 3x3
+    tensor-core conv with Ca + Cs output channels (the shortcut kernel sits on the centre tap of the virtual kernel, see
+    semb_merge_weights).  y holds [3x3 output | shortcut output]; its gradient is consumed by ONE data-gradient launch (no
+    read-modify-write of dx) and ONE weight-gradient launch whose result is folded into the two Keras-layout gradients.
+    bf16 tensor-core mode only; the builders fall back to two ConvOps elsewhere."""
+
+    def __init__(self, eng: Engine, x: View, y: View, hw: Tuple[int, int], w_a: str, w_s: str, ca: int, cs: int,
+                 stats: Optional[Tuple[str, int, int, int]] = None):
+        assert eng.tc_enabled and y.C == ca + cs
+        self.eng, self.x, self.y, self.w, self.w_s, self.bias, self.transposed = eng, x, y, w_a, w_s, None, False
+        h, wd = hw
+        n, cin, cout = eng.N, x.C, ca + cs
+        self.geom = L.ConvGeom(n, h, wd, h, wd, cin, cout, 3, 3, 1, 1, 1, L.PAD_ZERO, eng.dtype)
+        self.stats = stats
+        self.acc_x = 0
+        self.use_tc = True
+        self.pad_buf = self.s2d = self.tapfold = self.x_pad = self.split = None
+        self.rec = eng.merge_weight(w_a, w_s, cin, ca, cs)
+        self.pk_fwd = eng.tc_pack(self.rec["key"], 3, 3, cin, cout, 0, vw=self.rec)
+        self.pk_bwd = None
+        if x.requires_grad:
+            self.pk_bwd = eng.tc_pack(self.rec["key"], 3, 3, cin, cout, 1, vw=self.rec)
+            self.geom_d = L.ConvGeom(n, h, wd, h, wd, cout, cin, 3, 3, 1, 1, 1, L.PAD_ZERO, eng.dtype)
+        # algorithmic work of the two reference layers (the zero taps of the shortcut columns are not counted)
+        self.alg_flops = 2.0 * n * h * wd * cin * (9 * ca + cs)
+
+    def fwd(self, training: bool):
+        e = self.eng
+        sp, ns, cs = self._stats_args() if training else (None, 0, 0)
+        L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom), C.byref(self.x.t), self.pk_fwd["buf"].data_ptr(), None, C.byref(self.y.t),
+                                         sp, ns, cs, 0, e.stream))
+
+    def bwd(self):
+        e = self.eng
+        e.on_wgrad_stream(lambda: e.wgrad_tc(self.geom, self.x.t, self.y.g, self.rec["dw3"].data_ptr()))
+        if self.x.requires_grad:
+            L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_d), C.byref(self.y.g), self.pk_bwd["buf"].data_ptr(), None, C.byref(self.x.g),
+                                             None, 0, 0, self.acc_x, e.stream))
+
+
 class NormOp(Op):
     """Turns accumulated moments into (scale, shift, mean, invstd); BatchNorm (groups=1) or InstanceNorm (groups=N).
 
@@ -874,12 +954,20 @@ class NormOp(Op):
         self.nstride = 0 if groups == 1 else c
         self.stats_nstride = 0 if groups == 1 else 2 * c
         self.consumers = 0       # AffineOps applying this norm; with exactly one the finalize is folded into its kernel
+        # where the fp64 moments are: (zeroed-store name, channel offset, stride between the sum and the sum of squares);
+        # a PairConvOp writes the moments of two norms into ONE block (bind_stats)
+        self.stats_off, self.stats_cs = 0, c
+
+    def bind_stats(self, name: str, off: int, cstride: int):
+        """Moments come from a block shared with another norm: channel `off` of a `cstride`-channel record (BatchNorm only)."""
+        assert self.groups == 1
+        self.stats, self.stats_off, self.stats_cs = name, off, cstride
 
     def s(self, k: str) -> int:
         return self.eng.scratch.ptr(f"{self.name}/{k}")
 
     def stats_ref(self, coff: int = 0):
-        return (self.stats, coff, self.stats_nstride, self.C)
+        return (self.stats, self.stats_off + coff, self.stats_nstride, self.stats_cs)
 
     def folded(self, training: bool) -> bool:
         return self.eng.fold_norm and self.consumers == 1 and self.uses_batch_stats(training)
@@ -890,8 +978,8 @@ class NormOp(Op):
         f = L.NormFin()
         f.scale, f.shift = self.s("scale") + 4 * coff, self.s("shift") + 4 * coff
         if self.folded(training):
-            f.stats = e.zeroed.ptr(self.stats, 2 * coff)
-            f.stats_nstride, f.cstride = self.stats_nstride, self.C
+            f.stats = e.zeroed.ptr(self.stats, 2 * (self.stats_off + coff))
+            f.stats_nstride, f.cstride = self.stats_nstride, self.stats_cs
             f.count, f.eps = self.count, self.eps
             f.gamma = (e.params.ptr(self.gamma) + 4 * coff) if self.gamma else None
             f.beta = e.params.ptr(self.beta) + 4 * coff
@@ -910,7 +998,7 @@ class NormOp(Op):
         if training or self.moving is None:
             mm = e.state.ptr(self.moving[0]) if (self.moving and training) else None
             mv = e.state.ptr(self.moving[1]) if (self.moving and training) else None
-            L.check(e.lib.semb_norm_finalize(e.zeroed.ptr(self.stats), self.groups, self.C, self.C, self.stats_nstride,
+            L.check(e.lib.semb_norm_finalize(e.zeroed.ptr(self.stats, 2 * self.stats_off), self.groups, self.C, self.stats_cs, self.stats_nstride,
                                              self.count, self.eps, gamma, beta, self.s("scale"), self.s("shift"),
                                              self.s("mean"), self.s("invstd"), mm, mv, self.momentum, e.stream))
         else:

@@ -212,9 +212,16 @@ def profile_ops(inst, weighting, peaks, size, batch):
     e.on_wgrad_stream = timed_wgrad
     e.zero_step(zero_grads=True)
     inst.stage_in()
+    # The host needs ~20-40 us per op (ctypes call + two event records), more than most kernels run: without a head start the
+    # device idles between ops and every event pair also measures the launch latency of its kernel (round 1/2: the eager
+    # sum was 18.3 ms for a 14.4 ms serialised graph step, small kernels were overstated by 30-100 %).  A spin kernel keeps
+    # the device busy until the whole forward + backward is queued, so the events see back-to-back execution.
+    # (one spin per pass: the launch queue holds ~1k commands)
+    torch.cuda._sleep(int(0.040 * 1.9e9))
     for op in e.ops:
         timed("fwd", op, lambda op=op: op.fwd(True))
     inst.loss(weighting, with_grad=True)
+    torch.cuda._sleep(int(0.040 * 1.9e9))
     for op in reversed(e.ops):
         wg.pop("last", None)
         timed("bwd", op, lambda op=op: op.bwd())
@@ -232,7 +239,8 @@ def profile_ops(inst, weighting, peaks, size, batch):
         if isinstance(op, ConvOp):
             g = op.geom
             pix = g.N * g.OH * g.OW
-            flops = 2.0 * pix * g.R * g.S * g.Cin * g.Cout                     # physical (8-padded) channels
+            # physical (8-padded) channels; a merged res_path conv counts the work of its two reference layers (alg_flops)
+            flops = getattr(op, "alg_flops", None) or 2.0 * pix * g.R * g.S * g.Cin * g.Cout
             nbytes = (g.N * g.H * g.W * g.Cin + pix * g.Cout) * esz             # input + output activations once
             tc = op.use_tc and e.dtype_name == "bf16"
             row.update({"geom": f"{g.H}x{g.W} {g.Cin}->{g.Cout} k{g.R} s{g.stride}{' T' if op.transposed else ''}",

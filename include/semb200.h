@@ -157,6 +157,10 @@ int semb_pixel_shuffle2x(const semb_tensor* src, const semb_tensor* dst, int32_t
                          int32_t DW, const float* bias, int32_t dir, int32_t acc, int32_t dtype, void* stream);
 int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t Cin, int32_t Cout, float* w3, int32_t dir,
                      void* stream);
+/* res_path unit (UNet_Segmentation.py:490-499): Conv2D 3x3 (wa: 3,3,Cin,Ca) and the 1x1 shortcut Conv2D (ws: 1,1,Cin,Cs) of the
+ * same input as ONE 3x3 conv with Ca+Cs outputs.  dir 0: w3 (3,3,Cin,Ca+Cs) <- [wa | ws on the centre tap, 0 elsewhere];
+ * dir 1: dwa += dw3[..., :Ca], dws += dw3[1,1,:,Ca:] (gradient of the virtual kernel folded into the Keras-layout gradients). */
+int semb_merge_weights(float* wa, float* ws, int32_t Cin, int32_t Ca, int32_t Cs, float* w3, int32_t dir, void* stream);
 int semb_fold_stats4(const void* temp, void* stats, int32_t groups, int32_t C, int32_t stats_nstride, int32_t stats_cstride,
                      void* stream);
 

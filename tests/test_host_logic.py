@@ -286,3 +286,28 @@ def test_workflow_steps_0_and_5_and_step_functions(tmp_path):
         assert callable(getattr(SP, name))
     with pytest.raises(NotImplementedError):
         SP.start_step_1()
+
+
+def test_res_path_units_merge_into_pair_convs_only_in_bf16_mode(monkeypatch):
+    """Host logic only (dry engines): in bf16 tensor-core mode the res_path units whose merged weight image stays resident
+    (rp1 x 4 at full resolution, rp2 units 2-3) run their 3x3 conv and 1x1 shortcut as one PairConvOp; parameter names,
+    creation order and the Keras layer order are identical to the unmerged build; fp32 parity mode never merges."""
+    from sem_b200.engine import ConvOp, PairConvOp
+
+    def build(dtype):
+        e = Engine(1, dtype, dry=True)
+        b = UNetBuilder(e, 64, 64, 16)
+        e.finalize()
+        return e, b
+
+    e16, b16 = build("bf16")
+    e32, b32 = build("f32")
+    pairs = [op for op in e16.ops if isinstance(op, PairConvOp)]
+    assert len(pairs) == 6 and not any(isinstance(op, PairConvOp) for op in e32.ops)
+    assert [(op.geom.Cin, op.geom.Cout) for op in pairs] == [(32, 32), (16, 32), (16, 32), (16, 32), (32, 64), (32, 64)]
+    assert b16.creation_names == b32.creation_names and b16.keras_weight_names() == b32.keras_weight_names()
+    n_conv = lambda e: sum(isinstance(op, ConvOp) for op in e.ops)
+    assert n_conv(e32) - n_conv(e16) == 6
+    monkeypatch.setenv("SEMB_NO_PAIR_CONV", "1")
+    e_off, _ = build("bf16")
+    assert not any(isinstance(op, PairConvOp) for op in e_off.ops)

@@ -990,3 +990,56 @@ def test_reflect_padded_conv_op_bf16(case):
     torch.cuda.synchronize()
     assert U.rel_err(xb.grad_tensor().float().cpu() - 1.0, xr.grad) < 2e-2
     assert U.rel_err(torch.from_numpy(e.get_grad("w/kernel")), wr.grad) < 1e-3
+
+
+@pytest.mark.parametrize("case", [(2, 24, 40, 16, 16, 16), (3, 16, 16, 32, 32, 32), (1, 20, 12, 8, 8, 24)])
+def test_pair_conv_op_bf16(case):
+    """PairConvOp: the 3x3 conv and the 1x1 shortcut conv of a res_path unit (UNet_Segmentation.py:490-499) as ONE 3x3 conv
+    over the merged virtual kernel (semb_merge_weights): both outputs, their batch moments in the shared record, the data
+    gradient of the pair and the two Keras-layout weight gradients after the fold -- against the oracle's two convs."""
+    import numpy as np
+    from sem_b200.engine import Engine, PairConvOp, ParamSpec
+    n, h, w_, cin, ca, cs = case
+    g = torch.Generator().manual_seed(7)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wa = U.bf16_round(torch.randn(3, 3, cin, ca, generator=g) * 0.1)
+    ws = U.bf16_round(torch.randn(1, 1, cin, cs, generator=g) * 0.2)
+    xr, war, wsr = x.clone().requires_grad_(True), wa.clone().requires_grad_(True), ws.clone().requires_grad_(True)
+    ya = OL.conv2d(xr, war, None, 1, "same")
+    ys = OL.conv2d(xr, wsr, None, 1, "same")
+    y_ref = torch.cat([ya, ys], dim=-1)
+    dy = U.bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    e = Engine(n, "bf16")
+    xb = e.new_buf(h, w_, cin, "x")
+    yb = e.new_buf(h, w_, ca + cs, "y")
+    ident = lambda c: np.arange(c)
+    e.add_param(ParamSpec("a/kernel", "conv_kernel", (3, 3, cin, ca), (3, 3, cin, ca), {2: ident(cin), 3: ident(ca)}, True, "glorot", (1, 1)))
+    e.add_param(ParamSpec("s/kernel", "conv_kernel", (1, 1, cin, cs), (1, 1, cin, cs), {2: ident(cin), 3: ident(cs)}, True, "glorot", (1, 1)))
+    mom = e.zeroed.add("pair/moments", 4 * (ca + cs))
+    op = e.add_op(PairConvOp(e, xb.view(), yb.view(), (h, w_), "a/kernel", "s/kernel", ca, cs, stats=(mom, 0, 0, ca + cs)))
+    e.finalize()
+    e.set_param("a/kernel", wa.numpy())
+    e.set_param("s/kernel", ws.numpy())
+    xb.data.copy_(x.cuda().to(torch.bfloat16))
+    e.zero_step(zero_grads=True)
+    e.forward(True)
+    torch.cuda.synchronize()
+    assert U.rel_err(yb.data.float(), y_ref) < 1e-2
+    o, cnt = e.zeroed.entries[mom]
+    st = e.zeroed.t[o:o + cnt].view(torch.float64).cpu()
+    yq = yb.data.float().cpu()           # moments are taken from the fp32 accumulators, compare with the oracle's fp32 result
+    assert U.rel_err(st[:ca + cs].float(), y_ref.detach().sum(dim=(0, 1, 2))) < 2e-3, (st[:4], yq.sum(dim=(0, 1, 2))[:4])
+    assert U.rel_err(st[ca + cs:].float(), (y_ref.detach() ** 2).sum(dim=(0, 1, 2))) < 2e-3
+    yb.grad_tensor().copy_(dy.cuda().to(torch.bfloat16))
+    e.backward()
+    e.fold_virtual_grads()
+    torch.cuda.synchronize()
+    assert op.acc_x == 0
+    assert U.rel_err(xb.grad_tensor().float().cpu(), xr.grad) < 2e-2
+    assert U.rel_err(torch.from_numpy(e.get_grad("a/kernel")), war.grad) < 1e-3
+    assert U.rel_err(torch.from_numpy(e.get_grad("s/kernel")), wsr.grad) < 1e-3
+    # a second fold must not add anything (the virtual gradient buffer is zero again)
+    e.fold_virtual_grads()
+    torch.cuda.synchronize()
+    assert U.rel_err(torch.from_numpy(e.get_grad("s/kernel")), wsr.grad) < 1e-3
