@@ -6,6 +6,7 @@
 // carried in registers across the block's pixel loop, combined in shared memory and flushed with one
 // atomic per channel per block.
 #include "common.cuh"
+#include <stdlib.h>
 
 // pixels a thread keeps in flight per loop iteration (16-byte loads per operand), tuned on B200
 #ifndef SEMB_AFF_U_FWD
@@ -61,7 +62,40 @@ struct AffArgs {
     unsigned int* barrier;
     // b as a concatenation of up to three compact tensors (semb_affine_desc.nseg_b)
     int nseg_b; int seg_c0[3]; View seg_b[3], seg_db[3];
+    // bf16 operands through a per-thread cp.async ring in dynamic shared memory (byte offset ring_off), see OperandRing
+    int ring, ring_off;
 };
+
+// ---- per-thread asynchronous operand ring (bf16 tensors) ----------------------------------------------------------------
+// ncu, round 1: the affine kernels reached 64-66 % of the DRAM peak with 35 % of the warps resident and 21-31 % issue
+// utilisation -- latency-bound: with register prefetch a thread holds 2 pixels x 2-3 operands x 16 B in flight (49 KB per
+// SM, ~7 MB on the chip, about the bandwidth-delay product with nothing to spare while a warp computes and stores).
+// Here every thread copies ITS OWN 16-byte operand chunks S iterations ahead with cp.async (LDGSTS, L1 bypass) into a slot
+// only it reads back: no block-level synchronisation, no registers held by loads in flight, 75-170 KB in flight per SM.
+// Slot of (stage, operand) for thread t: ring + ((stage * NOPS + operand) * 256 + t) * 16 -- conflict-free LDS.128.
+// p.ring = number of stages S (a power of two <= 8; 0 = register prefetch).  Measured on B200 (profiles/r02_ab_ring.txt): the
+// ring lifts the two-operand forward from 3.8-4.3 to 5.2-5.7 TB/s and the reduction pass from 4.4-5.2 to 5.3-6.4 TB/s
+// (97 % of the measured copy peak at C = 32); the gradient pass and the one-operand forward, already at 5.3-6.0 TB/s alone,
+// gain nothing in isolation but the whole step is fastest with every kernel on the ring (12.45 vs 13.0 ms, r02_ab_ring3.txt).
+__device__ __forceinline__ void cp_async_wait_stages(int S) {      // wait until at most S - 1 groups are pending
+    switch (S) {
+        case 8: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 // The view and the channel offset inside it that hold channel c of the b operand (resp. of its gradient).
 __device__ __forceinline__ View b_view(const AffArgs& p, int c, int& cc, bool grad) {
@@ -169,7 +203,7 @@ __device__ __forceinline__ void fin_params(const semb_norm_fin& f, int g, int c,
 
 // y = act(a*sa+ta [+ actb(b*sb+tb)]), optional fp64 moments of y.  U pixels per thread are loaded before any is used.
 template <typename T, bool HAS_B, int ACT, int ACTB>
-__global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p) {
+__global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_fwd_kernel(const AffArgs p) {
     pdl_trigger();
     pdl_wait();
     extern __shared__ float sm[];  // [rows][2][C] + [<=256] when moments are requested
@@ -204,7 +238,47 @@ __global__ void __launch_bounds__(256, 3) affine_act_fwd_kernel(const AffArgs p)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
 
-    if (L.active) {
+    bool ringed = false;
+    if constexpr (sizeof(T) == 2) {
+        if (p.ring && L.active) {
+            ringed = true;
+            const int S = p.ring; constexpr int NOPS = HAS_B ? 2 : 1;
+            const uint32_t ring = smem_addr(sm) + (uint32_t)p.ring_off + threadIdx.x * 16u;
+            const int first = begin + L.prow;
+            const int niter = first < end ? (end - first + L.rows - 1) / L.rows : 0;
+            auto issue = [&](int it) {
+                if (it < niter) {
+                    const long long px = pix0 + first + (long long)it * L.rows;
+                    const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
+                    cp_async16(slot, vptr<T>(p.a, px, c));
+                    if (HAS_B) cp_async16(slot + 4096u, vptr<T>(bv, px, cb));
+                }
+                cp_async_commit();          // empty groups keep the group count uniform
+            };
+            for (int i = 0; i < S - 1; ++i) issue(i);
+            for (int it = 0; it < niter; ++it) {
+                issue(it + S - 1);
+                cp_async_wait_stages(S);
+                const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
+                Raw8<T> ra, rb;
+                ra.r = lds128(slot);
+                if (HAS_B) rb.r = lds128(slot + 4096u);
+                float va[8], vb[8], vy[8];
+                ra.unpack(va);
+                if (HAS_B) rb.unpack(vb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float t = fmaf(va[i], sa[i], ta[i]);
+                    if (HAS_B) t += act_fwd(fmaf(vb[i], sb[i], tb[i]), actb);
+                    vy[i] = act_fwd(t, act);
+                    s1[i] += vy[i];
+                    s2[i] += vy[i] * vy[i];
+                }
+                Vec8<T>::store(vptr_mut<T>(p.y, pix0 + first + (long long)it * L.rows, c), vy);
+            }
+        }
+    }
+    if (L.active && !ringed) {
         for (int base = begin + L.prow; base < end; base += L.rows * U) {
             Raw8<T> ra[U], rb[U];
 #pragma unroll
@@ -285,7 +359,54 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_reduce_kern
 #pragma unroll
     for (int i = 0; i < 8; ++i) { q0[i] = q1[i] = q2[i] = q3[i] = 0.f; }
 
-    if (L.active) {
+    bool ringed = false;
+    if constexpr (sizeof(T) == 2) {
+        if (p.ring && L.active) {
+            ringed = true;
+            const int S = p.ring; constexpr int NOPS = HAS_B ? 3 : 2;
+            const uint32_t ring = smem_addr(sm) + (uint32_t)p.ring_off + threadIdx.x * 16u;
+            const int first = begin + L.prow;
+            const int niter = first < end ? (end - first + L.rows - 1) / L.rows : 0;
+            auto issue = [&](int it) {
+                if (it < niter) {
+                    const long long px = pix0 + first + (long long)it * L.rows;
+                    const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
+                    cp_async16(slot, vptr<T>(p.dy, px, c));
+                    cp_async16(slot + 4096u, vptr<T>(p.a, px, c));
+                    if (HAS_B) cp_async16(slot + 8192u, vptr<T>(bv, px, cb));
+                }
+                cp_async_commit();
+            };
+            for (int i = 0; i < S - 1; ++i) issue(i);
+            for (int it = 0; it < niter; ++it) {
+                issue(it + S - 1);
+                cp_async_wait_stages(S);
+                const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
+                Raw8<T> rg, ra, rb;
+                rg.r = lds128(slot);
+                ra.r = lds128(slot + 4096u);
+                if (HAS_B) rb.r = lds128(slot + 8192u);
+                float g[8], va[8], vb[8];
+                rg.unpack(g);
+                ra.unpack(va);
+                if (HAS_B) rb.unpack(vb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float ub = 0.f, t = fmaf(va[i], sa[i], ta[i]);
+                    if (HAS_B) { ub = fmaf(vb[i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                    const float gg = g[i] * act_bwd_from_u(t, act);
+                    q0[i] += gg;
+                    q1[i] += gg * (va[i] - ma[i]);
+                    if (HAS_B) {
+                        const float gb = gg * act_bwd_from_u(ub, actb);
+                        q2[i] += gb;
+                        q3[i] += gb * (vb[i] - mb[i]);
+                    }
+                }
+            }
+        }
+    }
+    if (L.active && !ringed) {
         for (int base = begin + L.prow; base < end; base += L.rows * U) {
             Raw8<T> rg[U], ra[U], rb[U];
 #pragma unroll
@@ -411,6 +532,71 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
     const bool wa = p.da.ptr != nullptr, wb = HAS_B && dbv.ptr != nullptr;
     if (!wa && !wb) return;
 
+    if constexpr (sizeof(T) == 2) {
+        if (p.ring) {
+            extern __shared__ float sm[];
+            const int S = p.ring; constexpr int NOPS = HAS_B ? 3 : 2;
+            const uint32_t ring = smem_addr(sm) + (uint32_t)p.ring_off + threadIdx.x * 16u;
+            const int first = begin + L.prow;
+            const int niter = first < end ? (end - first + L.rows - 1) / L.rows : 0;
+            auto issue = [&](int it) {
+                if (it < niter) {
+                    const long long px = pix0 + first + (long long)it * L.rows;
+                    const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
+                    cp_async16(slot, vptr<T>(p.dy, px, c));
+                    cp_async16(slot + 4096u, vptr<T>(p.a, px, c));
+                    if (HAS_B) cp_async16(slot + 8192u, vptr<T>(bv, px, cb));
+                }
+                cp_async_commit();
+            };
+            for (int i = 0; i < S - 1; ++i) issue(i);
+            for (int it = 0; it < niter; ++it) {
+                issue(it + S - 1);
+                const long long px = pix0 + first + (long long)it * L.rows;
+                // gradients that accumulate (rare: a tensor with a second consumer earlier in the backward order) are read
+                // directly, before the wait, so that their latency overlaps the ring's
+                float olda[8], oldb[8];
+                if (wa && p.acc_a) Vec8<T>::load(vptr<T>(p.da, px, c), olda);
+                if (wb && p.acc_b) Vec8<T>::load(vptr<T>(dbv, px, cdb), oldb);
+                cp_async_wait_stages(S);
+                const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
+                Raw8<T> rg, ra, rb;
+                rg.r = lds128(slot);
+                ra.r = lds128(slot + 4096u);
+                if (HAS_B) rb.r = lds128(slot + 8192u);
+                float g[8], va[8], vb[8], da[8], db[8];
+                rg.unpack(g);
+                ra.unpack(va);
+                if (HAS_B) rb.unpack(vb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float ub = 0.f, t = fmaf(va[i], sa[i], ta[i]);
+                    if (HAS_B) { ub = fmaf(vb[i], sb[i], tb[i]); t += act_fwd(ub, actb); }
+                    const float gg = g[i] * act_bwd_from_u(t, act);
+                    da[i] = fmaf(sa[i], gg, fmaf(Pa[i], va[i], Qa[i]));
+                    if (HAS_B) {
+                        const float gb = gg * act_bwd_from_u(ub, actb);
+                        db[i] = fmaf(sb[i], gb, fmaf(Pb[i], vb[i], Qb[i]));
+                    }
+                }
+                if (wa) {
+                    if (p.acc_a) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) da[i] += olda[i];
+                    }
+                    Vec8<T>::store(vptr_mut<T>(p.da, px, c), da);
+                }
+                if (wb) {
+                    if (p.acc_b) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) db[i] += oldb[i];
+                    }
+                    Vec8<T>::store(vptr_mut<T>(dbv, px, cdb), db);
+                }
+            }
+            return;
+        }
+    }
     for (int base = begin + L.prow; base < end; base += L.rows * U) {
         Raw8<T> rg[U], ra[U], rb[U];
 #pragma unroll
@@ -843,7 +1029,42 @@ extern "C" int semb_norm_bwd_finalize(const float* sums, int32_t which, int32_t 
 
 
 // every affine kernel starts with pdl_trigger() / pdl_wait() (the fused cooperative one is launched elsewhere)
-#define SEMB_AFF_GO(grid, smem, st, p, ...) launch_pdl(__VA_ARGS__, dim3(grid), dim3(256), smem, st, p)
+#define SEMB_AFF_GO(grid, smem, st, p, ...)                                                                         \
+    do {                                                                                                            \
+        if ((smem) > 48 * 1024) cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
+        launch_pdl(__VA_ARGS__, dim3(grid), dim3(256), smem, st, p);                                                \
+    } while (0)
+
+// Operand ring of the bf16 kernels (OperandRing above): appends `stages * nops` 4 KB slot planes to the kernel's dynamic
+// shared memory and returns the total; `blocks` is lowered to what then fits an SM.  SEMB_AFF_NO_RING=1: register prefetch.
+enum { RING_FWD = 0, RING_FWDB, RING_RED, RING_REDB, RING_APP, RING_APPB };
+static int ring_stages(int which) {
+    // defaults from the B200 measurements above; SEMB_AFF_RING="fwd,fwdb,red,redb,app,appb" overrides (0 / 2 / 4 / 8 each)
+    static int st[6] = {8, 8, 4, 4, 8, 8};
+    static const bool init = [] {
+        if (const char* e = getenv("SEMB_AFF_RING")) {
+            int v[6];
+            if (sscanf(e, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6)
+                for (int i = 0; i < 6; ++i) if (v[i] == 0 || v[i] == 2 || v[i] == 4 || v[i] == 8) st[i] = v[i];
+        }
+        if (const char* e = getenv("SEMB_AFF_NO_RING")) if (e[0] && e[0] != '0') for (int i = 0; i < 6; ++i) st[i] = 0;
+        return true;
+    }();
+    (void)init;
+    return st[which];
+}
+static size_t ring_setup(AffArgs& p, int dtype, size_t base_bytes, int stages, int nops, int* blocks) {
+    p.ring = 0;
+    p.ring_off = 0;
+    if (dtype != SEMB_BF16 || stages == 0) return base_bytes;
+    const size_t off = (base_bytes + 15) / 16 * 16;
+    p.ring = stages;
+    p.ring_off = (int)off;
+    const size_t total = off + (size_t)stages * nops * 4096;
+    const int fit = (int)((224 * 1024) / (total + 1024));
+    if (*blocks > fit) *blocks = fit < 1 ? 1 : fit;
+    return total;
+}
 
 // (activation, second-operand activation) combinations compiled statically; anything else takes the runtime path
 #define SEMB_AFF_DISPATCH(KERNEL, T, HASB, grid, smem, st, p)                                                       \
@@ -886,8 +1107,9 @@ extern "C" int semb_affine_act_fwd(const semb_affine_desc* d, const semb_tensor*
     p.a = mkview(a); p.b = mkview(b); p.y = mkview(y);
     p.scale_a = scale_a; p.shift_a = shift_a; p.scale_b = scale_b; p.shift_b = shift_b;
     p.dstats = reinterpret_cast<double*>(stats); p.stats_nstride = stats_nstride; p.stats_cstride = stats_cstride;
-    dim3 grid = aff_grid(p, d->aff_nstride != 0 || (stats && stats_nstride != 0), 3);
-    const size_t smem = stats ? ((size_t)(256 / (d->C / 8)) * 2 * d->C + 256) * sizeof(float) : 0;
+    int blocks = 3;
+    const size_t smem = ring_setup(p, d->dtype, stats ? ((size_t)(256 / (d->C / 8)) * 2 * d->C + 256) * sizeof(float) : 0, ring_stages(b ? RING_FWDB : RING_FWD), b ? 2 : 1, &blocks);
+    dim3 grid = aff_grid(p, d->aff_nstride != 0 || (stats && stats_nstride != 0), blocks);
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_fwd_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_fwd");
@@ -914,8 +1136,9 @@ extern "C" int semb_affine_act_bwd_reduce(const semb_affine_desc* d, const semb_
     p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b;
     p.stats = sums; p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
-    dim3 grid = aff_grid(p, d->aff_nstride != 0 || sums_nstride != 0, b ? 2 : 3);
-    const size_t smem = ((size_t)(256 / (d->C / 8)) * (b ? 4 : 2) * d->C + 256) * sizeof(float);
+    int blocks = b ? 2 : 3;
+    const size_t smem = ring_setup(p, d->dtype, ((size_t)(256 / (d->C / 8)) * (b ? 4 : 2) * d->C + 256) * sizeof(float), ring_stages(b ? RING_REDB : RING_RED), b ? 3 : 2, &blocks);
+    dim3 grid = aff_grid(p, d->aff_nstride != 0 || sums_nstride != 0, blocks);
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_bwd_reduce_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_bwd_reduce");
@@ -946,9 +1169,11 @@ extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_t
     p.scale_a = scale_a; p.shift_a = shift_a; p.mean_a = mean_a; p.invstd_a = invstd_a; p.c1_a = c1_a; p.c2_a = c2_a;
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b; p.c1_b = c1_b; p.c2_b = c2_b;
     p.acc_a = acc_a; p.acc_b = acc_b;
-    dim3 grid = aff_grid(p, d->aff_nstride != 0, b ? 2 : 3);
+    int blocks = b ? 2 : 3;
+    const size_t smem = ring_setup(p, d->dtype, 0, ring_stages(b ? RING_APPB : RING_APP), b ? 3 : 2, &blocks);
+    dim3 grid = aff_grid(p, d->aff_nstride != 0, blocks);
     cudaStream_t st = as_stream(stream);
-    SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, 0, st, p);
+    SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_bwd_apply");
 }
 
@@ -972,8 +1197,9 @@ extern "C" int semb_affine_act_fwd_fin(const semb_affine_desc* d, const semb_ten
     if (fin_a) { p.fa = *fin_a; p.scale_a = fin_a->scale; p.shift_a = fin_a->shift; }
     if (fin_b) { p.fb = *fin_b; p.scale_b = fin_b->scale; p.shift_b = fin_b->shift; }
     p.dstats = reinterpret_cast<double*>(stats); p.stats_nstride = stats_nstride; p.stats_cstride = stats_cstride;
-    dim3 grid = aff_grid(p, d->aff_nstride != 0 || (stats && stats_nstride != 0), 3);
-    const size_t smem = stats ? ((size_t)(256 / (d->C / 8)) * 2 * d->C + 256) * sizeof(float) : 0;
+    int blocks = 3;
+    const size_t smem = ring_setup(p, d->dtype, stats ? ((size_t)(256 / (d->C / 8)) * 2 * d->C + 256) * sizeof(float) : 0, ring_stages(b ? RING_FWDB : RING_FWD), b ? 2 : 1, &blocks);
+    dim3 grid = aff_grid(p, d->aff_nstride != 0 || (stats && stats_nstride != 0), blocks);
     cudaStream_t st = as_stream(stream);
     SEMB_AFF_LAUNCH(affine_act_fwd_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_fwd_fin");
@@ -1007,9 +1233,11 @@ extern "C" int semb_affine_act_bwd_apply_sums(const semb_affine_desc* d, const s
     p.dgamma_a = dgamma_a; p.dbeta_a = dbeta_a; p.dgamma_b = dgamma_b; p.dbeta_b = dbeta_b;
     p.stats = const_cast<float*>(sums); p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
     p.acc_a = acc_a; p.acc_b = acc_b;
-    dim3 grid = aff_grid(p, d->aff_nstride != 0 || sums_nstride != 0, b ? 2 : 3);
+    int blocks = b ? 2 : 3;
+    const size_t smem = ring_setup(p, d->dtype, 0, ring_stages(b ? RING_APPB : RING_APP), b ? 3 : 2, &blocks);
+    dim3 grid = aff_grid(p, d->aff_nstride != 0 || sums_nstride != 0, blocks);
     cudaStream_t st = as_stream(stream);
-    SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, 0, st, p);
+    SEMB_AFF_LAUNCH(affine_act_bwd_apply_kernel, d->dtype, b != nullptr, grid, smem, st, p);
     return check_launch("affine_act_bwd_apply_sums");
 }
 
