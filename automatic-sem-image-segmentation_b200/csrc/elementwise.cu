@@ -64,6 +64,7 @@ struct AffArgs {
     int nseg_b; int seg_c0[3]; View seg_b[3], seg_db[3];
     // bf16 operands through a per-thread cp.async ring in dynamic shared memory (byte offset ring_off), see OperandRing
     int ring, ring_off;
+    int rev;    // gradient pass: walk the block's pixel range backwards (what the reduction pass read last is still in L2)
 };
 
 // ---- per-thread asynchronous operand ring (bf16 tensors) ----------------------------------------------------------------
@@ -539,9 +540,12 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
             const uint32_t ring = smem_addr(sm) + (uint32_t)p.ring_off + threadIdx.x * 16u;
             const int first = begin + L.prow;
             const int niter = first < end ? (end - first + L.rows - 1) / L.rows : 0;
+            // The reduction pass (same grid, same ranges) walked forwards: the tail of every block's range is what L2 still
+            // holds, so this pass walks BACKWARDS and ends on the heads, where the next layer's reduction pass starts.
+            const bool rev = p.rev != 0;
             auto issue = [&](int it) {
                 if (it < niter) {
-                    const long long px = pix0 + first + (long long)it * L.rows;
+                    const long long px = pix0 + first + (long long)(rev ? niter - 1 - it : it) * L.rows;
                     const uint32_t slot = ring + (uint32_t)((it & (S - 1)) * NOPS) * 4096u;
                     cp_async16(slot, vptr<T>(p.dy, px, c));
                     cp_async16(slot + 4096u, vptr<T>(p.a, px, c));
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(256, HAS_B ? 2 : 3) affine_act_bwd_apply_kerne
             for (int i = 0; i < S - 1; ++i) issue(i);
             for (int it = 0; it < niter; ++it) {
                 issue(it + S - 1);
-                const long long px = pix0 + first + (long long)it * L.rows;
+                const long long px = pix0 + first + (long long)(rev ? niter - 1 - it : it) * L.rows;
                 // gradients that accumulate (rare: a tensor with a second consumer earlier in the backward order) are read
                 // directly, before the wait, so that their latency overlaps the ring's
                 float olda[8], oldb[8];
@@ -1170,6 +1174,8 @@ extern "C" int semb_affine_act_bwd_apply(const semb_affine_desc* d, const semb_t
     p.scale_b = scale_b; p.shift_b = shift_b; p.mean_b = mean_b; p.invstd_b = invstd_b; p.c1_b = c1_b; p.c2_b = c2_b;
     p.acc_a = acc_a; p.acc_b = acc_b;
     int blocks = b ? 2 : 3;
+    static const int walk_back = [] { const char* e = getenv("SEMB_AFF_APPLY_FORWARD"); return (e && e[0] && e[0] != '0') ? 0 : 1; }();
+    p.rev = walk_back;
     const size_t smem = ring_setup(p, d->dtype, 0, ring_stages(b ? RING_APPB : RING_APP), b ? 3 : 2, &blocks);
     dim3 grid = aff_grid(p, d->aff_nstride != 0, blocks);
     cudaStream_t st = as_stream(stream);
@@ -1234,6 +1240,8 @@ extern "C" int semb_affine_act_bwd_apply_sums(const semb_affine_desc* d, const s
     p.stats = const_cast<float*>(sums); p.stats_nstride = sums_nstride; p.stats_cstride = sums_cstride;
     p.acc_a = acc_a; p.acc_b = acc_b;
     int blocks = b ? 2 : 3;
+    static const int walk_back = [] { const char* e = getenv("SEMB_AFF_APPLY_FORWARD"); return (e && e[0] && e[0] != '0') ? 0 : 1; }();
+    p.rev = walk_back;
     const size_t smem = ring_setup(p, d->dtype, 0, ring_stages(b ? RING_APPB : RING_APP), b ? 3 : 2, &blocks);
     dim3 grid = aff_grid(p, d->aff_nstride != 0 || sums_nstride != 0, blocks);
     cudaStream_t st = as_stream(stream);
