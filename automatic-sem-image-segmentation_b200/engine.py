@@ -219,6 +219,15 @@ class Engine:
         # meet again at the optimizer); set by the model front end, off for weight-sharing towers
         self.wgrad_stream: Optional[torch.cuda.Stream] = None
         self.skip_wgrad = False
+        # Side lanes: groups of ops whose results the main chain needs only much later (the res_path of every encoder level
+        # is consumed by the decoder level of the same resolution) are issued on their own stream and so overlap the deep,
+        # low-resolution part of the network, whose 64-1024-tile kernels leave most SMs idle.  Builders tag ops through
+        # `cur_lane` / `join_next`; the model front end switches the streams on (`enable_lanes`).
+        self.cur_lane = 0
+        self._pending_join: set = set()
+        self.lane_streams: Dict[int, torch.cuda.Stream] = {}
+        self.lanes_on = False
+        self.bwd_order: Optional[List["Op"]] = None
         # weight sharing between towers of the same network (CycleGAN applies each generator three times per step):
         # a sharing engine has its own buffers / ops / scratch but uses the root's parameters, gradients and packs
         self.share = share
@@ -246,8 +255,44 @@ class Engine:
         store.add(spec.name, int(np.prod(spec.phys_shape)))
 
     def add_op(self, op: "Op"):
+        op.lane = self.cur_lane
+        op.join_fwd, op.join_bwd = set(), set()
+        if self.cur_lane == 0 and self._pending_join:
+            op.join_fwd, self._pending_join = self._pending_join, set()     # first main-lane consumer of the lanes' results
         self.ops.append(op)
         return op
+
+    def join_next(self, lane: int):
+        """The next op added on the main lane reads what `lane` produces."""
+        if lane:
+            self._pending_join.add(lane)
+
+    def enable_lanes(self):
+        if any(op.lane for op in self.ops) and not self.dry:
+            for l in sorted({op.lane for op in self.ops if op.lane}):
+                self.lane_streams[l] = torch.cuda.Stream(device=self.device)
+            self.lanes_on = True
+
+    def _plan_bwd_order(self):
+        """Backward issue order: reversed forward order, except that the ops of a side lane move up to right after the
+        backward of the op that joined the lane in the forward pass -- the earliest reader of the lane's output, hence the
+        op that completes its gradient -- instead of waiting behind the whole deep part of the network.  The op that
+        followed the group in plain reversed order (it accumulates into the lane's input gradient) joins the lane."""
+        rev = list(reversed(self.ops))
+        lanes = sorted({op.lane for op in self.ops if op.lane})
+        for l in lanes:
+            group = [op for op in rev if op.lane == l]
+            first = rev.index(group[0])
+            after = [op for op in rev[first:] if op.lane == 0]
+            joiner = [op for op in rev if l in op.join_fwd]
+            if not joiner or rev.index(joiner[0]) > first:
+                continue            # no consumer recorded (or it already comes later): keep the plain order
+            if after:
+                after[0].join_bwd.add(l)
+            rest = [op for op in rev if op.lane != l]
+            at = rest.index(joiner[0]) + 1
+            rev = rest[:at] + group + rest[at:]
+        self.bwd_order = rev
 
     def finalize(self):
         if self.share is not None:
@@ -257,6 +302,7 @@ class Engine:
             self.grads, self.adam_m, self.adam_v, self.adam_state, self.lr = r.grads, r.adam_m, r.adam_v, r.adam_state, r.lr
             for op in reversed(self.ops):
                 op.plan_backward()
+            self._plan_bwd_order()
             self.finalized = True
             return
         for s in (self.params, self.state, self.zeroed, self.scratch):
@@ -269,6 +315,7 @@ class Engine:
         # static plan of gradient accumulation: walk the ops in backward order once
         for op in reversed(self.ops):
             op.plan_backward()
+        self._plan_bwd_order()
         for pk in self.tc_packs:
             nbytes = int(self.lib.semb_pack_weights_tc(None, pk["R"], pk["S"], pk["Cin"], pk["Cout"], pk["flip"], None, None))
             if nbytes < 0:
@@ -508,13 +555,37 @@ class Engine:
         root = self.share or self
         if root._pack_dirty and root.tc_packs:
             root.repack()
-        for op in self.ops:
-            op.fwd(training)
+        self._run(self.ops, lambda op: op.fwd(training), "join_fwd")
+
+    def _run(self, order, call, join_attr: str):
+        """Issues `order` with side-lane ops on their streams: a lane forks from the main stream at its first op (it then
+        depends on everything queued on the main stream so far) and is joined by the main-lane ops that name it."""
+        if not self.lanes_on:
+            for op in order:
+                call(op)
+            return
+        main = torch.cuda.current_stream(self.device)
+        active = set()
+        for op in order:
+            if op.lane:
+                st = self.lane_streams[op.lane]
+                if op.lane not in active:
+                    st.wait_stream(main)
+                    active.add(op.lane)
+                with torch.cuda.stream(st):
+                    call(op)
+            else:
+                for l in getattr(op, join_attr):
+                    if l in active:
+                        main.wait_stream(self.lane_streams[l])
+                        active.discard(l)
+                call(op)
+        for l in active:
+            main.wait_stream(self.lane_streams[l])
 
     def backward(self):
         (self.share or self)._vgrads_folded = False      # new gradients of the virtual kernels are about to be produced
-        for op in reversed(self.ops):
-            op.bwd()
+        self._run(self.bwd_order if self.bwd_order is not None else list(reversed(self.ops)), lambda op: op.bwd(), "join_bwd")
         if self.wgrad_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.wgrad_stream)       # join before the optimizer
 

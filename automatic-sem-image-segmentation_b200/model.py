@@ -41,6 +41,7 @@ class _Instance:
         e.finalize()
         if os.environ.get("SEMB_NO_WGRAD_STREAM") is None and not e.tc_split:      # split-operand scratch is shared: one stream
             e.wgrad_stream = torch.cuda.Stream(device=e.device)
+            e.enable_lanes()        # res_paths on their own streams (no-op under SEMB_NO_LANES)
         self.n, self.h, self.w = n, h, w
         self.x_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)
         self.y_dev = torch.zeros((n, h, w, 1), dtype=torch.float32, device=e.device)

@@ -259,6 +259,22 @@ class UNetBuilder:
         hw = inp.h * inp.w
         count = e.N * hw
         x = inp
+        # the decoder level of the same resolution is the only consumer: the whole path is a side lane (Engine.cur_lane)
+        # that overlaps the deeper levels in both passes
+        self._lanes = getattr(self, "_lanes", 0) + 1
+        lane = self._lanes if (final_view is not None and os.environ.get("SEMB_NO_LANES") is None) else 0
+        prev_lane, e.cur_lane = e.cur_lane, lane
+        try:
+            x = self._res_path_units(filters, length, inp, name, final_view, lay, hw, count)
+        finally:
+            e.cur_lane = prev_lane
+        x.lane = lane
+        self.taps[name] = x
+        return x
+
+    def _res_path_units(self, filters, length, inp, name, final_view, lay, hw, count):
+        e = self.e
+        x = inp
         for i in range(length):
             s_raw, bns, o_raw, bno = self.res_unit_raw(x, lay)
             kact1 = self.kg.layer("activation", [o_raw.klayer])
@@ -276,7 +292,6 @@ class UNetBuilder:
                 out_view = e.new_buf(inp.h, inp.w, lay.phys, f"{name}_{i}").view()
             e.add_op(AffineOp(e, hw, summed.view(), bng, None, None, out_view, L.ACT_NONE))
             x = T(out_view, inp.h, inp.w, lay, kbn)
-        self.taps[name] = x
         return x
 
     def up_concat(self, x: T, filters: int, skip_buf: Buf, skip: T, name: str) -> T:
@@ -318,6 +333,7 @@ class UNetBuilder:
         y4 = e.new_buf(x.h, x.w, 4 * co_p, name + "_y4")
         e.add_op(ConvOp(e, x.view, y4.view(), (x.h, x.w), (x.h, x.w), wname, None, 1, 1, (0, 0), L.PAD_ZERO, False))
         e.add_op(ShuffleOp(e, y4.view(), up_view, x.h, x.w, bname))
+        e.join_next(getattr(skip, "lane", 0))       # the next op (the decoder block's first conv) reads the res_path's output
         return T(skip_buf.view(), 2 * x.h, 2 * x.w, Layout.concat(lay, skip.layout), kcat)
 
     def _build(self, in_channels: int):

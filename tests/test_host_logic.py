@@ -311,3 +311,33 @@ def test_res_path_units_merge_into_pair_convs_only_in_bf16_mode(monkeypatch):
     monkeypatch.setenv("SEMB_NO_PAIR_CONV", "1")
     e_off, _ = build("bf16")
     assert not any(isinstance(op, PairConvOp) for op in e_off.ops)
+
+
+def test_res_path_lanes_are_planned_around_their_producers_and_consumers():
+    """Host logic only: every res_path is a side lane; forward joins at the decoder block that reads the skip concat; the
+    backward order moves the lane right behind that block's backward (not behind the whole deep part of the net) and the
+    op that accumulates into the lane's input gradient (the max-pool of the level) joins it."""
+    from sem_b200.engine import ConvOp, PoolOp
+    e = Engine(1, "bf16", dry=True)
+    UNetBuilder(e, 64, 64, 16)
+    e.finalize()
+    lanes = sorted({op.lane for op in e.ops if op.lane})
+    assert lanes == [1, 2, 3, 4]
+    order = e.bwd_order
+    assert sorted(map(id, order)) == sorted(map(id, e.ops))
+    pos = {id(op): i for i, op in enumerate(order)}
+    fpos = {id(op): i for i, op in enumerate(e.ops)}
+    for l in lanes:
+        group = [op for op in e.ops if op.lane == l]
+        joiner = [op for op in e.ops if l in op.join_fwd]
+        assert len(joiner) == 1 and isinstance(joiner[0], ConvOp) and joiner[0].lane == 0
+        assert fpos[id(joiner[0])] > max(fpos[id(op)] for op in group)          # forward: consumer after the lane
+        gp = sorted(pos[id(op)] for op in group)
+        assert gp == list(range(gp[0], gp[0] + len(group)))                      # contiguous in the backward order ...
+        assert gp[0] == pos[id(joiner[0])] + 1                                   # ... right behind the consumer's backward
+        assert [pos[id(op)] for op in reversed(group)] == gp                     # ... in reversed forward order
+        bj = [op for op in e.ops if l in op.join_bwd]
+        assert len(bj) == 1 and isinstance(bj[0], PoolOp) and pos[id(bj[0])] > gp[-1]
+    # ops that share a gradient buffer keep their planned relative order: the lane's first conv writes d(m_k) before the pool adds to it
+    main = [op for op in order if op.lane == 0]
+    assert main == [op for op in reversed(e.ops) if op.lane == 0]
