@@ -62,9 +62,13 @@ __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 
-// NCT: compile-time channel count of the register-moment epilogue (16 / 32, 0 = generic).  KR: kernel size.
+// NCT: compile-time channel count of the register-moment epilogue (16, 0 = generic).  KR: kernel size.
 // KS: K steps per chunk when all input channels fit one chunk (1..4, straight-line MMA issue), 0 = run-time.
-template <int NCT, int KR, int KS>
+// CS ("column split", NCT = 16 with an MMA width of 32): both epilogue groups work on EVERY tile, group g on the accumulator
+// columns [16 g, 16 g + 16), so that 32-channel layers (the merged res_path convs, the 1x1 shortcuts of the full-resolution
+// blocks) keep their moments in registers too -- the generic epilogue's per-tile butterfly reductions made N = 32 cost
+// 92 us where N = 16 cost 49 (256x256, batch 32).
+template <int NCT, int KR, int KS, bool CS = false>
 __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs args, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TM_MAX_STAGES], empty_bar[TM_MAX_STAGES], acc_full[TM_MAX_ACC], acc_empty[TM_MAX_ACC], b_full;
@@ -72,7 +76,9 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     pdl_trigger();                  // the successor's prologue may overlap this kernel's tail
     const TcArgs& a = args.t;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KC = a.p.KC, NC = NCT > 0 ? NCT : a.p.NC, kchunks = a.p.kchunks;
+    constexpr int NCM = CS ? 32 : NCT;                 // MMA width when it is a compile-time constant
+    constexpr int PN = CS ? 16 : NCT;                  // channels of one epilogue group (register-moment path)
+    const int KC = a.p.KC, NC = NCT > 0 ? NCM : a.p.NC, kchunks = a.p.kchunks;
     const int nchunk = blockIdx.y;
     const int nstages = args.nstages;
     const int nacc = args.nacc;
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     if (warp == 8) tmem_alloc_rt(smem_u32(&tmem_slot), (uint32_t)args.tmem_cols);
     if (tid == 0) {
         for (int i = 0; i < nstages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
-        for (int i = 0; i < TM_MAX_ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), 128); }
+        for (int i = 0; i < TM_MAX_ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), CS ? 256 : 128); }
         mbar_init(smem_u32(&b_full), 1);
     }
     // Planes beyond Cin (Cin % 16 == 8) are never written by the TMA: they must hold finite values (their weights are 0).
@@ -208,30 +214,31 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
         const int wq = warp & 3;                          // TMEM lane quarter this warp may read
         const int etid = tid & 127;
         float* part = part_all + grp * 8 * NC;
-        const int c_begin = nchunk * NC;
+        const int PW = CS ? 16 : NC;                       // channels this group reduces (row pitch of its partials)
+        const int c_begin = nchunk * NC + (CS ? grp * 16 : 0);
         int cur_n = -1;
         auto combine = [&](int n) {
             // the group's 128 threads: combine the four warps' partial moments in a fixed order, one fp64 atomic per channel
             asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-            for (int i = etid; i < NC; i += 128) {
+            for (int i = etid; i < PW; i += 128) {
                 const int c = c_begin + i;
                 if (c < a.Cout) {
-                    const float t1 = ((part[i] + part[NC + i]) + part[2 * NC + i]) + part[3 * NC + i];
-                    const float t2 = ((part[4 * NC + i] + part[5 * NC + i]) + part[6 * NC + i]) + part[7 * NC + i];
+                    const float t1 = ((part[i] + part[PW + i]) + part[2 * PW + i]) + part[3 * PW + i];
+                    const float t2 = ((part[4 * PW + i] + part[5 * PW + i]) + part[6 * PW + i]) + part[7 * PW + i];
                     double* st = a.stats + (size_t)n * a.stats_nstride + c;
                     atomicAdd(st, (double)t1);
                     atomicAdd(st + a.stats_cstride, (double)t2);
                 }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
-            for (int i = etid; i < 8 * NC; i += 128) part[i] = 0.f;
+            for (int i = etid; i < 8 * PW; i += 128) part[i] = 0.f;
             asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
         };
         const int m = wq * 32 + lane;
         const int my = m / TILE_W, mx = m % TILE_W;
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
         const int nuse = nacc >> 1;                        // buffers of this group: grp, grp + 2, ...
-        TileIter it(blockIdx.x + grp * gridDim.x, 2 * gridDim.x, a.tiles_x, a.tiles_y);
+        TileIter it(CS ? blockIdx.x : blockIdx.x + grp * gridDim.x, CS ? gridDim.x : 2 * gridDim.x, a.tiles_x, a.tiles_y);
         if constexpr (NCT > 0) {
             float s1[NCT], s2[NCT];
 #pragma unroll
@@ -243,21 +250,22 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
 #pragma unroll
                     for (int i = 0; i < 16; ++i) w[i] = s1[q * 16 + i];
                     warp_reduce16(w, lane);
-                    if ((lane & 1) == 0) part[wq * NC + q * 16 + (lane >> 1)] = w[0];
+                    if ((lane & 1) == 0) part[wq * PN + q * 16 + (lane >> 1)] = w[0];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) w[i] = s2[q * 16 + i];
                     warp_reduce16(w, lane);
-                    if ((lane & 1) == 0) part[(4 + wq) * NC + q * 16 + (lane >> 1)] = w[0];
+                    if ((lane & 1) == 0) part[(4 + wq) * PN + q * 16 + (lane >> 1)] = w[0];
                 }
 #pragma unroll
                 for (int i = 0; i < NCT; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
                 combine(n);
             };
-            for (int ti = grp, k = 0; ti < ntiles; ti += 2, ++k, it.next()) {
+            const int cg0 = CS ? grp * 16 : 0;                  // first channel (of the chunk) this group stores / reduces
+            for (int ti = CS ? 0 : grp, k = 0; ti < ntiles; ti += CS ? 1 : 2, ++k, it.next()) {
                 const int buf = ti % nacc;
-                const uint32_t acc_addr = lane_addr + buf * NC;
+                const uint32_t acc_addr = lane_addr + buf * NC + cg0;
                 const uint32_t full_u32 = smem_u32(&acc_full[buf]), empty_u32 = smem_u32(&acc_empty[buf]);
-                const uint32_t fpar = (uint32_t)(k / nuse) & 1u;
+                const uint32_t fpar = CS ? (uint32_t)(ti / nacc) & 1u : (uint32_t)(k / nuse) & 1u;
                 if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) flush_regs(cur_n);
                 cur_n = it.n;
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
@@ -272,7 +280,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                     tmem_ld16(acc_addr + h * 16, v16);
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        const int c = h * 16 + half * 8;
+                        const int cl = h * 16 + half * 8;           // channel inside this group's register moments
+                        const int c = cg0 + cl;                     // channel of the output tensor
                         const bool cvalid = c < a.Cout;
                         float v[8];
 #pragma unroll
@@ -283,7 +292,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
                         }
                         if (a.stats && pvalid && !(a.dbg & 8)) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) { s1[c + i] += v[i]; s2[c + i] = fmaf(v[i], v[i], s2[c + i]); }
+                            for (int i = 0; i < 8; ++i) { s1[cl + i] += v[i]; s2[cl + i] = fmaf(v[i], v[i], s2[cl + i]); }
                         }
                         if (pvalid && cvalid && !(a.dbg & 4)) {
                             if (a.accumulate) {
@@ -445,8 +454,13 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
 
     cudaError_t e = cudaSuccess;
 #define SEMB_TM_LAUNCH3(NCT, KR, KS)                                                                                     \
-    e = cudaFuncSetAttribute(conv_tma_kernel<NCT, KR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-    if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<NCT, KR, KS>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap);
+    if (colsplit) {                                                                                                      \
+        e = cudaFuncSetAttribute(conv_tma_kernel<16, KR, KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<16, KR, KS, true>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap); \
+    } else {                                                                                                             \
+        e = cudaFuncSetAttribute(conv_tma_kernel<NCT, KR, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<NCT, KR, KS>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap); \
+    }
 #define SEMB_TM_LAUNCH2(NCT, KR)                                                                                         \
     switch (ks_fixed) {                                                                                                  \
         case 1: SEMB_TM_LAUNCH3(NCT, KR, 1) break;                                                                       \
@@ -457,8 +471,11 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     }
 #define SEMB_TM_LAUNCH(NCT)                                                                                              \
     if (g->R == 3) { SEMB_TM_LAUNCH2(NCT, 3) } else { SEMB_TM_LAUNCH2(NCT, 1) }
-    // NC == 32 would need 64 moment registers per thread (spills under the 92-register cap): generic epilogue
-    if (a.p.NC == 16) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
+    // NC == 32 in one group would need 64 moment registers per thread (spills under the 92-register cap): the two epilogue
+    // groups split the columns instead (CS); wider layers take the generic epilogue
+    static const bool cs_on = [] { const char* e = getenv("SEMB_TMA_NO_COLSPLIT"); return !(e && e[0] && e[0] != '0'); }();
+    const bool colsplit = cs_on && a.p.NC == 32 && A.nacc == 4;
+    if (a.p.NC == 16 || colsplit) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
 #undef SEMB_TM_LAUNCH
 #undef SEMB_TM_LAUNCH2
 #undef SEMB_TM_LAUNCH3
