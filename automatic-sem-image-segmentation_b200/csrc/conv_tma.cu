@@ -68,8 +68,14 @@ __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
 // columns [16 g, 16 g + 16), so that 32-channel layers (the merged res_path convs, the 1x1 shortcuts of the full-resolution
 // blocks) keep their moments in registers too -- the generic epilogue's per-tile butterfly reductions made N = 32 cost
 // 92 us where N = 16 cost 49 (256x256, batch 32).
-template <int NCT, int KR, int KS, bool CS = false>
-__global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs args, const __grid_constant__ CUtensorMap xmap) {
+// PAIR (streamed weights only, NCT = KS = 0): the CTA walks 16x16 SUPER-tiles (two 16x8 tiles side by side, one 18x18 halo per
+// channel-group plane).  Every stage carries ONE weight chunk that both tiles use -- MMA warp j issues tile j's MMAs from the same
+// stage into its own accumulator, epilogue group j stores tile j -- so the L2 -> shared-memory weight stream, which paced the
+// deep layers (CycleGAN 512->512 at 32x32: 2.4 MB of weights per 128 output pixels, 88 us against a 19 us tensor-pipe floor), is
+// halved per output pixel, and the chunk plan caps N at 128 (A fetch and MMA both 64 cycles) so that two tiles x two
+// accumulator generations fit the 512 TMEM columns.
+template <int NCT, int KR, int KS, bool CS = false, bool PAIR = false>
+__global__ void __launch_bounds__(TM_THREADS, PAIR ? 1 : 2) conv_tma_kernel(const TmArgs args, const __grid_constant__ CUtensorMap xmap) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TM_MAX_STAGES], empty_bar[TM_MAX_STAGES], acc_full[TM_MAX_ACC], acc_empty[TM_MAX_ACC], b_full;
     __shared__ uint32_t tmem_slot;
@@ -82,7 +88,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
     const int nchunk = blockIdx.y;
     const int nstages = args.nstages;
     const int nacc = args.nacc;
-    constexpr int HALO_W = TILE_W + KR - 1;
+    constexpr int TW = PAIR ? 2 * TILE_W : TILE_W;     // width of the (super-)tile one ring stage serves
+    constexpr int HALO_W = TW + KR - 1;
     // smem (128-byte aligned): [resident B (optional)] [nstages x (A planes [+ B chunk])] [moment partials 2 x 8 x NC floats]
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
 
     if (warp == 8) tmem_alloc_rt(smem_u32(&tmem_slot), (uint32_t)args.tmem_cols);
     if (tid == 0) {
-        for (int i = 0; i < nstages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+        for (int i = 0; i < nstages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), PAIR ? 2 : 1); }
         for (int i = 0; i < TM_MAX_ACC; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), CS ? 256 : 128); }
         mbar_init(smem_u32(&b_full), 1);
     }
@@ -123,12 +130,14 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
             // The ring is split in two halves, one per MMA warp (tile parity): every barrier has exactly one consumer
             // that waits on each of its phases in order (a consumer that skipped phases could not tell them apart).
             TileIter it(blockIdx.x, gridDim.x, a.tiles_x, a.tiles_y);
-            const int half = args.nmma == 2 ? nstages >> 1 : nstages;
+            // (PAIR: one ring, both MMA warps consume every stage and the empty barriers count two commits)
+            const bool split = !PAIR && args.nmma == 2;
+            const int half = split ? nstages >> 1 : nstages;
             int slot0 = 0, slot1 = 0;
             uint32_t ph0 = 1, ph1 = 1;
             for (int ti = 0; ti < ntiles; ++ti, it.next()) {
-                const int y0 = it.ty * TILE_H - a.pad_t, x0 = it.tx * TILE_W - a.pad_l;
-                const int w = args.nmma == 2 ? (ti & 1) : 0;
+                const int y0 = it.ty * TILE_H - a.pad_t, x0 = it.tx * TW - a.pad_l;
+                const int w = split ? (ti & 1) : 0;
                 for (int kc = 0; kc < kchunks; ++kc) {
                     const int stage = w ? half + slot1 : slot0;
                     mbar_wait(smem_u32(&empty_bar[stage]), w ? ph1 : ph0);
@@ -172,20 +181,20 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
             const uint32_t stage16 = (uint32_t)a.stage_bytes >> 4;
             const uint32_t btap = (uint32_t)(KC / 8) * NC;
             if (a.b_resident) mbar_wait(smem_u32(&b_full), 0);
-            const int half = nmma == 2 ? nstages >> 1 : nstages;
+            const int half = PAIR ? nstages : (nmma == 2 ? nstages >> 1 : nstages);
             int slot = 0, buf = mw;
             uint32_t phase = 0, aphase = 1;
-            for (int ti = mw; ti < ntiles; ti += nmma) {
+            for (int ti = PAIR ? 0 : mw; ti < ntiles; ti += PAIR ? 1 : nmma) {
                 mbar_wait(smem_u32(&acc_empty[buf]), aphase);
                 tc_fence_after();
                 const uint32_t dcol = tmem + buf * NC;
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    const int stage = mw * half + slot;
+                    const int stage = PAIR ? slot : mw * half + slot;
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
                     const int ksteps = KS > 0 ? KS : (min(KC, a.Cin - kc * KC) + 15) / 16;
                     const uint32_t soff = (uint32_t)stage * stage16;
-                    const uint32_t a_lo = a_lo0 + soff;
+                    const uint32_t a_lo = a_lo0 + soff + (PAIR ? (uint32_t)(mw * TILE_W) : 0u);    // tile j of the pair: 8 pixels = 8 x 16 B to the right
                     const uint32_t b_lo = b_lo0 + (a.b_resident ? 0u : soff);
                     if (!(a.dbg & 2)) {
 #pragma unroll
@@ -238,7 +247,8 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
         const int my = m / TILE_W, mx = m % TILE_W;
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
         const int nuse = nacc >> 1;                        // buffers of this group: grp, grp + 2, ...
-        TileIter it(CS ? blockIdx.x : blockIdx.x + grp * gridDim.x, CS ? gridDim.x : 2 * gridDim.x, a.tiles_x, a.tiles_y);
+        // (CS and PAIR: both groups visit every (super-)tile of the CTA; otherwise the groups alternate tiles)
+        TileIter it((CS || PAIR) ? blockIdx.x : blockIdx.x + grp * gridDim.x, (CS || PAIR) ? gridDim.x : 2 * gridDim.x, a.tiles_x, a.tiles_y);
         if constexpr (NCT > 0) {
             float s1[NCT], s2[NCT];
 #pragma unroll
@@ -310,14 +320,14 @@ __global__ void __launch_bounds__(TM_THREADS, 2) conv_tma_kernel(const TmArgs ar
             }
             if (a.stats && cur_n >= 0) flush_regs(a.stats_nstride != 0 ? cur_n : 0);
         } else {
-            for (int ti = grp, k = 0; ti < ntiles; ti += 2, ++k, it.next()) {
-                const int buf = ti % nacc;
+            for (int ti = PAIR ? 0 : grp, k = 0; ti < ntiles; ti += PAIR ? 1 : 2, ++k, it.next()) {
+                const int buf = PAIR ? grp + 2 * (k % nuse) : ti % nacc;      // this group's buffers: grp, grp + 2
                 const uint32_t acc_addr = lane_addr + buf * NC;
                 const uint32_t full_u32 = smem_u32(&acc_full[buf]), empty_u32 = smem_u32(&acc_empty[buf]);
                 const uint32_t fpar = (uint32_t)(k / nuse) & 1u;
                 if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) combine(cur_n);
                 cur_n = it.n;
-                const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
+                const int oy = it.ty * TILE_H + my, ox = it.tx * TW + (PAIR ? grp * TILE_W : 0) + mx;
                 const bool pvalid = oy < a.OH && ox < a.OW;
                 bf16* yp = a.y + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
                 float* ypf = reinterpret_cast<float*>(a.y) + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
@@ -392,10 +402,19 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     a.wp = reinterpret_cast<const bf16*>(w_packed); a.bias = bias;
     a.stats = reinterpret_cast<double*>(stats); a.stats_nstride = stats_nstride; a.stats_cstride = stats_cstride;
     a.accumulate = accumulate;
-    a.tiles_x = cdiv(g->OW, TILE_W); a.tiles_y = cdiv(g->OH, TILE_H);
-    a.total_tiles = g->N * a.tiles_x * a.tiles_y;
     a.p = tc_plan(g->Cin, g->Cout, g->R * g->S);
-    a.halo_h = TILE_H + g->R - 1; a.halo_w = TILE_W + g->S - 1;
+    // PAIR mode (see the kernel): every layer whose weights are streamed per K chunk and whose image is wider than one tile
+    static const bool pair_on = [] { const char* e = getenv("SEMB_TMA_NO_PAIR"); return !(e && e[0] && e[0] != '0'); }();
+    bool pair = pair_on && a.p.kchunks > 1 && a.p.NC <= 128 && g->OW > TILE_W;
+    if (pair) {                              // two stages of pair-sized halo planes + weight chunk must fit (tc_plan sizes K chunks for it)
+        const size_t pp = (size_t)((TILE_H + g->R - 1) * (2 * TILE_W + g->S - 1) * 16 + 127) / 128 * 128;
+        const size_t st = (size_t)(a.p.KC / 8) * pp + (size_t)g->R * g->S * a.p.KC * a.p.NC * 2;
+        if (2 * st + (size_t)16 * a.p.NC * sizeof(float) + 128 > 220 * 1024) pair = false;
+    }
+    const int tw = pair ? 2 * TILE_W : TILE_W;
+    a.tiles_x = cdiv(g->OW, tw); a.tiles_y = cdiv(g->OH, TILE_H);
+    a.total_tiles = g->N * a.tiles_x * a.tiles_y;
+    a.halo_h = TILE_H + g->R - 1; a.halo_w = tw + g->S - 1;
     A.plane_box = a.halo_h * a.halo_w * 16;
     A.plane_pitch = (A.plane_box + 127) / 128 * 128;
     a.plane_bytes = A.plane_pitch;
@@ -409,21 +428,25 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     int nst = 2;
     while (nst < TM_MAX_STAGES && (size_t)(nst + 1) * a.stage_bytes + fixed <= 100 * 1024 && (size_t)nst * a.stage_bytes < 48 * 1024) ++nst;
     while (nst > 2 && (size_t)nst * a.stage_bytes + fixed > 220 * 1024) --nst;
+    if (pair) {                              // one CTA per SM: as many stages as fit (the weight stream wants bytes in flight)
+        nst = 2;
+        while (nst < TM_MAX_STAGES && (size_t)(nst + 1) * a.stage_bytes + fixed <= 200 * 1024) ++nst;
+    }
     if (const char* env = getenv("SEMB_TMA_STAGES")) { const int v = atoi(env); if (v >= 2 && v <= TM_MAX_STAGES) nst = v; }
-    A.nmma = nst >= 4 ? 2 : 1;
-    if (A.nmma == 2) nst &= ~1;             // two half-rings, one per MMA warp
+    A.nmma = (pair || nst >= 4) ? 2 : 1;
+    if (A.nmma == 2 && !pair) nst &= ~1;    // two half-rings, one per MMA warp
     A.nstages = nst;
     a.stages = nst;
     A.bsplit = 1;
     if (!a.b_resident) {
-        static const int want = [] { const char* e = getenv("SEMB_TMA_BSPLIT"); return e ? atoi(e) : 1; }();
-        int q = want < 1 ? 1 : want;
+        static const int want = [] { const char* e = getenv("SEMB_TMA_BSPLIT"); return e ? atoi(e) : 0; }();
+        int q = want < 1 ? (pair ? 4 : 1) : want;
         while (q > 1 && (a.b_bytes % (q * 16)) != 0) --q;
         A.bsplit = q;
     }
     const size_t smem = (size_t)nst * a.stage_bytes + fixed;
     SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tma: %zu bytes of shared memory needed", smem);
-    A.nacc = a.p.NC <= 64 ? 4 : 2;
+    A.nacc = (a.p.NC <= 64 || pair) ? 4 : 2;
     if (const char* env = getenv("SEMB_TMA_NACC")) { const int v = atoi(env); if (v == 2 || (v == 4 && a.p.NC <= 128)) A.nacc = v; }
     const int need = A.nacc * a.p.NC;
     const int ks_fixed = a.p.kchunks == 1 ? (g->Cin + 15) / 16 : 0;
@@ -474,8 +497,16 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     // NC == 32 in one group would need 64 moment registers per thread (spills under the 92-register cap): the two epilogue
     // groups split the columns instead (CS); wider layers take the generic epilogue
     static const bool cs_on = [] { const char* e = getenv("SEMB_TMA_NO_COLSPLIT"); return !(e && e[0] && e[0] != '0'); }();
-    const bool colsplit = cs_on && a.p.NC == 32 && A.nacc == 4;
-    if (a.p.NC == 16 || colsplit) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
+    const bool colsplit = cs_on && a.p.NC == 32 && A.nacc == 4 && !pair;
+    if (pair) {
+        if (g->R == 3) {
+            e = cudaFuncSetAttribute(conv_tma_kernel<0, 3, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<0, 3, 0, false, true>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap);
+        } else {
+            e = cudaFuncSetAttribute(conv_tma_kernel<0, 1, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<0, 1, 0, false, true>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap);
+        }
+    } else if (a.p.NC == 16 || colsplit) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
 #undef SEMB_TM_LAUNCH
 #undef SEMB_TM_LAUNCH2
 #undef SEMB_TM_LAUNCH3

@@ -12,20 +12,32 @@ constexpr int TC_THREADS = 128;
 struct TcPlan { int KC, NC, nchunks, kchunks, tmem_cols; };
 
 // Shared-memory budget: A planes + B taps must leave room for 2 CTAs per SM.
-static inline TcPlan tc_plan(int Cin, int Cout, int taps) {
+static inline TcPlan tc_plan_nc(int Cin, int Cout, int taps, int nc_max, int a_bytes_per_channel) {
     TcPlan p;
     const int c16 = (Cout + 15) / 16 * 16;
-    static const int nc_max = [] { const char* e = getenv("SEMB_TC_NC_MAX"); const int v = e ? atoi(e) : 256; return v >= 16 && v <= 256 ? v / 16 * 16 : 256; }();
     p.nchunks = (c16 + nc_max - 1) / nc_max;
     p.NC = ((c16 + p.nchunks - 1) / p.nchunks + 15) / 16 * 16;
     const int cin16 = (Cin + 15) / 16 * 16;
     int kc = 64;
     static const size_t stage_budget = [] { const char* e = getenv("SEMB_TC_STAGE_KB"); const int v = e ? atoi(e) : 96; return (size_t)(v >= 16 && v <= 200 ? v : 96) * 1024; }();
-    while (kc > 16 && (size_t)taps * kc * p.NC * 2 + (size_t)kc * 362 > stage_budget) kc >>= 1;
+    while (kc > 16 && (size_t)taps * kc * p.NC * 2 + (size_t)kc * a_bytes_per_channel > stage_budget) kc >>= 1;
     if (kc > cin16) kc = cin16 <= 16 ? 16 : (cin16 <= 32 ? 32 : 64);
     p.KC = kc;
     p.kchunks = (Cin + kc - 1) / kc;
     p.tmem_cols = p.NC <= 32 ? 32 : (p.NC <= 64 ? 64 : (p.NC <= 128 ? 128 : 256));
+    return p;
+}
+
+// The plan is a function of (Cin, Cout, taps) only: weight packing and every launch agree on it without sharing state.
+// Layers whose weights do not fit one K chunk (streamed per chunk from L2) are planned with N <= 128, which is what the
+// two-tiles-per-weight-chunk mode of conv_tma.cu needs (two tiles x two accumulator generations in 512 TMEM columns;
+// M128 x N128 x K16 is also where the A-operand fetch and the MMA take the same 64 cycles).
+static inline TcPlan tc_plan(int Cin, int Cout, int taps) {
+    static const int nc_max = [] { const char* e = getenv("SEMB_TC_NC_MAX"); const int v = e ? atoi(e) : 256; return v >= 16 && v <= 256 ? v / 16 * 16 : 256; }();
+    static const bool pair_on = [] { const char* e = getenv("SEMB_TMA_NO_PAIR"); return !(e && e[0] && e[0] != '0'); }();
+    TcPlan p = tc_plan_nc(Cin, Cout, taps, nc_max, 362);            // 16x8 tile: 18 x 10 halo pixels x 2 B, + slack
+    // streamed: N <= 128 and the K chunk sized for the 18 x 18 halo of a tile pair (5248 B per 8-channel plane)
+    if (pair_on && p.kchunks > 1) p = tc_plan_nc(Cin, Cout, taps, nc_max < 128 ? nc_max : 128, 656);
     return p;
 }
 

@@ -541,6 +541,11 @@ TC_CASES = [
     (4, 64, 64, 16, 16, 3, "zero"),        # many tiles
     (1, 16, 16, 13, 26, 3, "zero"),        # channel counts that are not multiples of 8 (padded lanes)
     (1, 16, 16, 105, 51, 1, "zero"),
+    # two-tiles-per-weight-chunk mode of conv_tma (streamed weights, image wider than one tile):
+    (3, 40, 24, 136, 40, 3, "zero"),       # second super-tile of a row has only its left tile inside the image; partial rows
+    (8, 128, 128, 72, 24, 3, "zero"),      # 512 super-tiles on <= 148 CTAs: ring wrap-around and accumulator phase flips
+    (2, 32, 40, 200, 136, 1, "zero"),      # 1x1, four K chunks, two N chunks
+    (2, 32, 32, 264, 200, 3, "zero"),      # N chunks of 112 (re-planned from one chunk of 208)
 ]
 
 
