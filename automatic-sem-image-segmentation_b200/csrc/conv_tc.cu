@@ -325,6 +325,18 @@ extern "C" int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x,
     return conv_tma_launch(g, x, w_packed, bias, y, stats, stats_nstride, stats_cstride, accumulate, stream);
 }
 
+extern "C" int semb_conv2d_fwd_tc_d2s(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
+                                      const semb_tensor* up, int32_t UH, int32_t UW, void* stream) {
+    SEMB_REQUIRE(g && x && up && w_packed, SEMB_ESHAPE, "conv_tc_d2s: null argument");
+    SEMB_REQUIRE(g->dtype == SEMB_BF16 && g->stride == 1 && g->R == 1 && g->S == 1 && g->pad_mode == SEMB_PAD_ZERO && g->pad_t == 0 && g->pad_l == 0 &&
+                 g->OH == g->H && g->OW == g->W, SEMB_ESHAPE, "conv_tc_d2s: 1x1 stride-1 bf16 geometry only");
+    SEMB_REQUIRE(view_ok(x) && view_ok(up) && x->C == g->Cin && g->Cout == 4 * up->C, SEMB_EALIGN,
+                 "conv_tc_d2s: bad tensor views (Cout %d must be 4 x %d destination channels)", g->Cout, up->C);
+    SEMB_REQUIRE(g->N > 0 && UH > 0 && UW > 0 && UH <= 2 * g->H && UW <= 2 * g->W && UH >= 2 * g->H - 1 && UW >= 2 * g->W - 1, SEMB_ESHAPE,
+                 "conv_tc_d2s: destination %dx%d does not match 2 x (%dx%d)", UH, UW, g->H, g->W);
+    return conv_tma_launch(g, x, w_packed, bias, up, nullptr, 0, 0, 0, stream, 0, UH, UW);
+}
+
 extern "C" int semb_conv2d_fwd_tc_f32(const semb_conv_geom* g, const semb_tensor* x3, const void* w_packed, const float* bias,
                                       const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                                       int32_t accumulate, void* stream) {

@@ -320,6 +320,7 @@ __global__ void __launch_bounds__(TM_THREADS, PAIR ? 1 : 2) conv_tma_kernel(cons
             }
             if (a.stats && cur_n >= 0) flush_regs(a.stats_nstride != 0 ? cur_n : 0);
         } else {
+            const int d2s_q0 = a.d2s_c ? c_begin / a.d2s_c : 0, d2s_c0 = a.d2s_c ? c_begin - d2s_q0 * a.d2s_c : 0;
             for (int ti = PAIR ? 0 : grp, k = 0; ti < ntiles; ti += PAIR ? 1 : 2, ++k, it.next()) {
                 const int buf = PAIR ? grp + 2 * (k % nuse) : ti % nacc;      // this group's buffers: grp, grp + 2
                 const uint32_t acc_addr = lane_addr + buf * NC;
@@ -333,11 +334,27 @@ __global__ void __launch_bounds__(TM_THREADS, PAIR ? 1 : 2) conv_tma_kernel(cons
                 float* ypf = reinterpret_cast<float*>(a.y) + ((size_t)(it.n * a.OH + (pvalid ? oy : 0)) * a.OW + (pvalid ? ox : 0)) * a.y_pitch + a.y_coff;
                 mbar_wait_warp(full_u32, fpar);
                 tc_fence_after();
+                int dq = d2s_q0, dc = d2s_c0;                 // depth-to-space: quadrant and channel inside it of group g
                 for (int g = 0; g < NC / 8; ++g) {
                     const int c = c_begin + g * 8;
                     float v[8];
                     tmem_ld8(acc_addr + g * 8, v);
                     const bool cvalid = c < a.Cout;
+                    if (a.d2s_c) {
+                        // Conv2DTranspose(2x2, s2): channel group (quadrant dq, channels dc..dc+7) of pixel (oy, ox) is pixel
+                        // (2 oy + dq/2, 2 ox + dq%2) of the up-sampled tensor; the C-long bias is added here (no separate pass)
+                        const int uy = 2 * oy + (dq >> 1), ux = 2 * ox + (dq & 1);
+                        if (pvalid && cvalid && uy < a.d2s_h && ux < a.d2s_w) {
+                            if (a.bias) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] += a.bias[dc + i];
+                            }
+                            Vec8<bf16>::store(a.y + ((size_t)(it.n * a.d2s_h + uy) * a.d2s_w + ux) * a.y_pitch + a.y_coff + dc, v);
+                        }
+                        dc += 8;
+                        if (dc >= a.d2s_c) { dc -= a.d2s_c; ++dq; }
+                        continue;
+                    }
                     if (a.bias && cvalid) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] += a.bias[c + i];
@@ -391,10 +408,12 @@ static EncodeTiledFn encode_tiled() {
 
 // Called by semb_conv2d_fwd_tc (conv_tc.cu) after argument validation, for SEMB_PAD_ZERO geometries.
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
-                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream, int out_f32) {
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream, int out_f32,
+                    int d2s_h, int d2s_w) {
     TmArgs A{};
     TcArgs& a = A.t;
     a.out_f32 = out_f32;
+    if (d2s_h > 0) { a.d2s_c = y->C; a.d2s_h = d2s_h; a.d2s_w = d2s_w; }
     a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;
     a.R = g->R; a.S = g->S; a.pad_t = g->pad_t; a.pad_l = g->pad_l; a.pad_mode = g->pad_mode;
     a.x = reinterpret_cast<const bf16*>(x->ptr); a.x_pitch = x->pitch; a.x_coff = x->coff;
@@ -497,7 +516,7 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     // NC == 32 in one group would need 64 moment registers per thread (spills under the 92-register cap): the two epilogue
     // groups split the columns instead (CS); wider layers take the generic epilogue
     static const bool cs_on = [] { const char* e = getenv("SEMB_TMA_NO_COLSPLIT"); return !(e && e[0] && e[0] != '0'); }();
-    const bool colsplit = cs_on && a.p.NC == 32 && A.nacc == 4 && !pair;
+    const bool colsplit = cs_on && a.p.NC == 32 && A.nacc == 4 && !pair && !a.d2s_c;
     if (pair) {
         if (g->R == 3) {
             e = cudaFuncSetAttribute(conv_tma_kernel<0, 3, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -506,7 +525,7 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
             e = cudaFuncSetAttribute(conv_tma_kernel<0, 1, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = launch_pdl(conv_tma_kernel<0, 1, 0, false, true>, grid, dim3(TM_THREADS), smem, as_stream(stream), A, xmap);
         }
-    } else if (a.p.NC == 16 || colsplit) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
+    } else if ((a.p.NC == 16 && !a.d2s_c) || colsplit) { SEMB_TM_LAUNCH(16) } else { SEMB_TM_LAUNCH(0) }
 #undef SEMB_TM_LAUNCH
 #undef SEMB_TM_LAUNCH2
 #undef SEMB_TM_LAUNCH3

@@ -193,6 +193,9 @@ struct TcArgs {
     int stages, b_resident, a_bytes, b_bytes, stage_bytes;
     int dbg;      // SEMB_TC_DEBUG ablation bits (profiling only): 1 no A loads, 2 no MMAs, 4 no stores, 8 no moments
     int out_f32;  // y is an fp32 tensor (parity mode: bf16 x 3 split operands, fp32 results); y_pitch / y_coff count floats
+    // depth-to-space epilogue (Conv2DTranspose 2x2 stride 2 as a 1x1 conv with 4*C outputs): d2s_c = C > 0 stores output channel
+    // (2r+s)*C + c of pixel (y, x) at pixel (2y+r, 2x+s), channel c of a (N, d2s_h, d2s_w) tensor; bias is C long
+    int d2s_c, d2s_h, d2s_w;
 };
 
 // Walks the tiles t = first + i*stride of an (N, tiles_y, tiles_x) grid without integer divisions in the loop.
@@ -233,7 +236,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // conv_tma.cu: TMA-staged variant of the forward / data-gradient conv for zero-padded geometries
 int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias, const semb_tensor* y,
-                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream, int out_f32 = 0);
+                    void* stats, int32_t stats_nstride, int32_t stats_cstride, int32_t accumulate, void* stream, int out_f32 = 0,
+                    int d2s_h = 0, int d2s_w = 0);
 
 // wgrad_tma.cu: TMA-staged weight gradient of the zero-padded 3x3 layers
 int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_tensor* dy, float* dw, void* workspace, void* stream);

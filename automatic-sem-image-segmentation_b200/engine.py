@@ -664,6 +664,7 @@ class ConvOp(Op):
         self.geom = L.ConvGeom(n, h, wd, oh, ow, cin, cout, k, k, stride, pad_tl[0], pad_tl[1], pad_mode, eng.dtype)
         self.stats = stats  # (zeroed-store name, offset, nstride, cstride)
         self.acc_x = 0
+        self.d2s_up = None  # set by ShuffleOp: (destination view, bias name, UH, UW) of a fused depth-to-space epilogue
         self.use_tc = (eng.tc_enabled and not transposed and stride == 1 and k in (1, 3))
         self.pad_buf = None
         if pad_mode == L.PAD_REFLECT and x.requires_grad and not transposed:
@@ -908,6 +909,12 @@ class ConvOp(Op):
                                         g.pad_t, g.pad_l, 0, e.dtype, 0, e.stream))
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom_v), C.byref(xp.t), self.pk_fwd["buf"].data_ptr(), bias,
                                              C.byref(self.y.t), sp, ns, cs, 0, e.stream))
+            return
+        if self.use_tc and self.d2s_up is not None:
+            # Conv2DTranspose(2x2, s2): the conv's epilogue scatters straight into the up-sampled tensor and adds the bias
+            up, up_bias, uh, uw = self.d2s_up
+            L.check(e.lib.semb_conv2d_fwd_tc_d2s(C.byref(self.geom), C.byref(self.x.t), self.pk_fwd["buf"].data_ptr(),
+                                                 e.params.ptr(up_bias) if up_bias else None, C.byref(up.t), uh, uw, e.stream))
             return
         if self.use_tc:
             L.check(e.lib.semb_conv2d_fwd_tc(C.byref(self.geom), C.byref(self.x.t), self.pk_fwd["buf"].data_ptr(), bias,
@@ -1309,8 +1316,15 @@ class PadCropOp(Op):
 class ShuffleOp(Op):
     """Depth-to-space half of Conv2DTranspose(2x2, stride 2): y4 (N,H,W,4C) -> out (N,2H,2W,C) + bias."""
 
-    def __init__(self, eng: Engine, y4: View, out: View, h: int, w: int, bias: Optional[str]):
+    def __init__(self, eng: Engine, y4: View, out: View, h: int, w: int, bias: Optional[str], conv: Optional["ConvOp"] = None):
         self.eng, self.y4, self.out, self.h, self.w, self.bias = eng, y4, out, h, w, bias
+        # bf16 tensor-core mode: the producing 1x1 conv scatters into `out` itself (semb_conv2d_fwd_tc_d2s); this op then
+        # only exists for the backward pass (gather of d(out) into d(y4), bias gradient)
+        self.fused_fwd = (conv is not None and conv.use_tc and conv.stats is None and conv.bias is None and conv.x_pad is None
+                          and conv.split is None and conv.s2d is None and conv.tapfold is None and conv.geom.R == 1
+                          and _os.environ.get("SEMB_NO_D2S_FUSE") is None)
+        if self.fused_fwd:
+            conv.d2s_up = (out, bias, 2 * h, 2 * w)
 
     def plan_backward(self):
         acc = plan_grad_write(self.y4)
@@ -1318,6 +1332,8 @@ class ShuffleOp(Op):
 
     def fwd(self, training: bool):
         e = self.eng
+        if self.fused_fwd:
+            return
         L.check(e.lib.semb_pixel_shuffle2(C.byref(self.y4.t), C.byref(self.out.t), e.N, self.h, self.w,
                                           e.params.ptr(self.bias) if self.bias else None, 0, e.dtype, e.stream))
 

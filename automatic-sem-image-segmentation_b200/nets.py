@@ -331,8 +331,9 @@ class UNetBuilder:
         kcat = self.kg.layer("concatenate", [kct, skip.klayer])
         up_view = skip_buf.view(0, lay.phys)
         y4 = e.new_buf(x.h, x.w, 4 * co_p, name + "_y4")
-        e.add_op(ConvOp(e, x.view, y4.view(), (x.h, x.w), (x.h, x.w), wname, None, 1, 1, (0, 0), L.PAD_ZERO, False))
-        e.add_op(ShuffleOp(e, y4.view(), up_view, x.h, x.w, bname))
+        ct = ConvOp(e, x.view, y4.view(), (x.h, x.w), (x.h, x.w), wname, None, 1, 1, (0, 0), L.PAD_ZERO, False)
+        e.add_op(ct)
+        e.add_op(ShuffleOp(e, y4.view(), up_view, x.h, x.w, bname, conv=ct))
         e.join_next(getattr(skip, "lane", 0))       # the next op (the decoder block's first conv) reads the res_path's output
         return T(skip_buf.view(), 2 * x.h, 2 * x.w, Layout.concat(lay, skip.layout), kcat)
 

@@ -133,6 +133,14 @@ int semb_conv2d_fwd_tc(const semb_conv_geom* g, const semb_tensor* x, const void
                        const semb_tensor* y, void* stats, int32_t stats_nstride, int32_t stats_cstride,
                        int32_t accumulate, void* stream);
 
+/* Conv2DTranspose(2x2, stride 2, bias) forward (UNet_Segmentation.py:542-551) in ONE launch: the 1x1 tensor-core conv with
+ * g->Cout = 4*C virtual outputs (channel (2r+s)*C + c, packed like any 1x1 kernel) whose epilogue stores pixel (y, x),
+ * quadrant (r, s) at pixel (2y+r, 2x+s) of `up` = the (N, UH, UW, C) destination view (a channel slice of the skip-concat
+ * buffer; UH in {2H-1, 2H}) and adds the C-long bias -- the depth-to-space pass semb_pixel_shuffle2 and the 4C-channel
+ * intermediate are gone from the forward pass.  No moments, no accumulate. */
+int semb_conv2d_fwd_tc_d2s(const semb_conv_geom* g, const semb_tensor* x, const void* w_packed, const float* bias,
+                           const semb_tensor* up, int32_t UH, int32_t UW, void* stream);
+
 /* Weight gradient of the same layers on tcgen05: D[co][ci] per tap, K = output pixels (split over CTAs), both
  * operands read as MN-major UMMA operands from the NHWC channel-group planes; accumulates (+=) into the fp32
  * HWIO gradient with coalesced reductions.  Same contract as semb_conv2d_wgrad without dbias. */

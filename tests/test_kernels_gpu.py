@@ -608,6 +608,55 @@ def test_conv_tc_fwd_and_dgrad(case):
     assert U.rel_err(dxd[..., :cin].float().cpu() - 1.0, xr.grad) < 2e-2
 
 
+@pytest.mark.parametrize("case", [
+    (2, 16, 16, 56, 32),        # resident weights, one N chunk of 128 = the four quadrants
+    (2, 16, 8, 24, 40),         # quadrant boundaries (40, 80, 120) inside one N chunk of 160
+    (1, 16, 24, 216, 128),      # streamed weights (two-tiles-per-chunk mode), four N chunks = one quadrant each
+    (2, 8, 16, 432, 256),       # eight N chunks, two per quadrant
+    (1, 20, 12, 51, 13),        # logical channel counts that are not multiples of 8; partial tiles
+])
+def test_conv_transpose_2x2_fused_depth_to_space(case):
+    """Conv2DTranspose(2x2, stride 2, bias) (UNet_Segmentation.py:542-551) as ONE tensor-core launch: 1x1 conv with 4*C virtual
+    outputs whose epilogue scatters into a channel slice of the (N, 2H, 2W) skip-concat buffer and adds the bias; against
+    oracle.layers.conv2d_transpose on bf16-rounded operands, and bit-identical to nothing else: the neighbouring channels of
+    the destination buffer must stay untouched."""
+    n, h, w_, cin, co = case
+    lib = L.load()
+    g = torch.Generator().manual_seed(41)
+    x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
+    wk = U.bf16_round(torch.randn(2, 2, co, cin, generator=g) * 0.1)          # Keras Conv2DTranspose kernel (kh, kw, Cout, Cin)
+    bias = torch.randn(co, generator=g)
+    y_ref = OL.conv2d_transpose(x, wk, bias, 2)                               # (n, 2h, 2w, co)
+    cpi, cpo = U.pad8(cin), U.pad8(co)
+    wphys = torch.zeros(1, 1, cpi, 4 * cpo)
+    for r in range(2):
+        for s_ in range(2):
+            wphys[0, 0, :cin, (2 * r + s_) * cpo:(2 * r + s_) * cpo + co] = wk[r, s_].T
+    xd = U.to_dev(x, "bf16", pitch=cpi + 8, coff=8)
+    geom = L.ConvGeom(n, h, w_, h, w_, cpi, 4 * cpo, 1, 1, 1, 0, 0, L.PAD_ZERO, L.BF16)
+    nbytes = lib.semb_pack_weights_tc(None, 1, 1, cpi, 4 * cpo, 0, None, None)
+    wp = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device="cuda")
+    wd = wphys.cuda().contiguous()
+    assert lib.semb_pack_weights_tc(wd.data_ptr(), 1, 1, cpi, 4 * cpo, 0, wp.data_ptr(), U.stream()) == nbytes
+    up = torch.full((n, 2 * h, 2 * w_, cpo + 24), 7.0, dtype=torch.bfloat16, device="cuda")     # destination = channels [16, 16 + cpo)
+    bd = U.pad_v(bias)
+    xv, uv = U.view(xd, 8, cpi), U.view(up, 16, cpo)
+    L.check(lib.semb_conv2d_fwd_tc_d2s(C.byref(geom), C.byref(xv), wp.data_ptr(), bd.data_ptr(), C.byref(uv), 2 * h, 2 * w_, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(up[..., 16:16 + co], y_ref) < 1e-2
+    assert float((up[..., :16].float() - 7.0).abs().max()) == 0 and float((up[..., 16 + cpo:].float() - 7.0).abs().max()) == 0
+    if cpo > co:
+        assert float(up[..., 16 + co:16 + cpo].float().abs().max()) == 0       # padded channels: zero weights + zero bias
+    # the unfused pair (1x1 conv -> semb_pixel_shuffle2 with bias) agrees to bf16 rounding of the intermediate
+    y4 = torch.zeros((n, h, w_, 4 * cpo), dtype=torch.bfloat16, device="cuda")
+    up2 = torch.zeros((n, 2 * h, 2 * w_, cpo), dtype=torch.bfloat16, device="cuda")
+    y4v, up2v = U.view(y4), U.view(up2)
+    L.check(lib.semb_conv2d_fwd_tc(C.byref(geom), C.byref(xv), wp.data_ptr(), None, C.byref(y4v), None, 0, 0, 0, U.stream()))
+    L.check(lib.semb_pixel_shuffle2(C.byref(y4v), C.byref(up2v), n, h, w_, bd.data_ptr(), 0, L.BF16, U.stream()))
+    torch.cuda.synchronize()
+    assert U.rel_err(up[..., 16:16 + cpo], up2.float().cpu()) < 1e-2
+
+
 @pytest.mark.parametrize("case", [(3, 32, 24, 8, 16, 3), (2, 16, 16, 64, 24, 3), (2, 16, 16, 144, 216, 3), (3, 16, 8, 56, 32, 1)])
 def test_conv_tc_per_sample_moments(case):
     """InstanceNorm statistics (one moment pair per sample) from the conv epilogue: register-moment and generic paths,
