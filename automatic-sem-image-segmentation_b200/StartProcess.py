@@ -23,6 +23,10 @@ TILE_SIZE_H = 384
 RUN_INFERENCE_ON_WHOLE_IMAGE = True
 USE_GPUS_NO = (0,)
 ALLOW_MEMORY_GROWTH = True
+INPUT_DIR_MASKS = os.path.join(ROOT_DIR, "Input_Masks")
+WGAN_BATCH_SIZE = 64
+WGAN_EPOCHS = 1000
+MAX_PARTICLE_OVERLAP = 0.5
 CYCLEGAN_BATCH_SIZE = 5
 CYCLEGAN_EPOCHS = 50
 CYCLEGAN_USE_SKIPS = False
@@ -45,8 +49,14 @@ def start_step_0():
 
 
 def start_step_1():
-    raise NotImplementedError("Step 1 (WGAN-GP training, WassersteinGAN.py:181-238) is outside this package: its gradient penalty "
-                              "needs a double backward through the convolutions (SURVEY.md 8f N2); run it with the reference")
+    """StartProcess.py:61-68: train the WGAN-GP on the single-particle masks in Input_Masks."""
+    from . import WassersteinGAN
+    print('Step 1: Training WGAN...')
+    wgan = WassersteinGAN.WGAN(root_dir=ROOT_DIR, allow_memory_growth=ALLOW_MEMORY_GROWTH, use_gpus_no=USE_GPUS_NO)
+    wgan.batch_size = WGAN_BATCH_SIZE
+    wgan.epochs = WGAN_EPOCHS
+    wgan.n_z = 128
+    return wgan.start_training()
 
 
 def start_step_2():

@@ -91,6 +91,8 @@ SIGNATURES = {
     "semb_split_weights": (C.c_int, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "semb_conv2d_fwd_tc_f32": (C.c_int, [_GP, _TP, _P, _P, _TP, _P, _I, _I, _I, _P]),
     "semb_conv2d_fwd_tc_d2s": (C.c_int, [_GP, _TP, _P, _P, _TP, _I, _I, _P]),
+    "semb_mask_mul": (C.c_int, [_TP, _TP, _TP, _TP, C.c_int64, C.c_float, _I, _I, _P]),
+    "semb_gp_direction": (C.c_int, [_TP, _TP, _I, C.c_int64, C.c_float, _P, _I, _P]),
     "semb_tile_gather": (C.c_int, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _I, _P]),
     "semb_tile_stitch": (C.c_int, [_P, _I, _I, _P, _I, _I, _P, _I, _P, _I, _I, _P]),
     "semb_upsample2x": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _P]),

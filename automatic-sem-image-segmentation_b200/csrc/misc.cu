@@ -391,6 +391,80 @@ __global__ void upsample2x_kernel(PView small, PView big, int N, int H, int W, i
     }
 }
 
+// ---- LeakyReLU x Dropout as one multiplicative mask (WGAN-GP critic, WassersteinGAN.py:547-621) -----------------------------
+// y (+)= x * slope(z) * m with slope(z) = 1 for z > 0 else `neg` (z == NULL: 1) and m the dropout keep mask already scaled by
+// 1/(1-rate) (m == NULL: 1).  With x = z it is LeakyReLU(z) * m (forward); with x = dy it is the gradient; with x = u it is
+// the critic LINEARISED at z (the gradient-penalty tower: dP/dW = backprop of <grad_x D, u> through the same masks).
+template <typename T>
+__global__ void mask_mul_kernel(PView x, PView z, PView m, PView y, long long npix, int C8, float neg, int has_z, int has_m, int acc) {
+    pdl_trigger();
+    pdl_wait();
+    const long long total = npix * C8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8) * 8;
+        const size_t p = (size_t)(i / C8);
+        float v[8], t[8];
+        Vec8<T>::load(at<T>(x, p, c), v);
+        if (has_z) {
+            Vec8<T>::load(at<T>(z, p, c), t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] *= t[k] > 0.f ? 1.f : neg;
+        }
+        if (has_m) {
+            Vec8<T>::load(at<T>(m, p, c), t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] *= t[k];
+        }
+        if (acc) {
+            Vec8<T>::load(at<T>(y, p, c), t);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += t[k];
+        }
+        Vec8<T>::store(at<T>(y, p, c), v);
+    }
+}
+
+// ---- gradient penalty of WGAN-GP (WassersteinGAN.py:88-121): one block per sample ------------------------------------------
+// g = d(critic)/d(x_hat) (N, HW pixels, C channels);  norm_n = sqrt(sum g_n^2);  sums[0] += (norm_n - 1)^2, sums[1] += norm_n;
+// u_n = scale * (norm_n - 1) / norm_n * g_n  = d(scale/2 * sum_n (norm_n - 1)^2) / d g_n   (scale = 2 * gp_weight / N).
+template <typename T>
+__global__ void __launch_bounds__(256) gp_direction_kernel(PView g, PView u, long long HW, int C8, float scale, float* __restrict__ sums) {
+    __shared__ float red[8];
+    __shared__ float s_coef;
+    const int n = blockIdx.x;
+    const long long total = HW * C8;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        float v[8];
+        Vec8<T>::load(at<T>(g, (size_t)(n * HW + i / C8), (int)(i % C8) * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(v[k], v[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        const float norm = sqrtf(t);
+        atomicAdd(sums, (norm - 1.f) * (norm - 1.f));
+        atomicAdd(sums + 1, norm);
+        s_coef = norm > 0.f ? scale * (norm - 1.f) / norm : 0.f;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        float v[8];
+        const size_t p = (size_t)(n * HW + i / C8);
+        const int c = (int)(i % C8) * 8;
+        Vec8<T>::load(at<T>(g, p, c), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= coef;
+        Vec8<T>::store(at<T>(u, p, c), v);
+    }
+}
+
 // Stride-2 convolutions on the stride-1 tensor-core kernels: a k x k (k = 3, 4) stride-2 conv over X equals a 2x2 stride-1
 // conv over the space-to-depth image X' (H/2, W/2, 4C), embedded here in a 3x3 kernel (taps with r2 = 2 or s2 = 2 are zero):
 //   w3[r2][s2][(2dy+dx)*Cin + ci][co] = w[2 r2 + dy - pt][2 s2 + dx - pl][ci][co]   (0 outside the k x k kernel)
@@ -802,6 +876,28 @@ extern "C" int semb_upsample2x(const semb_tensor* small, const semb_tensor* big,
     if (dtype == SEMB_BF16) upsample2x_kernel<bf16><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, C8, dir, acc);
     else upsample2x_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>(pv(small), pv(big), N, H, W, C8, dir, acc);
     return check_launch("upsample2x");
+}
+
+extern "C" int semb_mask_mul(const semb_tensor* x, const semb_tensor* z, const semb_tensor* m, const semb_tensor* y, int64_t n_pixels,
+                             float negative_slope, int32_t accumulate, int32_t dtype, void* stream) {
+    SEMB_REQUIRE(view_ok(x) && view_ok(y) && x->C == y->C && n_pixels > 0 && (!z || (view_ok(z) && z->C == x->C)) &&
+                 (!m || (view_ok(m) && m->C == x->C)), SEMB_ESHAPE, "mask_mul: bad arguments");
+    const int C8 = x->C / 8;
+    const PView zv = z ? pv(z) : pv(x), mv = m ? pv(m) : pv(x);
+    if (dtype == SEMB_BF16) launch_pdl(mask_mul_kernel<bf16>, dim3(grid_for(n_pixels * C8)), dim3(256), 0, as_stream(stream), pv(x), zv, mv, pv(y),
+                                       (long long)n_pixels, C8, negative_slope, z ? 1 : 0, m ? 1 : 0, accumulate);
+    else launch_pdl(mask_mul_kernel<float>, dim3(grid_for(n_pixels * C8)), dim3(256), 0, as_stream(stream), pv(x), zv, mv, pv(y),
+                    (long long)n_pixels, C8, negative_slope, z ? 1 : 0, m ? 1 : 0, accumulate);
+    return check_launch("mask_mul");
+}
+
+extern "C" int semb_gp_direction(const semb_tensor* g, const semb_tensor* u, int32_t N, int64_t HW, float scale, float* sums, int32_t dtype,
+                                 void* stream) {
+    SEMB_REQUIRE(view_ok(g) && view_ok(u) && g->C == u->C && N > 0 && HW > 0 && sums, SEMB_ESHAPE, "gp_direction: bad arguments");
+    const int C8 = g->C / 8;
+    if (dtype == SEMB_BF16) gp_direction_kernel<bf16><<<N, 256, 0, as_stream(stream)>>>(pv(g), pv(u), (long long)HW, C8, scale, sums);
+    else gp_direction_kernel<float><<<N, 256, 0, as_stream(stream)>>>(pv(g), pv(u), (long long)HW, C8, scale, sums);
+    return check_launch("gp_direction");
 }
 
 extern "C" int semb_merge_weights(float* wa, float* ws, int32_t Cin, int32_t Ca, int32_t Cs, float* w3, int32_t dir, void* stream) {

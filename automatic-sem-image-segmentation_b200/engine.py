@@ -102,6 +102,28 @@ class Buf:
     def view(self, coff: int = 0, c: Optional[int] = None, layout: Optional[Layout] = None) -> View:
         return View(self, coff, self.pitch - coff if c is None else c, layout)
 
+    def alias(self, n: int, h: int, w: int, pitch: int, name: str) -> "Buf":
+        """The same storage (values AND gradient) seen with another NHWC shape: keras Flatten / Reshape of a dense NHWC tensor
+        (WassersteinGAN.py:617,657).  All gradient writers must go through ONE of the two objects (the plans are per object)."""
+        assert n * h * w * pitch == self.data.numel(), (self.name, (n, h, w, pitch), tuple(self.data.shape))
+        return _AliasBuf(self, n, h, w, pitch, name)
+
+
+class _AliasBuf(Buf):
+    def __init__(self, base: Buf, n: int, h: int, w: int, pitch: int, name: str):
+        self.eng, self.N, self.H, self.W, self.pitch, self.name = base.eng, n, h, w, pitch, name
+        self.base = base
+        self.requires_grad = base.requires_grad
+        self.data = base.data.view(n, h, w, pitch)
+        self._grad = None
+        self.grad_cover = []
+        self.force_acc = False
+
+    def grad_tensor(self) -> torch.Tensor:
+        if self._grad is None:
+            self._grad = self.base.grad_tensor().view(self.N, self.H, self.W, self.pitch)
+        return self._grad
+
 
 class FlatStore:
     """Named fp32 slices of one flat device tensor (parameters, optimizer state, scratch)."""
@@ -1365,6 +1387,55 @@ class UpsampleOp(Op):
             return
         e = self.eng
         L.check(e.lib.semb_upsample2x(C.byref(self.x.g), C.byref(self.y.g), self.n, self.h, self.w, 1, self.acc, e.dtype, e.stream))
+
+
+class MaskOp(Op):
+    """y = x * slope(z) * m: LeakyReLU and/or inverted Dropout as ONE multiplicative mask (semb_mask_mul; WassersteinGAN.py
+    conv_block :547-567, Dropout :618).  z = the pre-activation whose sign selects slope 1 / `neg` (None: no activation),
+    m = the keep mask in `drop` (values 0 or 1/(1-rate); None: no dropout).  `like` = another MaskOp whose z and m this op
+    re-uses: the critic linearised at that tower's operating point (the gradient-penalty tower).
+
+    The keep mask is drawn by torch's device generator (random bits, not arithmetic of the path); `frozen=True` keeps the
+    current content of `drop` (parity tests feed the oracle the same masks); training=False makes Dropout the identity."""
+
+    def __init__(self, eng: Engine, x: View, y: View, npix: int, z: Optional[View] = None, rate: float = 0.0, neg: float = 0.2,
+                 like: Optional["MaskOp"] = None, n: Optional[int] = None):
+        self.eng, self.x, self.y, self.npix, self.neg, self.like = eng, x, y, npix, float(neg), like
+        self.z = like.z if like is not None else z
+        self.rate = like.rate if like is not None else float(rate)
+        self.drop = None
+        if like is not None:
+            self.drop = like.drop
+        elif self.rate > 0:
+            self.drop = eng.new_buf(x.buf.H, x.buf.W, x.C, f"dropmask_{len(eng.ops)}", requires_grad=False, n=x.buf.N)
+        self.frozen = False
+        self.acc_x = 0
+        self._training = True
+
+    def plan_backward(self):
+        if self.x.requires_grad:
+            self.acc_x = plan_grad_write(self.x)
+
+    def _m(self):
+        return C.byref(self.drop.view().t) if (self.drop is not None and self._training) else None
+
+    def fwd(self, training: bool):
+        e = self.eng
+        self._training = training
+        if self.like is None and self.drop is not None and training and not self.frozen:
+            d = self.drop.data
+            d.copy_((torch.rand(d.shape, device=d.device) >= self.rate).to(d.dtype) * (1.0 / (1.0 - self.rate)))
+        elif self.like is not None:
+            self._training = self.like._training
+        L.check(e.lib.semb_mask_mul(C.byref(self.x.t), C.byref(self.z.t) if self.z is not None else None, self._m(), C.byref(self.y.t),
+                                    self.npix, self.neg, 0, e.dtype, e.stream))
+
+    def bwd(self):
+        e = self.eng
+        if not self.x.requires_grad:
+            return
+        L.check(e.lib.semb_mask_mul(C.byref(self.y.g), C.byref(self.z.t) if self.z is not None else None, self._m(), C.byref(self.x.g),
+                                    self.npix, self.neg, self.acc_x, e.dtype, e.stream))
 
 
 class NoiseOp(Op):

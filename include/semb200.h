@@ -339,6 +339,20 @@ int semb_pixel_shuffle2(const semb_tensor* src, const semb_tensor* dst, int32_t 
 int semb_upsample2x(const semb_tensor* small, const semb_tensor* big, int32_t N, int32_t H, int32_t W, int32_t dir,
                     int32_t accumulate, int32_t dtype, void* stream);
 
+/* ---- WGAN-GP (WassersteinGAN.py) ------------------------------------------------------------------------
+ * semb_mask_mul: y (+)= x * slope(z) * m over n_pixels pixels of C channels; slope(z) = 1 where z > 0 else negative_slope
+ *   (z == NULL: 1), m = dropout keep mask already scaled by 1/(1-rate) (m == NULL: 1).  x = z: LeakyReLU(0.2) followed by
+ *   Dropout (conv_block :547-567) in one pass; x = dy: its gradient; x = u: the critic linearised at z, which is what the
+ *   gradient penalty's second-order term needs (dP/dW = backprop of <grad_x D(x_hat), dP/dgrad> through the SAME masks, since
+ *   LeakyReLU and Dropout are piecewise linear -- the double backward of gradient_penalty :88-121 without a second-order graph).
+ * semb_gp_direction: g = grad_x D(x_hat) (N samples x HW pixels x C channels).  Per sample norm = ||g_n||_2;
+ *   sums[0] += (norm-1)^2, sums[1] += norm;  u_n = scale * (norm-1)/norm * g_n  (scale = 2*gp_weight/N gives
+ *   u = d(gp_weight * mean_n (norm_n-1)^2)/dg). */
+int semb_mask_mul(const semb_tensor* x, const semb_tensor* z, const semb_tensor* m, const semb_tensor* y, int64_t n_pixels,
+                  float negative_slope, int32_t accumulate, int32_t dtype, void* stream);
+int semb_gp_direction(const semb_tensor* g, const semb_tensor* u, int32_t N, int64_t HW, float scale, float* sums, int32_t dtype,
+                      void* stream);
+
 /* ---- parity mode on the tensor cores (fp32 storage, split bf16 operands) ----------------------------------------------
  * north_star: "within 1e-3 relative fp32 (bit-exact for the argmax mask)" for an implicit GEMM on tcgen05.  An fp32 value
  * is x = xh + xm + xl (three bf16 terms, exact to 2^-24); x*w ~ xh*wh + xh*wm + xm*wh + xh*wl + xl*wh + xm*wm keeps every

@@ -285,7 +285,7 @@ def test_workflow_steps_0_and_5_and_step_functions(tmp_path):
     for name in ("start_step_0", "start_step_1", "start_step_2", "start_step_3", "start_step_4", "start_step_5", "start_step_6a", "start_step_6b"):
         assert callable(getattr(SP, name))
     with pytest.raises(NotImplementedError):
-        SP.start_step_1()
+        SP.start_step_2()            # mask simulation (opensimplex): still the reference's job; step 1 (WGAN-GP) is tests/test_wgan_gpu.py
 
 
 def test_res_path_units_merge_into_pair_convs_only_in_bf16_mode(monkeypatch):
