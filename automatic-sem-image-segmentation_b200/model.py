@@ -107,6 +107,11 @@ class _TrainIO:
         self.x_stage, self.y_stage = [mk(), mk()], [mk(), mk()]
         self.x_pin, self.y_pin = [None, None], [None, None]
         self.copy_stream = torch.cuda.Stream(device=dev)
+        # The staging buffers above were allocated and zero-filled on the CURRENT stream.  The first upload must not overtake
+        # those fills: on a busy main stream the H2D copy on the copy stream used to land first and was then zeroed -- the
+        # first train_step of an instance intermittently saw an all-zero batch (found by tests/test_dp_gpu.py on a GPU shared
+        # by two processes; every later step was ordered by ev_free).
+        self.copy_stream.wait_stream(torch.cuda.current_stream(dev))
         self.ev_h2d = [torch.cuda.Event(), torch.cuda.Event()]
         self.ev_free = [torch.cuda.Event(), torch.cuda.Event()]
         self.sums_pin = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(self.RING)]

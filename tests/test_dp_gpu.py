@@ -4,6 +4,10 @@ gradient buffer -> Adam with 1/world folded in).  torch.distributed runs over gl
 device; gloo all-reduces CUDA tensors through the host), so the collective call sites, buffer and scaling are the
 product's, only the transport differs from the 8-GPU runs.
 
+(This test found a real race: the first upload of a training instance ran on the copy stream before the zero fill of its
+freshly allocated staging buffers had executed on the main stream -- an all-zero first batch, once in three runs on a GPU
+shared by two processes; see model._TrainIO.)
+
 Checked on rank 0: (1) rank 1's weights equal rank 0's after the broadcast although they were initialised differently,
 (2) the engine's gradient buffer after the step is the SUM of the two ranks' local gradients (each recomputed by a
 world_size-1 replica on the same half batch), (3) both ranks hold identical weights after Adam, and they equal a
@@ -55,8 +59,25 @@ def _worker(rank, world, port, ret):
         torch.cuda.synchronize()
         e = m.engine
         bcast_err = float((e.params.t - w_before).abs().max())          # (1) rank 0's weights everywhere
+        seen = {}
+        orig_allreduce = m._allreduce
+
+        def spy(eng):                                                   # the engine's LOCAL gradient right before the collective
+            seen["local"] = eng.grads.detach().clone()
+            orig_allreduce(eng)
+
+        m._allreduce = spy
         logs = m.train_step(xs, ys)
         torch.cuda.synchronize()
+        local_err = float((seen["local"] - g_local).abs().max() / g_local.abs().max())
+        if local_err > 1e-4:                                            # which tensors differ (diagnostics for the assertion message)
+            bad = []
+            for name, (o, cnt) in e.params.entries.items():
+                a, b = seen["local"][o:o + cnt], g_local[o:o + cnt]
+                d = float((a - b).abs().max())
+                if d > 1e-6 * float(g_local.abs().max()):
+                    bad.append((name, float(a.abs().max()), float(b.abs().max()), d))
+            ret[f"bad{rank}"] = bad[:12] + [("count", len(bad), len(e.params.entries), 0.0)]
         g_sum = g_local.clone()
         dist.all_reduce(g_sum)                                          # reference: sum of the two local gradients
         grad_err = float((e.grads - g_sum).abs().max() / g_sum.abs().max())
@@ -73,12 +94,14 @@ def _worker(rank, world, port, ret):
         if rank == 0:
             ret["bcast_err"] = bcast_err
             ret["grad_err"] = grad_err
+            ret["local_err"] = local_err
             ret["adam_err"] = adam_err
             ret["rank_diff"] = float((w_all[0] - w_all[1]).abs().max())
             ret["moved"] = float((w_after - w_before).abs().max())
             ret["loss"] = float(logs["loss"])
         else:
             ret["bcast_err1"] = bcast_err
+            ret["local_err1"] = local_err
     finally:
         dist.destroy_process_group()
 
@@ -88,6 +111,7 @@ def test_two_ranks_on_one_gpu_run_the_engine_dp_path():
     port = 29500 + (os.getpid() * 7) % 2000
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret["bcast_err"] == 0.0 and ret["bcast_err1"] == 0.0, dict(ret)
+    assert ret["local_err"] < 1e-4 and ret["local_err1"] < 1e-4, dict(ret)
     assert ret["grad_err"] < 1e-4, dict(ret)          # fp32 atomics order inside one rank's backward: run-to-run noise only
     assert ret["rank_diff"] == 0.0, dict(ret)
     assert ret["adam_err"] < 1e-6 and ret["moved"] > 1e-4, dict(ret)
