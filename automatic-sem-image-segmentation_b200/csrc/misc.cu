@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) gp_direction_kernel(PView g, PView u, lon
     }
 }
 
-// Stride-2 convolutions on the stride-1 tensor-core kernels: a k x k (k = 3, 4) stride-2 conv over X equals a 2x2 stride-1
+// Stride-2 convolutions on the stride-1 tensor-core kernels: a k x k (k = 3, 4; 5 with leading pad 1: a full 3x3) stride-2 conv over X equals a 2x2 stride-1
 // conv over the space-to-depth image X' (H/2, W/2, 4C), embedded here in a 3x3 kernel (taps with r2 = 2 or s2 = 2 are zero):
 //   w3[r2][s2][(2dy+dx)*Cin + ci][co] = w[2 r2 + dy - pt][2 s2 + dx - pl][ci][co]   (0 outside the k x k kernel)
 // with pt, pl in {0, 1} the leading padding.  dir 0 writes w3 from the master weights, dir 1 ADDS the gradient of w3
@@ -480,7 +480,9 @@ __global__ void s2d_weights_kernel(float* __restrict__ w, int k, int pt, int pl,
         const int q = kk / Cin, ci = kk - q * Cin;
         const int r2 = tap / 3, s2 = tap - 3 * r2;
         const int r = 2 * r2 + (q >> 1) - pt, s_ = 2 * s2 + (q & 1) - pl;
-        const bool valid = r2 < 2 && s2 < 2 && r >= 0 && r < k && s_ >= 0 && s_ < k;
+        // k = 3, 4 fill a 2x2 corner of the 3x3 kernel (r < k cuts the rest); k = 5 with a leading pad of 1 (Keras 'same' on even
+        // sizes: input rows 2y-1 .. 2y+3 = row pairs y-1, y, y+1) fills all nine positions
+        const bool valid = r >= 0 && r < k && s_ >= 0 && s_ < k;
         if (dir == 0) w3[i] = valid ? w[((size_t)(r * k + s_) * Cin + ci) * Cout + co] : 0.f;
         else if (valid) w[((size_t)(r * k + s_) * Cin + ci) * Cout + co] += w3[i];      // the map valid (tap, kk) -> (r, s, ci) is injective
     }
@@ -909,7 +911,7 @@ extern "C" int semb_merge_weights(float* wa, float* ws, int32_t Cin, int32_t Ca,
 
 extern "C" int semb_s2d_weights(float* w, int32_t k, int32_t pad_t, int32_t pad_l, int32_t Cin, int32_t Cout, float* w3, int32_t dir,
                                 void* stream) {
-    SEMB_REQUIRE(w && w3 && (k == 3 || k == 4) && (pad_t == 0 || pad_t == 1) && (pad_l == 0 || pad_l == 1) && Cin > 0 && Cout > 0 &&
+    SEMB_REQUIRE(w && w3 && (k == 3 || k == 4 || (k == 5 && pad_t == 1 && pad_l == 1)) && (pad_t == 0 || pad_t == 1) && (pad_l == 0 || pad_l == 1) && Cin > 0 && Cout > 0 &&
                  (dir == 0 || dir == 1), SEMB_ESHAPE, "s2d_weights: bad arguments");
     const long long total = 9LL * 4 * Cin * Cout;
     s2d_weights_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(w, k, pad_t, pad_l, Cin, Cout, w3, dir);

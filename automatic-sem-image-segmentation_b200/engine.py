@@ -699,7 +699,9 @@ class ConvOp(Op):
         # Stride-2 3x3 / 4x4 convs (CycleGAN down / up-sampling, PatchGAN): 3x3-embedded 2x2 stride-1 conv over the
         # space-to-depth image of the big tensor, on the TMA / tcgen05 kernels (2.25x the FLOPs, but ~30x the CUDA-core rate).
         self.s2d = None
-        if (eng.tc_enabled and stride == 2 and k in (3, 4) and pad_mode == L.PAD_ZERO and pad_tl[0] in (0, 1) and pad_tl[1] in (0, 1)
+        # (k = 5 with a leading pad of 1 -- Keras 'same' on even sizes, the WGAN critic's convs -- fills the whole 3x3 kernel)
+        if (eng.tc_enabled and stride == 2 and (k in (3, 4) or (k == 5 and tuple(pad_tl) == (1, 1) and not transposed))
+                and pad_mode == L.PAD_ZERO and pad_tl[0] in (0, 1) and pad_tl[1] in (0, 1)
                 and not (transposed and bias is not None and stats is not None) and _os.environ.get("SEMB_NO_S2D") is None):
             pt, pl = pad_tl
             h2, w2 = (h + 1) // 2, (wd + 1) // 2

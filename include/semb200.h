@@ -155,7 +155,8 @@ int semb_conv2d_wgrad_tc_ws(const semb_conv_geom* g, const semb_tensor* x, const
                             int64_t workspace_bytes, void* stream);
 
 /* ---- stride-2 convolutions on the stride-1 tensor-core kernels (space-to-depth) ------------------------------
- * A k x k (k = 3, 4) stride-2 Conv2D / Conv2DTranspose (CycleGAN.py:339-358, 425-451) is run as a 3x3-embedded 2x2
+ * A k x k (k = 3, 4; also the 5x5 'same' convs of the WGAN critic, WassersteinGAN.py:571-614, with pad_t = pad_l = 1, which fill the
+ * whole 3x3) stride-2 Conv2D / Conv2DTranspose (CycleGAN.py:339-358, 425-451) is run as a 3x3-embedded 2x2
  * stride-1 conv over the space-to-depth image (H/2, W/2, 4C): semb_pixel_shuffle2x moves activations between the two
  * domains (DH x DW is the true size of the full-resolution tensor, 2H-1 <= DH <= 2H: a missing last row / column reads
  * as zero and is not written; acc = 1 accumulates in dir 0), semb_s2d_weights builds the virtual fp32 HWIO kernel

@@ -809,6 +809,8 @@ S2D_CASES = [
     (1, 30, 22, 8, 16, 4, (0, 0), False),       # PatchGAN: 4x4 s2 valid
     (2, 31, 27, 13, 8, 4, (0, 0), False),       # odd input size (127 -> 62 in the real discriminator), padded channel lanes
     (2, 16, 16, 24, 16, 3, (1, 1), True),       # generator upsample: Conv2DTranspose 3x3 s2 'same'
+    (2, 32, 32, 1, 64, 5, (1, 1), False),       # WGAN critic (WassersteinGAN.py:571-580): 5x5 s2 'same' on an even size, one input channel
+    (2, 16, 24, 64, 40, 5, (1, 1), False),      # 5x5 s2 'same': all nine positions of the virtual 3x3 kernel are populated
 ]
 
 
@@ -823,12 +825,12 @@ def test_strided_conv_space_to_depth(case):
     g = torch.Generator().manual_seed(17)
     cpi, cpo = U.pad8(cin), U.pad8(cout)
     if not transposed:
-        oh, ow = (h + 1) // 2 if k == 3 else (h - 4) // 2 + 1, (w_ + 1) // 2 if k == 3 else (w_ - 4) // 2 + 1
+        oh, ow = (h + 1) // 2 if k != 4 else (h - 4) // 2 + 1, (w_ + 1) // 2 if k != 4 else (w_ - 4) // 2 + 1
         x = U.bf16_round(torch.randn(n, h, w_, cin, generator=g))
         wt = U.bf16_round(torch.randn(k, k, cin, cout, generator=g) * 0.1)          # Keras HWIO
         xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
         # the oracle's Keras rules (oracle/layers.py: asymmetric 'same' padding for stride 2)
-        y_ref = OL.conv2d(xr, wr, None, 2, "same" if k == 3 else "valid")
+        y_ref = OL.conv2d(xr, wr, None, 2, "same" if k != 4 else "valid")
         assert tuple(y_ref.shape[1:3]) == (oh, ow)
         in_hw, out_hw, lw, pw = (h, w_), (oh, ow), (k, k, cin, cout), (k, k, cpi, cpo)
         maps = {2: np.arange(cin), 3: np.arange(cout)}
