@@ -645,11 +645,12 @@ def run_cyclegan(args):
     # ---- per-op profile of one eager step (CUDA events around every op of all twelve towers)
     engines = [bb.e for bb in (m.GA_ra, m.GB_rb, m.GB_fb, m.GA_fa, m.GB_ra, m.GA_rb, m.DA_fa, m.DB_fb, m.DA_real, m.DA_pool, m.DB_real, m.DB_pool)]
     recs, restore = instrument(engines)
-    saved = m.use_cuda_graph
+    saved, saved_world = m.use_cuda_graph, m.world_size
     m.use_cuda_graph = False
+    m.world_size = 1           # rank 0 profiles alone: the other ranks have left, a collective here would wait for them forever
     m.step_device()
     torch.cuda.synchronize()
-    m.use_cuda_graph = saved
+    m.use_cuda_graph, m.world_size = saved, saved_world
     restore()
     rows = cg_rows(recs, args.dtype)
     table, total_ms = kernel_table(rows, peaks)
