@@ -380,7 +380,8 @@ extern "C" int semb_conv2d_wgrad_tc(const semb_conv_geom* g, const semb_tensor* 
     SEMB_REQUIRE(g->stride == 1 && ((g->R == 1 && g->S == 1) || (g->R == 3 && g->S == 3)), SEMB_ESHAPE,
                  "wgrad_tc: stride-1 1x1 / 3x3 only (got %dx%d stride %d)", g->R, g->S, g->stride);
     SEMB_REQUIRE(view_ok(x) && view_ok(dy) && x->C == g->Cin && dy->C == g->Cout, SEMB_EALIGN, "wgrad_tc: bad tensor views");
-    if (g->R == 3 && g->pad_mode == SEMB_PAD_ZERO && g->pad_t <= 2 && g->pad_l <= 2 && !getenv("SEMB_WGRAD_NO_TMA"))
+    static const bool no_tma = getenv("SEMB_WGRAD_NO_TMA") != nullptr;
+    if (g->R == 3 && g->pad_mode == SEMB_PAD_ZERO && g->pad_t <= 2 && g->pad_l <= 2 && !no_tma)
         return wgrad_tma_launch(g, x, dy, dw, nullptr, stream);
     WgArgs a{};
     a.N = g->N; a.H = g->H; a.W = g->W; a.OH = g->OH; a.OW = g->OW; a.Cin = g->Cin; a.Cout = g->Cout;

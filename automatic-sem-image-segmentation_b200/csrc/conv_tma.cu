@@ -451,7 +451,13 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
         nst = 2;
         while (nst < TM_MAX_STAGES && (size_t)(nst + 1) * a.stage_bytes + fixed <= 200 * 1024) ++nst;
     }
-    if (const char* env = getenv("SEMB_TMA_STAGES")) { const int v = atoi(env); if (v >= 2 && v <= TM_MAX_STAGES) nst = v; }
+    // tuning / ablation knobs, read once per process (scripts/ablate_conv.sh, scripts/sweep_stage.sh)
+    struct Knobs { int stages, nacc, dbg, per_sm; };
+    static const Knobs knobs = [] {
+        auto num = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : 0; };
+        return Knobs{num("SEMB_TMA_STAGES"), num("SEMB_TMA_NACC"), num("SEMB_TC_DEBUG"), num("SEMB_TC_PER_SM")};
+    }();
+    if (knobs.stages >= 2 && knobs.stages <= TM_MAX_STAGES) nst = knobs.stages;
     A.nmma = (pair || nst >= 4) ? 2 : 1;
     if (A.nmma == 2 && !pair) nst &= ~1;    // two half-rings, one per MMA warp
     A.nstages = nst;
@@ -466,7 +472,7 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     const size_t smem = (size_t)nst * a.stage_bytes + fixed;
     SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "conv_tma: %zu bytes of shared memory needed", smem);
     A.nacc = (a.p.NC <= 64 || pair) ? 4 : 2;
-    if (const char* env = getenv("SEMB_TMA_NACC")) { const int v = atoi(env); if (v == 2 || (v == 4 && a.p.NC <= 128)) A.nacc = v; }
+    if (knobs.nacc == 2 || (knobs.nacc == 4 && a.p.NC <= 128)) A.nacc = knobs.nacc;
     const int need = A.nacc * a.p.NC;
     const int ks_fixed = a.p.kchunks == 1 ? (g->Cin + 15) / 16 : 0;
     const int cols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
@@ -474,8 +480,8 @@ int conv_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const void* w
     int per_sm = 512 / cols;                                  // TMEM columns
     if ((size_t)per_sm * (smem + 2048) > 220 * 1024) per_sm = (int)(220 * 1024 / (smem + 2048));   // shared memory
     if (per_sm > 2) per_sm = 2;                               // registers: 352 threads x <= 93
-    if (const char* env = getenv("SEMB_TC_DEBUG")) a.dbg = atoi(env);
-    if (const char* env = getenv("SEMB_TC_PER_SM")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
+    a.dbg = knobs.dbg;
+    if (knobs.per_sm >= 1 && knobs.per_sm < per_sm) per_sm = knobs.per_sm;
     if (per_sm < 1) per_sm = 1;
     int gx = 148 * per_sm;
     if (gx > a.total_tiles) gx = a.total_tiles;

@@ -279,7 +279,8 @@ int wgrad_tma_launch(const semb_conv_geom* g, const semb_tensor* x, const semb_t
     const size_t slack = 16 * WT_PLANE_A + 128;                        // garbage-row reads of the last stage + alignment
     int nst = 2;
     while (nst < WT_MAX_STAGES && (size_t)(nst + 1) * a.stage_bytes + slack <= 104 * 1024) ++nst;
-    if (const char* env = getenv("SEMB_WGRAD_STAGES")) { const int v = atoi(env); if (v >= 2 && v <= WT_MAX_STAGES) nst = v; }
+    static const int want_stages = [] { const char* e = getenv("SEMB_WGRAD_STAGES"); return e ? atoi(e) : 0; }();
+    if (want_stages >= 2 && want_stages <= WT_MAX_STAGES) nst = want_stages;
     a.nstages = nst;
     const size_t smem = (size_t)nst * a.stage_bytes + slack;
     SEMB_REQUIRE(smem <= 220 * 1024, SEMB_EWORKSPACE, "wgrad_tma: %zu bytes of shared memory needed", smem);
