@@ -1,11 +1,10 @@
 """Drop-in for Releases/Version 1.2.0/StartProcess.py: same constants, same step functions, one spawned process per step
 (:178-221; state travels between steps through the 1_WGAN / 2_CycleGAN / 3_UNet tree only).
 
-Steps 3, 4, 6a, 6b are the conv-stack hot path (CycleGAN training / inference, MultiRes-UNet training / inference) on the
-sm_100a engine.  Steps 0 and 5 are host-side file handling and classical post-processing, restated in HelperFunctions /
-Measurements.  Steps 1 and 2 (WGAN-GP training on single-particle masks and the Perlin-noise mask simulation,
-WassersteinGAN.py) are NOT part of this package (double-backward through convs, opensimplex): they raise
-with that reason; run them with the reference and point ROOT_DIR at the same tree (2_CycleGAN/data/trainB).
+Steps 1, 3, 4, 6a, 6b run networks on the sm_100a engine (WGAN-GP training, CycleGAN training / inference, MultiRes-UNet
+training / inference).  Steps 0, 2 and 5 are host-side work around them (file handling, mask synthesis from the WGAN's
+generator with simplex-noise clustering, classical post-processing), restated in HelperFunctions / WassersteinGAN /
+Measurements.
 """
 import os
 from datetime import datetime
@@ -60,8 +59,16 @@ def start_step_1():
 
 
 def start_step_2():
-    raise NotImplementedError("Step 2 (mask simulation, WassersteinGAN.py:375-540) is outside this package (needs the WGAN of step 1 "
-                              "and opensimplex); run it with the reference, it fills 2_CycleGAN/data/trainB")
+    """StartProcess.py:71-87: simulate the fake masks (2_CycleGAN/data/trainB) with the WGAN trained in step 1."""
+    from . import WassersteinGAN
+    print('Step 2: Simulating fake masks...')
+    num_masks = max(NUM_SIMULATED_MASKS, len(os.listdir(os.path.join(ROOT_DIR, '2_CycleGAN', 'data', 'trainA'))))
+    w_gan = WassersteinGAN.WGAN(root_dir=ROOT_DIR, allow_memory_growth=ALLOW_MEMORY_GROWTH, use_gpus_no=USE_GPUS_NO)
+    w_gan.n_z = 128
+    w_gan.simulate_masks(no_of_images=num_masks, min_no_of_particles=100, max_no_of_particles=150, use_perlin_noise=True,
+                         perlin_noise_threshold=0.5, perlin_noise_frequency=4, use_normal_distribution=True,
+                         use_random_rotation='DISABLE', grid_type='DISABLE', max_overlap=MAX_PARTICLE_OVERLAP,
+                         img_width=TILE_SIZE_W, img_height=TILE_SIZE_H)
 
 
 def _cycle_gan():

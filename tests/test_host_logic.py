@@ -1,7 +1,9 @@
 """Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol, channel layouts,
 parameter packing, Keras weight ordering, tiling / stitching, the no-CPU-fallback guarantee."""
 import ctypes
+import math
 import os
+import random
 import re
 
 import numpy as np
@@ -284,8 +286,6 @@ def test_workflow_steps_0_and_5_and_step_functions(tmp_path):
     assert o[75, 100] == 255 and o[165, 25] == 0
     for name in ("start_step_0", "start_step_1", "start_step_2", "start_step_3", "start_step_4", "start_step_5", "start_step_6a", "start_step_6b"):
         assert callable(getattr(SP, name))
-    with pytest.raises(NotImplementedError):
-        SP.start_step_2()            # mask simulation (opensimplex): still the reference's job; step 1 (WGAN-GP) is tests/test_wgan_gpu.py
 
 
 def test_res_path_units_merge_into_pair_convs_only_in_bf16_mode(monkeypatch):
@@ -341,3 +341,64 @@ def test_res_path_lanes_are_planned_around_their_producers_and_consumers():
     # ops that share a gradient buffer keep their planned relative order: the lane's first conv writes d(m_k) before the pool adds to it
     main = [op for op in order if op.lane == 0]
     assert main == [op for op in reversed(e.ops) if op.lane == 0]
+
+
+def test_simplex_noise_and_mask_grid_helpers():
+    """Host pieces of WGAN.simulate_masks (WassersteinGAN.py:375-545): the restated 2-D OpenSimplex noise is deterministic per
+    seed, smooth and inside [-1, 1]; the jittered hexagonal grid offsets odd rows by half a cell and keeps the reference's unfilled
+    trailing slots at the origin."""
+    from sem_b200 import simplex_noise as sn
+    from sem_b200.WassersteinGAN import WGAN
+    sn.seed(7)
+    x, y = np.arange(0, 4, 4 / 300), np.arange(0, 4, 4 / 200)
+    a = sn.noise2array(x, y)
+    assert a.shape == (200, 300) and -1.0 <= a.min() < -0.3 and 0.3 < a.max() <= 1.0
+    assert np.abs(np.diff(a, axis=0)).max() < 0.05 and np.abs(np.diff(a, axis=1)).max() < 0.05        # continuous
+    sn.seed(7)
+    assert np.array_equal(a, sn.noise2array(x, y))
+    sn.seed(8)
+    assert np.abs(a - sn.noise2array(x, y)).max() > 0.1
+    assert abs(float(sn.noise2array(np.array([0.0]), np.array([0.0]))[0, 0])) < 1e-12                  # lattice points carry zero noise
+    np.random.seed(0)
+    px, py = WGAN._grid_positions('HEXAGONAL', 200, 100, 8.0, 8.0, 1, 1)
+    assert px.size == py.size == math.ceil(100 / 8) * math.ceil(200 / 8) + 1 and px.min() >= 0 and px.max() <= 200 and py.max() <= 100
+    rows = {}
+    for xx, yy in zip(px, py):
+        rows.setdefault(int(round(yy / 8)), []).append(int(xx))
+    assert np.median(np.asarray(sorted(rows[1])) % 8) in (3, 4, 5)               # odd rows: shifted by half of the 8-pixel cell (+- jitter 1)
+    cx, cy = WGAN._grid_positions('CUBIC', 64, 64, 8.0, 8.0, 1, 1)
+    assert cx.size == 64
+
+
+def test_simulate_masks_places_separated_particles(tmp_path):
+    """WGAN.simulate_masks (WassersteinGAN.py:375-545) with the generator replaced by discs: hexagonal grid + noise clustering +
+    overlap limit (the default path), and the free-position path with noise-driven rotation and normally distributed sizes."""
+    from PIL import Image
+    from scipy import ndimage
+    from sem_b200.WassersteinGAN import WGAN
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "Input_Masks"))
+    yy, xx = np.mgrid[0:32, 0:32]
+    disc = ((yy - 16) ** 2 + (xx - 16) ** 2 < 100).astype(np.uint8) * 255
+    Image.fromarray(disc).save(os.path.join(root, "Input_Masks", "p.tif"))
+    wg = WGAN(root_dir=root)
+    assert wg.train_images.shape == (4, 32, 32, 1)
+    wg.model = object()                                            # never called: the particles come from the stub below
+    wg._generate_particles = lambda count: np.repeat(disc[None], count, 0)
+    np.random.seed(1)
+    random.seed(1)
+    wg.simulate_masks(no_of_images=2, img_width=128, img_height=96)
+    files = sorted(os.listdir(wg.generate_dir))
+    assert files == ["00000.tif", "00001.tif"] and sorted(os.listdir(os.path.join(root, "2_CycleGAN", "data", "testB"))) == files
+    for f in files:
+        m = np.array(Image.open(os.path.join(wg.generate_dir, f)))
+        assert m.shape == (96, 128) and set(np.unique(m)) <= {0, 255} and 0.02 < (m > 0).mean() < 0.9
+        lab, n = ndimage.label(m > 0)
+        sizes = ndimage.sum(m > 0, lab, range(1, n + 1))
+        # an eroded disc of radius 10 has ~200 pixels; overlap <= 1 % keeps the particles apart (clipped ones at the border are smaller)
+        assert n >= 3 and sizes.max() < 2.2 * 210
+    wg.generate_dir = os.path.join(root, "free")
+    wg.simulate_masks(no_of_images=1, min_no_of_particles=20, max_no_of_particles=30, use_normal_distribution=True, max_overlap=None,
+                      use_random_rotation='PERLIN', img_width=96, img_height=96)
+    m = np.array(Image.open(os.path.join(root, "free", "00000.tif")))
+    assert m.shape == (96, 96) and (m > 0).any()
