@@ -155,5 +155,5 @@ def run_steps(steps):
 
 if __name__ == "__main__":
     print("Process started: " + str(datetime.now()))
-    run_steps((start_step_0, start_step_3, start_step_4, start_step_5, start_step_6a, start_step_6b))
+    run_steps((start_step_0, start_step_1, start_step_2, start_step_3, start_step_4, start_step_5, start_step_6a, start_step_6b))
     print("Process finished: " + str(datetime.now()))
