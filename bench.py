@@ -677,7 +677,7 @@ def run_cyclegan(args):
           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
           "data": "synthetic",
           "config": {"workload": f"CycleGAN filters={F} {size}x{size}x1 train_step_torch (6 G fwd, 2+4 D fwd, 2 backward phases, 4 Adam), batch {n} per GPU, image pools 50",
-                     "global_batch": n * world, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+                     "global_batch": n * world, "parallelism": f"dp{world}", "cuda_graph": (not args.no_graph) and world == 1,
                      "l2": "per-step working set (activations of 12 towers, several GB) exceeds the 126 MB L2; no explicit flush"},
           "e2e": {"value": e2e_value, "unit": "image pairs/s", "ms_per_step": e2e_ms / args.steps,
                   "h2d_bytes_per_step": int(2 * n * size * size * 4), "d2h_bytes_per_step": 64},
