@@ -894,9 +894,15 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const AffArgs p) {
 
 static int pick_ppb(int HW, int N, int C) {
     const int rows = 256 / (C / 8);
-    long long target_blocks = 148LL * 12;
+    // Per-sample (InstanceNorm) grids are cut into ~148 * 3 blocks of at least 8 block iterations each.  Every block derives the
+    // scale / shift of its channels from the fp64 moments before its first pixel (the folded finalize), so short blocks are
+    // prologue-bound: measured on the CycleGAN step [B200] 148 * 12 blocks x >= 4 iterations 10.6 ms of affine kernels per step,
+    // 148 * 3 x >= 8: 8.0 ms (step 52.6 -> 50.1 ms); 148 * 1 x >= 32: 11.0 ms.  SEMB_AFF_PS="blocks_per_sm,min_iterations" overrides.
+    static const int knob_blocks = [] { const char* e = getenv("SEMB_AFF_PS"); int a = 3, b = 8; if (e) sscanf(e, "%d,%d", &a, &b); return a > 0 ? a : 3; }();
+    static const int knob_iters = [] { const char* e = getenv("SEMB_AFF_PS"); int a = 3, b = 8; if (e) sscanf(e, "%d,%d", &a, &b); return b > 0 ? b : 8; }();
+    long long target_blocks = 148LL * knob_blocks;
     int ppb = (int)cdivl((long long)HW * N, target_blocks);
-    int min_ppb = rows * 4;
+    int min_ppb = rows * knob_iters;
     if (ppb < min_ppb) ppb = min_ppb;
     ppb = cdiv(ppb, rows) * rows;
     return ppb;
@@ -913,8 +919,10 @@ static dim3 aff_grid(AffArgs& p, bool per_sample, int blocks_per_sm) {
         if (total < (1LL << 31)) {
             p.N = 1;
             p.HW = (int)total;
+            // at least 8 block iterations per block (same prologue argument as pick_ppb; 4 -> 8: 11.535 -> 11.52 ms per UNet step)
+            static const int bn_iters = [] { const char* e = getenv("SEMB_AFF_BN_ITERS"); const int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();
             int ppb = (int)cdivl(total, 148LL * blocks_per_sm);
-            if (ppb < rows * 4) ppb = rows * 4;
+            if (ppb < rows * bn_iters) ppb = rows * bn_iters;
             p.ppb = cdiv(ppb, rows) * rows;
             return dim3(cdiv(p.HW, p.ppb), 1);
         }
