@@ -45,7 +45,14 @@ def load_and_preprocess_images(input_dir_or_filelist, threshold_value=None, norm
             if threshold_value is not None:
                 img = (img > threshold_value).astype("float32")
             img = normalization_range[0] + (normalization_range[1] - normalization_range[0]) * img
-        out.append(img)
+        out.append(img.astype("float32"))
+    if len({im.shape for im in out}) > 1:
+        # images of different sizes (the single-particle masks of the WGAN, WassersteinGAN.py:331-352): the numpy of the
+        # reference's era returned an object array here, today's raises -- keep the old contract (an iterable of arrays)
+        arr = np.empty(len(out), dtype=object)
+        for i, im in enumerate(out):
+            arr[i] = im
+        return arr
     return np.array(out, dtype="float32")
 
 

@@ -402,3 +402,38 @@ def test_simulate_masks_places_separated_particles(tmp_path):
                       use_random_rotation='PERLIN', img_width=96, img_height=96)
     m = np.array(Image.open(os.path.join(root, "free", "00000.tif")))
     assert m.shape == (96, 96) and (m > 0).any()
+
+
+def test_wgan_dataset_preparation_and_archive_layout(tmp_path):
+    """WGAN.__init__ (WassersteinGAN.py:288-357) without a device: masks thresholded to {-1, 1}, four flips each, zero-padded
+    (value 0, the middle of the [-1, 1] range -- the reference's choice) to a common size divisible by 16, with the reference's
+    width rule (the running HEIGHT maximum enters the width maximum, :333)."""
+    from PIL import Image
+    from sem_b200.WassersteinGAN import WGAN, GANMonitor
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "Input_Masks"))
+    a = np.zeros((20, 30), np.uint8); a[5:15, 8:22] = 200
+    b = np.zeros((40, 18), np.uint8); b[10:30, 4:14] = 255
+    Image.fromarray(a).save(os.path.join(root, "Input_Masks", "a.tif"))
+    Image.fromarray(b).save(os.path.join(root, "Input_Masks", "b.tif"))
+    wg = WGAN(root_dir=root)
+    # heights 20, 40 -> 48; widths: max(20, 30) = 30, then max(40, 18) = 40 (the height leaks in) -> 48
+    assert wg.train_images.shape == (8, 48, 48, 1) and wg.train_images.dtype == np.float32
+    assert set(np.unique(wg.train_images)) == {-1.0, 0.0, 1.0}
+    first = wg.train_images[0, :, :, 0]
+    top, left = (48 - 20) // 2, (48 - 30) // 2
+    assert np.array_equal(first[top:top + 20, left:left + 30] > 0, a > 127) and float(np.abs(first[:top]).max()) == 0.0
+    assert np.array_equal(wg.train_images[1, :, :, 0][top:top + 20, left:left + 30], np.fliplr(first[top:top + 20, left:left + 30]))
+    assert (wg.batch_size, wg.epochs, wg.n_z) == (64, 1000, 128)
+    assert wg.generate_dir.endswith(os.path.join("2_CycleGAN", "data", "trainB")) and wg.model_dir.endswith(os.path.join("1_WGAN", "Models"))
+    assert WGAN.discriminator_loss(np.array([1.0, 3.0]), np.array([0.0, 1.0])) == -1.5 and WGAN.generator_loss(np.array([2.0, 4.0])) == -3.0
+
+    class _Stub:                                             # GANMonitor only needs `n` and a callable model
+        n = 4
+        def __call__(self, z, training=False):
+            return np.tile(np.linspace(-1, 1, 48, dtype=np.float32)[None, :, None, None], (z.shape[0], 1, 48, 1))
+    mon = GANMonitor(os.path.join(root, "mosaics"), num_img=9, latent_dim=16, output_epochs=20)
+    mon.set_model(_Stub())
+    assert mon.on_epoch_end(1) is None                       # only every 20th epoch
+    sheet = np.array(Image.open(mon.on_epoch_end(20)))
+    assert sheet.shape == (2 * 48, 3 * 48) and sheet[0, 0] == 0 and sheet[47, 0] == 255
