@@ -1,4 +1,7 @@
 """CPU checks of oracle/wgan.py (WassersteinGAN.py restated) and of the identity the CUDA path's gradient penalty rests on."""
+import json
+import os
+
 import numpy as np
 import torch
 
@@ -112,3 +115,41 @@ def test_engine_builders_create_the_oracle_variables_in_keras_order():
             want += [(base + "/moving_mean", tuple(shape)), (base + "/moving_variance", tuple(shape))]
     assert [(n, tuple(e3.specs[n].logical_shape)) for n in g.creation_names] == want
     assert g.out_hw == (64, 64) and c.feat == 4 * 4 * 512
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wgan_step_known_answers.json")
+
+
+def _known_answers():
+    tr, real, zs, alphas, masks = _setup(seed=0)
+    logs = tr.train_step(real, zs, alphas, masks)
+    out = {k: float(v) for k, v in logs.items()}
+    out["critic_grad_l2"] = {k: float(v.norm()) for k, v in tr.last_grads["critic"].items()}
+    out["generator_grad_l2"] = {k: float(v.norm()) for k, v in tr.last_grads["generator"].items()}
+    out["fake_mean_abs"] = float(tr.last_fake.abs().mean())
+    return out
+
+
+def test_seeded_train_step_reproduces_the_committed_known_answers():
+    """Pins oracle/wgan.py against silent changes: metrics and per-tensor gradient norms of one seeded train step (32x32, batch 4,
+    latent 16; generated by `PYTHONPATH=. python tests/test_oracle_wgan.py --regen` with this very oracle -- a regression pin, not a reference
+    vector: the reference cannot run here)."""
+    want = json.load(open(GOLDEN))
+    got = _known_answers()
+
+    def close(a, b):
+        return abs(a - b) <= 2e-4 * max(1e-3, abs(b))
+
+    for k, v in want.items():
+        if isinstance(v, dict):
+            assert set(v) == set(got[k]) and all(close(got[k][n], v[n]) for n in v), k
+        else:
+            assert close(got[k], v), (k, got[k], v)
+
+
+if __name__ == "__main__":
+    import sys
+    if "--regen" in sys.argv:
+        with open(GOLDEN, "w") as fh:
+            json.dump(_known_answers(), fh, indent=1, sort_keys=True)
+        print("wrote", GOLDEN)
