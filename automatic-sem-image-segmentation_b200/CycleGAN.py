@@ -232,7 +232,8 @@ class CycleGAN:
         if weights_from is not None:
             z = self._read(weights_from)
             named = {k[len(which) + 1:]: v for k, v in z.items() if k.startswith(which + "/")}
-        for i in range(images.shape[0]):
+        from . import dp
+        for i in dp.inference_indices(len(images)):           # every image here; a rank-strided share under torchrun
             img = images[i]
             if which == "gen_a" and self.invert_images:
                 img = img * -1

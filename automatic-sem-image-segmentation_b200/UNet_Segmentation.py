@@ -249,7 +249,8 @@ class UNet:
                                                             contrast_optimization_range=self.contrast_optimization_range)
         names = HelperFunctions.get_image_file_paths_from_directory(files)
         os.makedirs(output_directory, exist_ok=True)
-        for i in range(images.shape[0]):
+        from . import dp
+        for i in dp.inference_indices(len(images)):           # every image here; a rank-strided share under torchrun
             img = images[i]
             if tile_images:
                 th, tw = self.image_shape[0], self.image_shape[1]

@@ -30,3 +30,17 @@ def broadcast_(flat: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.broadcast(flat, src=src, group=group)
     return flat
+
+
+def inference_indices(n_items: int) -> List[int]:
+    """The items THIS process handles in run_inference: all of them in a single process; under torchrun (RANK / WORLD_SIZE
+    in the environment) a rank-strided slice of the file list -- images are independent, every rank writes its own output
+    files, there is no collective.  Unlike shard_indices the tail is not dropped: rank r gets r, r+W, r+2W, ..."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1") or 1)
+    rank = int(os.environ.get("RANK", "0") or 0)
+    if dist.is_initialized():
+        world, rank = dist.get_world_size(), dist.get_rank()
+    if world <= 1:
+        return list(range(n_items))
+    return list(range(rank, n_items, world))

@@ -55,3 +55,18 @@ def test_two_rank_gradients_equal_single_rank():
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret["idx"] == [0, 2]
     assert ret["err"] < 1e-5, ret["err"]
+
+
+def test_inference_work_list_is_rank_strided(monkeypatch):
+    """run_inference shards the file list by rank under torchrun (no collective) and keeps every file in a
+    single process."""
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    assert dp.inference_indices(5) == [0, 1, 2, 3, 4]
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    got = []
+    for r in range(4):
+        monkeypatch.setenv("RANK", str(r))
+        got.append(dp.inference_indices(10))
+    assert got == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    assert sorted(i for g in got for i in g) == list(range(10))
