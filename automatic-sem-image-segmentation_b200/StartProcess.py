@@ -153,7 +153,12 @@ def run_steps(steps):
             print(f"{step.__name__} exited with code {p.exitcode}")
 
 
-if __name__ == "__main__":
+def main():
+    """The reference's `__main__` (:178-221): all eight steps, one spawned process each."""
     print("Process started: " + str(datetime.now()))
     run_steps((start_step_0, start_step_1, start_step_2, start_step_3, start_step_4, start_step_5, start_step_6a, start_step_6b))
     print("Process finished: " + str(datetime.now()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,4 @@
-"""Builds libsemb200.so (sm_100a only) in-tree with nvcc.  Run: python -m sem_b200.build"""
+"""Builds libsemb200.so (sm_100a only) in-tree with nvcc.  Run: python __graft_entry__.py (or sem_b200.build.build())."""
 from __future__ import annotations
 
 import hashlib
