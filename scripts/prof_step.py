@@ -6,12 +6,13 @@ WARM un-profiled steps first (lazy gradient-buffer allocation and its fill kerne
 profiled steps."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import sem_b200
 from sem_b200 import UNetModel, _lib
-from oracle import unet as OU
+from _inputs import synthetic_batch          # (scripts/ does not import oracle/)
 n = int(os.environ.get("BATCH", "32"))
-x, y, wgt = OU.synthetic_batch(n, 256, 256)
+x, y, wgt = synthetic_batch(n, 256, 256)
 m = UNetModel((256, 256, 1), 16, dtype="bf16", batch_size=n, use_cuda_graph=False)
 m.compile(weighting=wgt)
 for i in range(int(os.environ.get("WARM", "1"))):

@@ -6,10 +6,11 @@ so every duration is the kernel's own (only the programmatic-dependent-launch pr
 """
 import argparse, collections, json, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import sem_b200
-from oracle import unet as OU
+from _inputs import synthetic_batch          # (scripts/ does not import oracle/)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default="gpurun_out/kernels.json")
@@ -18,7 +19,7 @@ ap.add_argument("--size", type=int, default=256)
 args = ap.parse_args()
 
 from sem_b200 import UNetModel
-x, y, wgt = OU.synthetic_batch(args.batch, args.size, args.size)
+x, y, wgt = synthetic_batch(args.batch, args.size, args.size)
 m = UNetModel((args.size, args.size, 1), 16, dtype="bf16", batch_size=args.batch)
 m.compile(weighting=wgt)
 xp, yp = x.pin_memory(), y.pin_memory()

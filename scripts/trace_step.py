@@ -5,10 +5,11 @@ of the weight-gradient stream, and how large the gaps between dependent kernels 
 """
 import argparse, collections, json, os, random, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 from torch.profiler import profile, ProfilerActivity
 import sem_b200
-from oracle import unet as OU
+from _inputs import synthetic_batch          # (scripts/ does not import oracle/)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="unet")
@@ -18,7 +19,7 @@ args = ap.parse_args()
 
 if args.workload == "unet":
     from sem_b200 import UNetModel
-    x, y, wgt = OU.synthetic_batch(32, 256, 256)
+    x, y, wgt = synthetic_batch(32, 256, 256)
     m = UNetModel((256, 256, 1), 16, dtype="bf16", batch_size=32)
     m.compile(weighting=wgt)
     xp, yp = x.pin_memory(), y.pin_memory()

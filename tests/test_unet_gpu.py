@@ -196,7 +196,7 @@ def test_cuda_graph_step_equals_eager():
     outs = [outs[0], outs[2]]
     # Not bit-identical: the backward reductions (BN sums, split-K weight gradients) use fp32 atomics, and on this
     # tiny problem three Adam steps amplify that rounding noise to ~4e-4 of the loss by the third step -- measured
-    # between two EAGER runs as well as between eager and graph (scripts/debug_graph_eager.py).  What this test pins is
+    # between two EAGER runs as well as between eager and graph (tests/tools/debug_graph_eager.py).  What this test pins is
     # that graph replay computes the same step: identical first loss, trajectories within the run-to-run band.
     for i, (a, b) in enumerate(zip(outs[0][0], outs[1][0])):
         assert abs(a["loss"] - b["loss"]) < (1e-5 if i == 0 else 2e-3) * abs(a["loss"])

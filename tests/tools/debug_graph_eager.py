@@ -1,6 +1,6 @@
 """Loss trajectories of eager vs CUDA-graph training steps (f32 and bf16) under the current env switches."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import sem_b200
 from sem_b200 import UNetModel

@@ -1,6 +1,6 @@
 """Experiment: per-tensor gradient agreement GPU vs oracle at 256x256 batch 32 for random vs real data, bf16 vs f32 storage."""
 import os, sys, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import unet as OU
 from sem_b200 import UNetModel
