@@ -247,6 +247,10 @@ __global__ void __launch_bounds__(TM_THREADS, PAIR ? 1 : 2) conv_tma_kernel(cons
         const int my = m / TILE_W, mx = m % TILE_W;
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
         const int nuse = nacc >> 1;                        // buffers of this group: grp, grp + 2, ...
+        // nacc is 2 or 4 (conv_tma_launch): the per-tile buffer index / phase are masks and shifts -- `ti % nacc` and `k / nuse` by
+        // run-time values were a signed-division sequence per tile in all eight epilogue warps (ncu source page: IABS / I2F lines
+        // among the top stall sites of the issue-bound full-resolution launches)
+        const int amask = nacc - 1, ashift = nacc == 4 ? 2 : 1, umask = nuse - 1, ushift = ashift - 1;
         // (CS and PAIR: both groups visit every (super-)tile of the CTA; otherwise the groups alternate tiles)
         TileIter it((CS || PAIR) ? blockIdx.x : blockIdx.x + grp * gridDim.x, (CS || PAIR) ? gridDim.x : 2 * gridDim.x, a.tiles_x, a.tiles_y);
         if constexpr (NCT > 0) {
@@ -272,10 +276,10 @@ __global__ void __launch_bounds__(TM_THREADS, PAIR ? 1 : 2) conv_tma_kernel(cons
             };
             const int cg0 = CS ? grp * 16 : 0;                  // first channel (of the chunk) this group stores / reduces
             for (int ti = CS ? 0 : grp, k = 0; ti < ntiles; ti += CS ? 1 : 2, ++k, it.next()) {
-                const int buf = ti % nacc;
+                const int buf = ti & amask;
                 const uint32_t acc_addr = lane_addr + buf * NC + cg0;
                 const uint32_t full_u32 = smem_u32(&acc_full[buf]), empty_u32 = smem_u32(&acc_empty[buf]);
-                const uint32_t fpar = CS ? (uint32_t)(ti / nacc) & 1u : (uint32_t)(k / nuse) & 1u;
+                const uint32_t fpar = CS ? (uint32_t)(ti >> ashift) & 1u : (uint32_t)(k >> ushift) & 1u;
                 if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) flush_regs(cur_n);
                 cur_n = it.n;
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TILE_W + mx;
@@ -322,10 +326,10 @@ __global__ void __launch_bounds__(TM_THREADS, PAIR ? 1 : 2) conv_tma_kernel(cons
         } else {
             const int d2s_q0 = a.d2s_c ? c_begin / a.d2s_c : 0, d2s_c0 = a.d2s_c ? c_begin - d2s_q0 * a.d2s_c : 0;
             for (int ti = PAIR ? 0 : grp, k = 0; ti < ntiles; ti += PAIR ? 1 : 2, ++k, it.next()) {
-                const int buf = PAIR ? grp + 2 * (k % nuse) : ti % nacc;      // this group's buffers: grp, grp + 2
+                const int buf = PAIR ? grp + 2 * (k & umask) : ti & amask;    // this group's buffers: grp, grp + 2
                 const uint32_t acc_addr = lane_addr + buf * NC;
                 const uint32_t full_u32 = smem_u32(&acc_full[buf]), empty_u32 = smem_u32(&acc_empty[buf]);
-                const uint32_t fpar = (uint32_t)(k / nuse) & 1u;
+                const uint32_t fpar = (uint32_t)(k >> ushift) & 1u;
                 if (a.stats && a.stats_nstride != 0 && cur_n >= 0 && it.n != cur_n) combine(cur_n);
                 cur_n = it.n;
                 const int oy = it.ty * TILE_H + my, ox = it.tx * TW + (PAIR ? grp * TILE_W : 0) + mx;
