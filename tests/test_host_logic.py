@@ -437,3 +437,18 @@ def test_wgan_dataset_preparation_and_archive_layout(tmp_path):
     assert mon.on_epoch_end(1) is None                       # only every 20th epoch
     sheet = np.array(Image.open(mon.on_epoch_end(20)))
     assert sheet.shape == (2 * 48, 3 * 48) and sheet[0, 0] == 0 and sheet[47, 0] == 255
+
+
+def test_weight_pack_sizes_follow_the_chunk_plan():
+    """semb_pack_weights_tc(dst=NULL) is a host-side size query (no device work): the packed bf16 image is
+    [n-chunk][k-chunk][tap][K chunk][N chunk], and layers whose weights are STREAMED per K chunk are planned with N <= 128
+    (the two-tiles-per-weight-chunk mode of conv_tma.cu, tc_common.cuh::tc_plan)."""
+    lib = L.load()
+    size = lambda k, ci, co, flip=0: lib.semb_pack_weights_tc(None, k, k, ci, co, flip, None, None)
+    assert size(3, 16, 16) == 9 * 16 * 16 * 2                                   # resident, one chunk
+    assert size(3, 8, 32) == 9 * 16 * 32 * 2                                    # K padded to one 16-channel MMA step
+    assert size(3, 512, 512) == 4 * 16 * 9 * 32 * 128 * 2 == 9 * 512 * 512 * 2  # CycleGAN residual conv: 4 N chunks of 128, 16 K chunks of 32
+    assert size(3, 144, 216) == 2 * 5 * 9 * 32 * 112 * 2                        # re-planned from one N chunk of 224 to two of 112
+    assert size(3, 120, 64) == 1 * 4 * 9 * 32 * 64 * 2                          # K chunk sized for the 18 x 18 pair halo (32, not 64)
+    assert size(1, 216, 1024, 0) == 8 * 4 * 64 * 128 * 2 and size(1, 216, 1024, 1) == 2 * 16 * 64 * 112 * 2      # forward / flipped (data gradient)
+    assert lib.semb_pack_weights_tc(None, 5, 5, 16, 16, 0, None, None) < 0      # only 1x1 and 3x3 images exist (5x5 runs via space-to-depth)
