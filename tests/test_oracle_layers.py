@@ -32,6 +32,10 @@ def test_conv_same_valid_and_strided_same():
     assert np.allclose(OL.conv2d(xt, wt, None, 2, "same").numpy(), naive_conv(x, w, 2, 1, 0, 5, 4))
     w4 = rng.standard_normal((4, 4, 3, 2))
     assert np.allclose(OL.conv2d(xt, torch.from_numpy(w4), None, 2, "valid").numpy(), naive_conv(x, w4, 2, 0, 0, 3, 3))
+    # the WGAN critic's 5x5 stride-2 'same' (WassersteinGAN.py:571-614): total pad 3 on even sizes (1 before, 2 after), 4 on odd sizes
+    assert OL.same_pad_amounts(8, 5, 2) == (1, 2) and OL.same_pad_amounts(9, 5, 2) == (2, 2)
+    w5 = rng.standard_normal((5, 5, 3, 2))
+    assert np.allclose(OL.conv2d(xt, torch.from_numpy(w5), None, 2, "same").numpy(), naive_conv(x, w5, 2, 2, 1, 5, 4))
 
 
 def test_conv_transpose_2x2_and_3x3():
